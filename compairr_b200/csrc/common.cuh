@@ -1,0 +1,216 @@
+// common.cuh — data layout and the host/device-shared pieces of the overlap hot path.
+//
+// Everything in here is plain integer arithmetic that both the kernels (kernels.cu) and the
+// host side of the engine (engine.cu: table generation, probe counting) use.  The functions
+// marked CB_HD are also compiled by g++ in tests/ (tests/hd_check.cpp) so that the variant
+// decoding rules can be checked against the oracle without a GPU; that harness is a test of
+// this header, not a product path.
+//
+// Reference semantics restated here (file:line in /root/reference/src):
+//   variant enumeration rules     variants.cc:260-428
+//   exact verification            variants.cc:166-240
+//   score summands                overlap.cc:144-166
+//   Zobrist hash                  zobrist.cc:74-88   (table VALUES are ours)
+//   Bloom filter                  bloompat.h:40-58   (geometry is ours)
+//   hash-table indexing           hashtable.h:36-46
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define CB_HD __host__ __device__ __forceinline__
+#else
+#define CB_HD inline
+#endif
+
+namespace cb {
+
+// ---- device data layout -------------------------------------------------------------------
+
+// One 32-byte record per sequence = exactly one L2/DRAM sector, so a verify touches one sector
+// for all of (offset, length, V, J, repertoire, count) instead of six (reference AoS seqinfo_s,
+// db.cc:77-88, is 56 B).
+struct alignas(32) SeqMeta {
+  uint64_t off;    // first residue in the residue arena
+  uint64_t count;  // duplicate_count
+  uint32_t len;
+  uint32_t v;
+  uint32_t j;
+  uint32_t rep;
+};
+static_assert(sizeof(SeqMeta) == 32, "SeqMeta must be one 32-byte sector");
+
+// Open-addressing slot, probed with one 128-bit load (reference keeps three arrays:
+// hash_values / hash_data / hash_occupied bitmap, hashtable.h:22-29).  "Empty" lives in the
+// index word, so a stored hash may legitimately be any 64-bit value including 0.
+struct alignas(16) Slot {
+  uint64_t hash;
+  uint64_t idx;
+};
+static_assert(sizeof(Slot) == 16, "Slot must be 16 bytes");
+constexpr uint64_t SLOT_EMPTY = ~0ull;
+
+enum VariantKind : uint32_t {  // same numbering as mutation_kind_enum, variants.h:24-31
+  VK_IDENTICAL = 0,
+  VK_SUBSTITUTION = 1,
+  VK_DELETION = 2,
+  VK_INSERTION = 3,
+  VK_SUB_SUB = 4
+};
+
+constexpr int MAXDIFF_HASH = 2;     // compairr.h:113
+constexpr int BLOOM_K_HALF = 3;     // bits set in each 32-bit half of a 64-bit Bloom block
+
+// ---- hashing --------------------------------------------------------------------------------
+
+CB_HD uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// Zobrist value of residue r at position p.  A pure function of (seed, p, r) so the table can be
+// extended to longer sequences without invalidating hashes already computed (the reference draws
+// from glibc random(), zobrist.cc:52-63; results do not depend on the values).
+CB_HD uint64_t zobrist_gen(uint64_t seed, uint32_t p, uint32_t r) {
+  return splitmix64(splitmix64(seed ^ 0x5A0B1157ull) + ((uint64_t)p << 8) + r);
+}
+
+// Contribution of the (V gene, J gene) pair: zobrist_v_base[v] ^ zobrist_d_base[j] in the
+// reference (zobrist.cc:83-84).  Computed, not tabulated, so no table sized by #V + #J.
+CB_HD uint64_t vj_hash(uint64_t seed, uint32_t v, uint32_t j) {
+  return splitmix64(splitmix64(seed ^ 0x7E11C0DEull) ^ (((uint64_t)v << 32) | j));
+}
+
+// Home slot: upper half of the hash (hashtable.h:36-41).
+CB_HD uint64_t table_home(uint64_t h, uint64_t mask) { return (h >> 32) & mask; }
+
+// Bloom: one 64-bit block per key; block chosen by multiply-shift range reduction over bits
+// 30..61 (any block count, not only powers of two), pattern = 3 bits in each 32-bit half taken
+// from the low 30 hash bits.  Normal polarity (1 = present); the reference's is inverted
+// (bloompat.h:50-58), which is an implementation detail.
+CB_HD uint32_t bloom_block(uint64_t h, uint32_t nblocks) {
+  uint32_t x = (uint32_t)(h >> 30);
+#if defined(__CUDA_ARCH__)
+  return __umulhi(x, nblocks);
+#else
+  return (uint32_t)(((uint64_t)x * nblocks) >> 32);
+#endif
+}
+CB_HD uint32_t bloom_pat_lo(uint64_t h) {
+  uint32_t x = (uint32_t)h;
+  return (1u << (x & 31)) | (1u << ((x >> 5) & 31)) | (1u << ((x >> 10) & 31));
+}
+CB_HD uint32_t bloom_pat_hi(uint64_t h) {
+  uint32_t x = (uint32_t)h;
+  return (1u << ((x >> 15) & 31)) | (1u << ((x >> 20) & 31)) | (1u << ((x >> 25) & 31));
+}
+CB_HD uint64_t bloom_pattern(uint64_t h) {
+  return (uint64_t)bloom_pat_lo(h) | ((uint64_t)bloom_pat_hi(h) << 32);
+}
+
+// ---- score summand (overlap.cc:144-166) ---------------------------------------------------------
+
+CB_HD double score_of(int score, bool ignore_counts, uint64_t a, uint64_t b) {
+  if (ignore_counts) return 1.0;
+  switch (score) {
+    case 0:  // product
+    case 5:  // MH uses the sum of products
+      return (double)a * (double)b;
+    case 1:  // ratio
+      return (double)a / (double)b;
+    case 2:  // min
+    case 6:  // Jaccard uses the sum of minima
+      return (double)(a < b ? a : b);
+    case 3:  // max
+      return (double)(a > b ? a : b);
+    default:  // 4: mean
+      return ((double)a + (double)b) / 2;
+  }
+}
+
+// ---- variant index space ------------------------------------------------------------------------
+//
+// For one seed of length L over an alphabet of S residues the engine walks these candidate
+// index spaces (the reference materialises a var_s list, variants.cc:242-258; we never do):
+//
+//   identical      1 candidate                                              variants.cc:260-268
+//   substitution   t in [0,(S-1)L): pos = t/(S-1), r' = t%(S-1),
+//                  new residue r = r' + (r' >= seed[pos])                   variants.cc:280-293
+//   deletion       p in [0,L), emitted iff L > 1 and (p == 0 or
+//                  seed[p] != seed[p-1])   (one per run of equal residues)  variants.cc:301-325
+//   insertion      (p,r) in [0,L] x [0,S), emitted iff p == 0 or
+//                  r != seed[p-1]   (leftmost position of equal results)    variants.cc:329-353
+//   sub_sub        i<j, two substitutions as above                          variants.cc:357-400
+//
+// Every emitted candidate is a distinct variant SEQUENCE of the seed, which is what makes each
+// matching (seed, hit) pair count exactly once.
+
+CB_HD uint32_t sub_residue(uint32_t rprime, uint32_t seed_residue) {
+  return rprime + (rprime >= seed_residue ? 1u : 0u);
+}
+
+// Number of maximal runs of equal residues.
+CB_HD uint32_t count_runs(const uint8_t* s, uint32_t len) {
+  uint32_t runs = 0;
+  for (uint32_t p = 0; p < len; p++)
+    if (p == 0 || s[p] != s[p - 1]) runs++;
+  return runs;
+}
+
+// Closed-form variant count = what generate_variants() emits (variants.cc:402-428).
+CB_HD uint64_t probe_count(const uint8_t* s, uint32_t len, uint32_t sigma, int d, bool indels) {
+  uint64_t L = len, S = sigma;
+  uint64_t n = 1;
+  if (d >= 1) {
+    n += (S - 1) * L;
+    if (indels) {
+      if (L > 1) n += count_runs(s, len);
+      n += S * (L + 1) - L;
+    }
+  }
+  if (d >= 2) n += (S - 1) * (S - 1) * (L * (L - 1) / 2);
+  return n;
+}
+
+// Exact verification: is `hit` exactly the seed with THIS edit applied? (check_variant,
+// variants.cc:166-240).  Verifying the specific edit, not just "distance <= d", is what rejects
+// a hash collision between two different variants of one seed and keeps the once-only count.
+CB_HD bool verify_variant(const uint8_t* seed, uint32_t slen, const uint8_t* hit, uint32_t hlen,
+                          uint32_t kind, uint32_t pos1, uint32_t r1, uint32_t pos2, uint32_t r2) {
+  switch (kind) {
+    case VK_IDENTICAL:
+      if (hlen != slen) return false;
+      for (uint32_t p = 0; p < slen; p++)
+        if (seed[p] != hit[p]) return false;
+      return true;
+    case VK_SUBSTITUTION:
+      if (hlen != slen || hit[pos1] != r1) return false;
+      for (uint32_t p = 0; p < slen; p++)
+        if (p != pos1 && seed[p] != hit[p]) return false;
+      return true;
+    case VK_DELETION:
+      if (hlen + 1 != slen) return false;
+      for (uint32_t p = 0; p < pos1; p++)
+        if (seed[p] != hit[p]) return false;
+      for (uint32_t p = pos1; p < hlen; p++)
+        if (seed[p + 1] != hit[p]) return false;
+      return true;
+    case VK_INSERTION:
+      if (hlen != slen + 1 || hit[pos1] != r1) return false;
+      for (uint32_t p = 0; p < pos1; p++)
+        if (seed[p] != hit[p]) return false;
+      for (uint32_t p = pos1; p < slen; p++)
+        if (seed[p] != hit[p + 1]) return false;
+      return true;
+    case VK_SUB_SUB:
+      if (hlen != slen || hit[pos1] != r1 || hit[pos2] != r2) return false;
+      for (uint32_t p = 0; p < slen; p++)
+        if (p != pos1 && p != pos2 && seed[p] != hit[p]) return false;
+      return true;
+    default:
+      return false;
+  }
+}
+
+}  // namespace cb

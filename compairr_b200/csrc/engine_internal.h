@@ -1,0 +1,76 @@
+// engine_internal.h — context and device-set structs shared by engine.cu and brute.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/compairr_b200.h"
+#include "kernels.cuh"
+
+struct cb_dset {
+  uint64_t n = 0;
+  uint64_t index_base = 0;
+  uint64_t res_bytes = 0;
+  uint32_t n_reps = 0;
+  uint32_t longest = 0;
+  cb::SeqMeta* d_meta = nullptr;
+  uint8_t* d_res = nullptr;
+  uint64_t* d_hash = nullptr;
+  // d >= 3 only (set B): bucket order by (length[, V, J]), packed words, host bucket directory
+  uint32_t* d_order = nullptr;
+  uint32_t* d_packed = nullptr;
+  std::vector<uint64_t> bucket_key;    // sorted unique keys
+  std::vector<uint64_t> bucket_start;  // n_buckets + 1 positions into d_order
+  std::vector<uint64_t> pack_off;      // n_buckets + 1 word offsets into d_packed
+};
+
+struct cb_ctx {
+  cb_config cfg{};
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8]{};
+  std::string err;
+
+  uint64_t* d_ztab = nullptr;
+  uint32_t zrows = 0;
+
+  unsigned long long* d_counters = nullptr;
+  unsigned long long* h_counters = nullptr;  // pinned
+
+  cb_dset* b = nullptr;
+  bool b_owned = false;
+  cb::Slot* d_table = nullptr;
+  uint64_t slots = 0;
+  unsigned long long* d_bloom = nullptr;
+  uint32_t bloom_blocks = 0;
+  uint64_t dups_b = 0;
+
+  double* d_matrix = nullptr;
+  uint64_t rows = 0, cols = 0;
+
+  cb::PairOut* d_pairs = nullptr;
+  uint64_t pairs_cap = 0;
+  std::vector<cb_pair> pending;
+
+  cb_stats stats{};
+};
+
+int cb_fail(cb_ctx* c, int code, const char* fmt, ...);
+cb::DeviceSetView cb_view_of(const cb_dset* s);
+
+#define CU(c, expr)                                                                        \
+  do {                                                                                     \
+    cudaError_t e__ = (expr);                                                              \
+    if (e__ != cudaSuccess)                                                                \
+      return cb_fail((c), e__ == cudaErrorMemoryAllocation ? CB_ERR_NOMEM : CB_ERR_CUDA,   \
+                     "%s: %s", #expr, cudaGetErrorString(e__));                            \
+  } while (0)
+
+// brute.cu
+int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bool pairs_only,
+                 int* launches);

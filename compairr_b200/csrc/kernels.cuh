@@ -1,0 +1,88 @@
+// kernels.cuh — launch interface between the engine (engine.cu) and the sm_100a kernels
+// (kernels.cu).  Internal; the public boundary is include/compairr_b200.h.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "common.cuh"
+
+namespace cb {
+
+struct PairOut {
+  uint64_t a, b;
+};
+
+// Device counters, one block of 8 u64 per context.
+enum Counter : int {
+  CTR_MATCHES = 0,
+  CTR_BLOOM_PASS = 1,
+  CTR_PAIRS = 2,    // pair cursor (may exceed capacity: overflow is detected from it)
+  CTR_WORK = 3,     // work-item dispenser of the probe kernels
+  CTR_DUPS = 4,
+  CTR_MAXLEN = 5,
+  CTR_PROBES = 6,
+  CTR_COUNT = 8
+};
+
+struct DeviceSetView {
+  const SeqMeta* meta;
+  const uint8_t* res;
+  const uint64_t* hash;
+  uint64_t n;
+  uint64_t index_base;
+};
+
+struct ProbeParams {
+  DeviceSetView a;
+  DeviceSetView b;
+  uint64_t a_first;  // first seed of this launch
+  uint64_t a_count;  // seeds in this launch
+  const Slot* table;
+  uint64_t table_mask;
+  const unsigned long long* bloom;
+  uint32_t bloom_blocks;
+  const uint64_t* ztab;  // global copy of the Zobrist table, zrows x sigma
+  uint32_t zrows;        // rows staged in shared memory by the variant kernel (>= longest A + 1)
+  uint32_t sigma;
+  uint64_t seed;
+  double* matrix;  // rows x n_cols
+  uint64_t n_cols;
+  PairOut* pairs;
+  uint64_t pairs_cap;
+  unsigned long long* counters;
+  uint32_t lmax;   // longest seed in the launch (sizes the per-warp scratch)
+  uint32_t split;  // d=2: work items per seed
+  int32_t score;
+  uint8_t ignore_counts, ignore_genes, existence, no_matrix;
+  uint8_t want_pairs, use_bloom, count_bloom, matrix_only_pairs_off;
+  int32_t differences;
+  uint8_t indels;
+};
+
+// pack SoA upload into SeqMeta records, find the longest sequence
+void launch_pack_meta(const uint64_t* offsets, const uint32_t* v, const uint32_t* j,
+                      const uint32_t* rep, const uint64_t* count, uint64_t n, uint64_t off_base,
+                      SeqMeta* out, unsigned long long* counters, cudaStream_t st);
+
+// K1: batched Zobrist hashing
+void launch_hash(const SeqMeta* meta, const uint8_t* res, uint64_t n, const uint64_t* ztab,
+                 uint32_t zrows, uint32_t sigma, uint64_t seed, bool ignore_genes, uint64_t* out,
+                 cudaStream_t st);
+
+// K2: table + Bloom build, duplicate count
+void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st);
+void launch_build(const uint64_t* hash, uint64_t n, Slot* table, uint64_t mask,
+                  unsigned long long* bloom, uint32_t bloom_blocks, cudaStream_t st);
+void launch_count_dups(DeviceSetView s, const Slot* table, uint64_t mask, bool ignore_genes,
+                       unsigned long long* counters, cudaStream_t st);
+
+// K3+K4: enumerate variants, Bloom, probe, verify, accumulate.  Returns launches made, <0 on
+// a configuration the kernels cannot take (message in *err).
+int launch_probe(const ProbeParams& p, int sm_count, cudaStream_t st, const char** err);
+
+// Closed-form variant count of seeds [first, first+count) summed into counters[CTR_PROBES]
+// (bookkeeping for the probes/s metric; not part of the timed hot path).
+void launch_count_probes(DeviceSetView a, uint64_t first, uint64_t count, uint32_t sigma, int d,
+                         bool indels, unsigned long long* counters, cudaStream_t st);
+
+}  // namespace cb

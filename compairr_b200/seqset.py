@@ -1,0 +1,139 @@
+"""Sequence sets in structure-of-arrays form — what the reference's db_read() (src/db.cc:708-901)
+leaves in memory, minus the C strings: one residue arena, offsets, gene / repertoire numbers and
+duplicate counts.  Residue codes follow src/db.cc:33-71 (ACDEFGHIKLMNPQRSTVWY -> 0..19,
+ACGT/U -> 0..3, case-insensitive)."""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+AA_ALPHABET = "ACDEFGHIKLMNPQRSTVWY"
+NT_ALPHABET = "ACGT"
+
+
+def _code_table(nucleotides: bool) -> np.ndarray:
+    t = np.full(256, 255, dtype=np.uint8)
+    alpha = NT_ALPHABET if nucleotides else AA_ALPHABET
+    for i, ch in enumerate(alpha):
+        t[ord(ch)] = i
+        t[ord(ch.lower())] = i
+    if nucleotides:
+        t[ord("U")] = t[ord("u")] = 3
+    return t
+
+
+def encode_sequences(seqs: Sequence[str], nucleotides: bool = False):
+    """strings -> (residue arena uint8, offsets uint64[n+1]); raises on an illegal symbol."""
+    lens = np.fromiter((len(s) for s in seqs), dtype=np.uint64, count=len(seqs))
+    offsets = np.zeros(len(seqs) + 1, dtype=np.uint64)
+    np.cumsum(lens, out=offsets[1:])
+    raw = np.frombuffer("".join(seqs).encode("ascii"), dtype=np.uint8)
+    res = _code_table(nucleotides)[raw]
+    if res.size and res.max() == 255:
+        bad = int(np.argmax(res == 255))
+        raise ValueError(f"illegal character {chr(raw[bad])!r} in sequence")
+    return np.ascontiguousarray(res), offsets
+
+
+@dataclass
+class SeqSet:
+    residues: np.ndarray            # uint8, codes 0..sigma-1
+    offsets: np.ndarray             # uint64, n+1
+    v_gene: np.ndarray              # uint32
+    j_gene: np.ndarray              # uint32
+    rep: np.ndarray                 # uint32, repertoire number 0..n_reps-1
+    count: np.ndarray               # uint64, duplicate_count >= 1
+    n_reps: int
+    nucleotides: bool = False
+    rep_names: Optional[List[str]] = None
+    v_names: Optional[List[str]] = None
+    j_names: Optional[List[str]] = None
+    seq_ids: Optional[List[str]] = None
+    index_base: int = 0
+    _keep: list = field(default_factory=list, repr=False)
+
+    def __post_init__(self):
+        self.residues = np.ascontiguousarray(self.residues, dtype=np.uint8)
+        self.offsets = np.ascontiguousarray(self.offsets, dtype=np.uint64)
+        self.v_gene = np.ascontiguousarray(self.v_gene, dtype=np.uint32)
+        self.j_gene = np.ascontiguousarray(self.j_gene, dtype=np.uint32)
+        self.rep = np.ascontiguousarray(self.rep, dtype=np.uint32)
+        self.count = np.ascontiguousarray(self.count, dtype=np.uint64)
+        n = self.n
+        assert self.offsets.shape == (n + 1,)
+        assert self.v_gene.shape == self.j_gene.shape == self.rep.shape == self.count.shape == (n,)
+
+    @property
+    def n(self) -> int:
+        return int(self.offsets.shape[0] - 1)
+
+    @property
+    def lengths(self) -> np.ndarray:
+        return np.diff(self.offsets).astype(np.int64)
+
+    @property
+    def sigma(self) -> int:
+        return 4 if self.nucleotides else 20
+
+    def sequence(self, i: int) -> str:
+        alpha = NT_ALPHABET if self.nucleotides else AA_ALPHABET
+        a, b = int(self.offsets[i]), int(self.offsets[i + 1])
+        return "".join(alpha[c] for c in self.residues[a:b])
+
+    def slice(self, first: int, count: int) -> "SeqSet":
+        """A shard sharing the residue arena (offsets stay absolute), reporting global indices."""
+        sl = slice(first, first + count)
+        return SeqSet(self.residues, self.offsets[first:first + count + 1], self.v_gene[sl],
+                      self.j_gene[sl], self.rep[sl], self.count[sl], self.n_reps, self.nucleotides,
+                      self.rep_names, self.v_names, self.j_names,
+                      None if self.seq_ids is None else self.seq_ids[sl],
+                      index_base=self.index_base + first)
+
+    @staticmethod
+    def from_records(records, nucleotides=False, gene_maps=None) -> "SeqSet":
+        """records: iterable of (repertoire_id, sequence_id, count, v_call, j_call, sequence).
+        Numbering is first-seen order like the reference (db.cc:510-520, 592-631); gene_maps =
+        (v_map, j_map) dicts shared between the two sets of a comparison (db.cc:119-125)."""
+        v_map, j_map = gene_maps if gene_maps is not None else ({}, {})
+        rep_map: Dict[str, int] = {}
+        reps, ids, cnt, vs, js, seqs = [], [], [], [], [], []
+        for rid, sid, c, v, j, s in records:
+            reps.append(rep_map.setdefault(rid, len(rep_map)))
+            ids.append(sid)
+            cnt.append(int(c))
+            vs.append(v_map.setdefault(v, len(v_map)))
+            js.append(j_map.setdefault(j, len(j_map)))
+            seqs.append(s)
+        res, off = encode_sequences(seqs, nucleotides)
+        return SeqSet(res, off, np.array(vs, np.uint32), np.array(js, np.uint32),
+                      np.array(reps, np.uint32), np.array(cnt, np.uint64), len(rep_map), nucleotides,
+                      list(rep_map), None, None, ids)
+
+    # ---- AIRR TSV (the reference's file contract, README.md "Input files") ------------------
+    def names(self):
+        rn = self.rep_names or [f"R{r:04d}" for r in range(self.n_reps)]
+        nv = int(self.v_gene.max()) + 1 if self.n else 0
+        nj = int(self.j_gene.max()) + 1 if self.n else 0
+        vn = self.v_names or [f"TRBV{v + 1:02d}" for v in range(nv)]
+        jn = self.j_names or [f"TRBJ{j + 1:02d}" for j in range(nj)]
+        return rn, vn, jn
+
+    def write_tsv(self, path: str, id_prefix: str = "s") -> None:
+        alpha = np.frombuffer((NT_ALPHABET if self.nucleotides else AA_ALPHABET).encode(), np.uint8)
+        text = alpha[self.residues].tobytes().decode("ascii")
+        rn, vn, jn = self.names()
+        col = "junction" if self.nucleotides else "junction_aa"
+        off = self.offsets
+        with open(path, "w") as f:
+            f.write(f"repertoire_id\tsequence_id\tduplicate_count\tv_call\tj_call\t{col}\n")
+            lines = []
+            for i in range(self.n):
+                sid = self.seq_ids[i] if self.seq_ids is not None else f"{id_prefix}{i + self.index_base}"
+                lines.append(f"{rn[self.rep[i]]}\t{sid}\t{self.count[i]}\t{vn[self.v_gene[i]]}\t"
+                             f"{jn[self.j_gene[i]]}\t{text[int(off[i]):int(off[i + 1])]}\n")
+                if len(lines) >= 65536:
+                    f.write("".join(lines))
+                    lines = []
+            f.write("".join(lines))

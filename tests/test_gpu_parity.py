@@ -1,0 +1,86 @@
+"""GPU parity: the CUDA engine, through the C ABI, against the CPU oracle on the same seeded
+inputs.  Bit-exact for integer-valued scores, counts and pair lists; 1e-12 relative for ratio."""
+import numpy as np
+import pytest
+
+from compairr_b200 import OverlapOptions, overlap, synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _pairs(p):
+    return sorted(map(tuple, np.asarray(p).tolist()))
+
+
+def _check(a, b, tol=None, **kw):
+    eng_kw = dict(kw)
+    m, p, info = overlap(a, b, OverlapOptions(want_pairs=True, nucleotides=a.nucleotides, **eng_kw))
+    mo, po, io = orc.overlap(a, b, want_pairs=True, **kw)
+    if tol is None:
+        assert np.array_equal(m, mo)
+    else:
+        np.testing.assert_allclose(m, mo, rtol=tol, atol=0)
+    assert _pairs(p) == _pairs(po)
+    assert info["run"]["matches"] == io["matches"]
+    if kw.get("differences", 0) <= 2:
+        assert info["run"]["probes"] == io["probes"]
+    return info
+
+
+CASES = [(0, False), (1, False), (1, True), (2, False), (3, False), (4, False)]
+
+
+@pytest.mark.parametrize("d,indels", CASES)
+@pytest.mark.parametrize("ignore_genes", [False, True])
+def test_dense_small_aa(d, indels, ignore_genes):
+    a = synth.small_dense_set(3, 3, 120)
+    b = synth.small_dense_set(4, 4, 120)
+    _check(a, b, differences=d, indels=indels, ignore_genes=ignore_genes)
+
+
+@pytest.mark.parametrize("d,indels", CASES)
+def test_dense_small_nt(d, indels):
+    a = synth.small_dense_set(5, 2, 150, alphabet="ACG", max_len=12, nucleotides=True)
+    b = synth.small_dense_set(6, 3, 150, alphabet="ACG", max_len=12, nucleotides=True)
+    _check(a, b, differences=d, indels=indels)
+
+
+@pytest.mark.parametrize("score", ["product", "min", "max", "mean", "ratio"])
+def test_scores(score):
+    a = synth.small_dense_set(7, 3, 100)
+    b = synth.small_dense_set(8, 3, 100)
+    _check(a, b, tol=1e-12 if score == "ratio" else None, differences=1, indels=True, score=score)
+
+
+def test_ignore_counts_and_self():
+    a = synth.small_dense_set(9, 4, 100)
+    _check(a, None, differences=1, ignore_counts=True)
+    _check(a, None, differences=0, score="mh")
+    _check(a, None, differences=0, score="jaccard")
+
+
+@pytest.mark.parametrize("d,indels", [(0, False), (1, True), (2, False), (3, False)])
+def test_existence(d, indels):
+    a = synth.small_dense_set(10, 1, 90)
+    b = synth.small_dense_set(11, 5, 100)
+    _check(a, b, differences=d, indels=indels, existence=True)
+
+
+@pytest.mark.parametrize("d,indels", [(0, False), (1, False), (1, True), (2, False)])
+def test_cdr3_like(d, indels):
+    pool = synth.make_pool(21, 3000)
+    a = synth.make_set(22, 6, 1500, pool=pool, indel_mutants=True)
+    b = synth.make_set(23, 7, 1500, pool=pool, indel_mutants=True)
+    info = _check(a, b, differences=d, indels=indels)
+    assert info["run"]["matches"] > 0
+
+
+def test_dups():
+    from compairr_b200 import Engine
+    a = synth.small_dense_set(12, 3, 300, max_len=4)
+    with Engine(OverlapOptions(differences=1), n_reps_a=a.n_reps) as eng:
+        d = eng.upload(a)
+        eng.build_b(d)
+        assert eng.dups_b() == orc.count_dups(a) > 0
+        assert eng.count_dups(d) == orc.count_dups(a)
