@@ -62,13 +62,17 @@ __device__ __forceinline__ uint64_t pack_variant(uint32_t kind, uint32_t pos1, u
 // K4: walk the probe chain of hash hv; for every slot with an equal stored hash compare V/J,
 // verify the edit exactly, score, accumulate, append the pair.  Linear probing to the first
 // empty slot, every equal-hash slot is visited (overlap.cc:181-250).  Returns matches found.
-// Deliberately not inlined: <1 % of probes get here, and keeping it out of line keeps the
-// enumeration loop's register footprint small.
-__device__ __noinline__ uint32_t table_probe(const ProbeParams* __restrict__ P, uint64_t seed_idx,
-                                             uint64_t seed_count, uint32_t slen, uint32_t sv,
-                                             uint32_t sj, uint32_t row, const uint8_t* sres,
-                                             uint64_t var, uint64_t hv) {
+// Not inlined (keeps the enumeration loop's register footprint small) and always CALLED
+// warp-uniformly — lanes without work pass active = false.  A call from divergent code leaves
+// the warp split for the rest of the kernel (measured: 4 of 32 lanes active, profiles/r01),
+// so survivors of the Bloom test are first compacted into a per-warp queue and drained 32 at a
+// time (see variant_kernel).
+__device__ __noinline__ uint32_t table_probe(const ProbeParams* __restrict__ P, bool active,
+                                             uint64_t seed_idx, uint64_t seed_count, uint32_t slen,
+                                             uint32_t sv, uint32_t sj, uint32_t row,
+                                             const uint8_t* sres, uint64_t var, uint64_t hv) {
   uint32_t found = 0;
+  if (!active) return 0;
   const uint64_t mask = P->table_mask;
   uint64_t slot = table_home(hv, mask);
   for (;;) {
@@ -322,19 +326,23 @@ void launch_count_probes(DeviceSetView a, uint64_t first, uint64_t count, uint32
 
 __global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ ProbeParams P) {
   uint32_t nmatch = 0, npass = 0;
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < P.a_count;
-       i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t sidx = P.a_first + i;
+  // warp-uniform trip count, so the table_probe call below is made by all 32 lanes together
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); i0 < P.a_count;
+       i0 += stride) {
+    const uint64_t i = i0 + (threadIdx.x & 31);
+    const bool in = i < P.a_count;
+    const uint64_t sidx = P.a_first + (in ? i : 0);
     const uint64_t h = P.a.hash[sidx];
-    bool pass = true;
-    if (P.use_bloom) pass = bloom_test(P.bloom, P.bloom_blocks, h);
-    if (pass) {
-      npass++;
-      const SeqMeta m = ld_meta(P.a.meta + sidx);
-      const uint32_t row = P.existence ? (uint32_t)i : m.rep;
-      nmatch += table_probe(&P, sidx, m.count, m.len, m.v, m.j, row, P.a.res + m.off,
-                            pack_variant(VK_IDENTICAL, 0, 0, 0, 0), h);
-    }
+    bool pass = in;
+    if (P.use_bloom && in) pass = bloom_test(P.bloom, P.bloom_blocks, h);
+    npass += pass;
+    SeqMeta m = {};
+    if (pass) m = ld_meta(P.a.meta + sidx);
+    const uint32_t row = P.existence ? (uint32_t)i : m.rep;
+    nmatch += table_probe(&P, pass, sidx, m.count, m.len, m.v, m.j, row, P.a.res + m.off,
+                          pack_variant(VK_IDENTICAL, 0, 0, 0, 0), h);
+    __syncwarp();
   }
   flush_counters(P, nmatch, P.count_bloom ? npass : 0);
 }
@@ -354,13 +362,66 @@ __global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ 
 
 constexpr int VK_THREADS = 256;
 constexpr int VK_WARPS = VK_THREADS / 32;
+constexpr int VK_QCAP = 64;  // per-warp survivor queue entries (ring); drained 32 at a time
 
 __host__ __device__ inline uint32_t vk_lpad(uint32_t lmax) { return (lmax + 2 + 7) & ~7u; }
 __host__ __device__ inline size_t vk_warp_u64(uint32_t lmax, bool indels) {
-  return (size_t)vk_lpad(lmax) * (indels ? 4 : 1);
+  return (size_t)vk_lpad(lmax) * (indels ? 4 : 1) + 2 * VK_QCAP;  // scratch + queue hv/var
+}
+__host__ __device__ inline size_t vk_warp_bytes(uint32_t lmax) {
+  return (size_t)vk_lpad(lmax) + VK_QCAP * 4;  // residues + queue seed numbers
 }
 static size_t vk_smem_bytes(uint32_t zrows, uint32_t sigma, uint32_t lmax, bool indels) {
-  return (size_t)zrows * sigma * 8 + VK_WARPS * (vk_warp_u64(lmax, indels) * 8 + vk_lpad(lmax));
+  return (size_t)zrows * sigma * 8 + VK_WARPS * (vk_warp_u64(lmax, indels) * 8 + vk_warp_bytes(lmax));
+}
+
+// Per-warp ring of Bloom survivors waiting for the table probe.
+struct WarpQueue {
+  uint64_t* hv;
+  uint64_t* var;
+  uint32_t* seed;  // seed number relative to a_first
+  uint32_t head, count;
+};
+
+// Probe up to 32 queued survivors, one per lane; all 32 lanes make the call.
+__device__ __forceinline__ uint32_t queue_drain(const ProbeParams& P, WarpQueue& q, uint32_t lane,
+                                                uint32_t n) {
+  const bool act = lane < n;
+  const uint32_t e = (q.head + lane) & (VK_QCAP - 1);
+  uint64_t hv = 0, var = 0, sidx = P.a_first;
+  uint32_t slocal = 0;
+  SeqMeta m = {};
+  if (act) {
+    hv = q.hv[e];
+    var = q.var[e];
+    slocal = q.seed[e];
+    sidx = P.a_first + slocal;
+    m = ld_meta(P.a.meta + sidx);
+  }
+  const uint32_t row = P.existence ? slocal : m.rep;
+  const uint32_t found =
+      table_probe(&P, act, sidx, m.count, m.len, m.v, m.j, row, P.a.res + m.off, var, hv);
+  __syncwarp();
+  q.head = (q.head + n) & (VK_QCAP - 1);
+  q.count -= n;
+  return found;
+}
+
+// Append this step's survivors (ballot + prefix popcount), drain when 32 are waiting.
+__device__ __forceinline__ uint32_t queue_push(const ProbeParams& P, WarpQueue& q, uint32_t lane,
+                                               bool pass, uint64_t hv, uint64_t var,
+                                               uint32_t slocal) {
+  const unsigned m = __ballot_sync(FULL, pass);
+  if (m == 0) return 0;
+  if (pass) {
+    const uint32_t e = (q.head + q.count + __popc(m & ((1u << lane) - 1))) & (VK_QCAP - 1);
+    q.hv[e] = hv;
+    q.var[e] = var;
+    q.seed[e] = slocal;
+  }
+  q.count += __popc(m);
+  __syncwarp();
+  return q.count >= 32 ? queue_drain(P, q, lane, 32) : 0;
 }
 
 template <int SIGMA, bool INDELS, int D>
@@ -371,12 +432,20 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t lpad = vk_lpad(P.lmax);
   const size_t wu64 = vk_warp_u64(P.lmax, INDELS);
-  uint64_t* const zo = z + (size_t)P.zrows * SIGMA + warp * wu64;
+  uint64_t* const wbase = z + (size_t)P.zrows * SIGMA + warp * wu64;
+  WarpQueue q;
+  q.hv = wbase;
+  q.var = wbase + VK_QCAP;
+  uint64_t* const zo = wbase + 2 * VK_QCAP;
   uint64_t* const pre = zo + lpad;
   uint64_t* const sm = pre + lpad;
   uint64_t* const sp = sm + lpad;
-  uint8_t* const sres =
-      reinterpret_cast<uint8_t*>(z + (size_t)P.zrows * SIGMA + VK_WARPS * wu64) + warp * lpad;
+  unsigned char* const bbase = reinterpret_cast<unsigned char*>(z + (size_t)P.zrows * SIGMA + VK_WARPS * wu64) +
+                               warp * vk_warp_bytes(P.lmax);
+  q.seed = reinterpret_cast<uint32_t*>(bbase);
+  uint8_t* const sres = bbase + VK_QCAP * 4;
+  q.head = 0;
+  q.count = 0;
 
   for (uint32_t i = threadIdx.x; i < P.zrows * SIGMA; i += VK_THREADS) z[i] = P.ztab[i];
   __syncthreads();
@@ -386,6 +455,7 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
   const uint64_t total_items = P.a_count * P.split;
   const uint32_t split_mask = P.split - 1;
   const uint32_t split_shift = 31 - __clz(P.split);
+  const bool use_bloom = P.use_bloom;
   uint32_t nmatch = 0, npass = 0;
 
   for (;;) {
@@ -396,13 +466,12 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
     const uint64_t item_end = (item0 + BATCH < total_items) ? item0 + BATCH : total_items;
 
     for (uint64_t item = item0; item < item_end; ++item) {
-      const uint64_t slocal = item >> split_shift;
+      const uint32_t slocal = (uint32_t)(item >> split_shift);
       const uint32_t part = (uint32_t)item & split_mask;
       const uint64_t sidx = P.a_first + slocal;
       const SeqMeta m = ld_meta(P.a.meta + sidx);  // same address in all lanes: one broadcast
       const uint64_t h = __ldg(P.a.hash + sidx);
       const uint32_t L = m.len;
-      const uint32_t row = P.existence ? (uint32_t)slocal : m.rep;
 
       __syncwarp();  // all lanes are done with the previous item's scratch
       for (uint32_t p = lane; p < L; p += 32) {
@@ -434,10 +503,10 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
         for (uint32_t base = 0; base < L; base += 32) {
           const uint32_t t = base + lane;
           const bool ok = t < L;
-          const uint32_t q = ok ? L - 1 - t : 0;
-          const uint32_t r = sres[q];
-          uint64_t xm = (ok && q >= 1) ? z[(q - 1) * SIGMA + r] : 0ull;
-          uint64_t xp = ok ? z[(q + 1) * SIGMA + r] : 0ull;
+          const uint32_t qq = ok ? L - 1 - t : 0;
+          const uint32_t r = sres[qq];
+          uint64_t xm = (ok && qq >= 1) ? z[(qq - 1) * SIGMA + r] : 0ull;
+          uint64_t xp = ok ? z[(qq + 1) * SIGMA + r] : 0ull;
 #pragma unroll
           for (int o = 1; o < 32; o <<= 1) {
             const uint64_t ym = __shfl_up_sync(FULL, xm, o);
@@ -448,8 +517,8 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
             }
           }
           if (ok) {
-            sm[q] = cm ^ xm;
-            sp[q] = cp ^ xp;
+            sm[qq] = cm ^ xm;
+            sp[qq] = cp ^ xp;
           }
           cm ^= __shfl_sync(FULL, xm, 31);
           cp ^= __shfl_sync(FULL, xp, 31);
@@ -467,14 +536,14 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
         const uint32_t T = 1 + nsub + (INDELS ? L + SIGMA * (L + 1) : 0);
         for (uint32_t base = 0; base < T; base += 64) {
           uint64_t hv[2], var[2];
-          bool valid[2];
+          bool pass[2];
 #pragma unroll
           for (int u = 0; u < 2; u++) {
             const uint32_t idx = base + u * 32 + lane;
-            valid[u] = idx < T;
+            pass[u] = idx < T;
             hv[u] = h;
             var[u] = pack_variant(VK_IDENTICAL, 0, 0, 0, 0);
-            if (valid[u] && idx >= 1) {
+            if (pass[u] && idx >= 1) {
               uint32_t t = idx - 1;
               if (t < nsub) {
                 const uint32_t pos = t / S1, rp = t - pos * S1;
@@ -484,31 +553,28 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
               } else if (INDELS) {
                 t -= nsub;
                 if (t < L) {  // deletion of residue t, only at the start of a run, only if L > 1
-                  valid[u] = (L > 1) && (t == 0 || sres[t] != sres[t - 1]);
+                  pass[u] = (L > 1) && (t == 0 || sres[t] != sres[t - 1]);
                   hv[u] = vjh ^ pre[t] ^ sm[t + 1];
                   var[u] = pack_variant(VK_DELETION, t, 0, 0, 0);
                 } else {  // insertion of residue r before seed position pos
                   t -= L;
                   const uint32_t pos = t / SIGMA, r = t - pos * SIGMA;
-                  valid[u] = (pos == 0) || (r != sres[pos - 1]);
+                  pass[u] = (pos == 0) || (r != sres[pos - 1]);
                   hv[u] = vjh ^ pre[pos] ^ z[pos * SIGMA + r] ^ sp[pos];
                   var[u] = pack_variant(VK_INSERTION, pos, r, 0, 0);
                 }
               }
             }
           }
-          bool pass[2];
+          if (use_bloom) {
 #pragma unroll
-          for (int u = 0; u < 2; u++) {
-            pass[u] = valid[u];
-            if (P.use_bloom && valid[u]) pass[u] = bloom_test(P.bloom, P.bloom_blocks, hv[u]);
+            for (int u = 0; u < 2; u++)
+              if (pass[u]) pass[u] = bloom_test(P.bloom, P.bloom_blocks, hv[u]);
           }
 #pragma unroll
           for (int u = 0; u < 2; u++) {
-            if (pass[u]) {
-              npass++;
-              nmatch += table_probe(&P, sidx, m.count, L, m.v, m.j, row, sres, var[u], hv[u]);
-            }
+            npass += pass[u];
+            nmatch += queue_push(P, q, lane, pass[u], hv[u], var[u], slocal);
           }
         }
       }
@@ -520,39 +586,44 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
           const uint32_t i = o / S1, vp = o - i * S1;
           const uint32_t v = sub_residue(vp, sres[i]);
           const uint64_t base2 = h ^ zo[i] ^ z[i * SIGMA + v];
+          const uint64_t var_iv = pack_variant(VK_SUB_SUB, i, v, 0, 0);
           const uint32_t ninner = S1 * (L - 1 - i);
           for (uint32_t tb = 0; tb < ninner; tb += 64) {
-            uint64_t hv[2], var[2];
+            uint64_t hv[2];
+            uint32_t jw[2];
             bool pass[2];
 #pragma unroll
             for (int u = 0; u < 2; u++) {
               const uint32_t t = tb + u * 32 + lane;
               pass[u] = t < ninner;
               hv[u] = 0;
-              var[u] = 0;
+              jw[u] = 0;
               if (pass[u]) {
                 const uint32_t jj = t / S1, wp = t - jj * S1;
                 const uint32_t j = i + 1 + jj;
                 const uint32_t w = sub_residue(wp, sres[j]);
                 hv[u] = base2 ^ zo[j] ^ z[j * SIGMA + w];
-                var[u] = pack_variant(VK_SUB_SUB, i, v, j, w);
+                jw[u] = (j << 8) | w;
               }
             }
+            if (use_bloom) {
 #pragma unroll
-            for (int u = 0; u < 2; u++)
-              if (P.use_bloom && pass[u]) pass[u] = bloom_test(P.bloom, P.bloom_blocks, hv[u]);
+              for (int u = 0; u < 2; u++)
+                if (pass[u]) pass[u] = bloom_test(P.bloom, P.bloom_blocks, hv[u]);
+            }
 #pragma unroll
             for (int u = 0; u < 2; u++) {
-              if (pass[u]) {
-                npass++;
-                nmatch += table_probe(&P, sidx, m.count, L, m.v, m.j, row, sres, var[u], hv[u]);
-              }
+              npass += pass[u];
+              const uint64_t var = var_iv | ((uint64_t)(jw[u] & 0xff) << 16) | ((uint64_t)(jw[u] >> 8) << 44);
+              nmatch += queue_push(P, q, lane, pass[u], hv[u], var, slocal);
             }
           }
         }
       }
     }
   }
+  __syncwarp();
+  if (q.count) nmatch += queue_drain(P, q, lane, q.count);  // q.count < 32 here
   flush_counters(P, nmatch, P.count_bloom ? npass : 0);
 }
 
