@@ -1,0 +1,40 @@
+// airr_tsv.h — AIRR TSV reader: file -> structure-of-arrays sequence set + the strings the
+// writers need.  Behaviour-compatible with the reference's db_read()/parse_airr_tsv_*()
+// (src/db.cc:172-901): same column names, same defaults, same error texts and exit codes, ids
+// numbered in first-seen order.  Host-only; the GPU never sees strings.
+#pragma once
+#include <stdint.h>
+
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "options.h"
+
+struct GeneTables {  // V and J gene names are shared by both sets (db.cc:119-125)
+  std::vector<std::string> v_names, j_names;
+  std::unordered_map<std::string, uint32_t> v_map, j_map;
+};
+
+struct SeqDb {
+  std::vector<uint8_t> residues;
+  std::vector<uint64_t> offsets{0};
+  std::vector<uint32_t> v, j, rep;
+  std::vector<uint64_t> count;
+  std::vector<std::string> seq_id;  // only filled when needed (pairs / existence)
+  std::vector<std::string> keep;    // -k columns, tab-joined
+  std::vector<std::string> rep_names;
+  std::unordered_map<std::string, uint32_t> rep_map;
+  unsigned longest = 0, shortest = ~0u;
+  uint64_t total_count = 0, ignored_unknown = 0, ignored_empty = 0;
+  uint64_t n() const { return v.size(); }
+};
+
+// Reads `filename` ("-" = stdin) into db; logs the summary block; exits with the reference's
+// messages on malformed input.
+void read_airr_tsv(const char* filename, const Options& o, bool require_sequence_id, bool want_ids,
+                   const char* default_repertoire_id, GeneTables& genes, SeqDb& db);
+
+// progress/timing lines in the reference's format (util.cc:32-70)
+void progress_begin(const Options& o, const char* prompt);
+void progress_end(const Options& o, const char* prompt);

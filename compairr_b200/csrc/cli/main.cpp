@@ -1,0 +1,46 @@
+// main.cpp — compairr_b200: a CompAIRR-compatible command line for the -m / -x commands on top of
+// the GPU engine (main(), src/compairr.cc:743-798).
+#include <stdlib.h>
+#include <string.h>
+#include <unistd.h>
+
+#include "options.h"
+#include "overlap_cmd.h"
+
+static FILE* open_output(const char* name) {  // "-" = stdout (util.cc:157-170)
+  if (!strcmp(name, "-")) {
+    const int fd = dup(STDOUT_FILENO);
+    return fd < 0 ? nullptr : fdopen(fd, "w");
+  }
+  return fopen(name, "w");
+}
+
+int main(int argc, char** argv) {
+  Options o;
+  parse_args(argc, argv, o);
+  if (o.log) {
+    g_log = open_output(o.log);
+    if (!g_log) fatal("Unable to open log file for writing.");
+  }
+  FILE* outfile = open_output(o.output);
+  if (!outfile) fatal("Unable to open output file for writing.");
+  FILE* pairsfile = nullptr;
+  if (o.pairs) {
+    pairsfile = open_output(o.pairs);
+    if (!pairsfile) fatal("Unable to open pairs file for writing.");
+  }
+  show_header();
+  if (o.version || o.help) {
+    if (o.help) show_usage();
+    return 0;
+  }
+  show_time("Start time:        ");
+  show_args(o);
+  fprintf(g_log, "\n");
+  overlap_command(o, outfile, pairsfile);
+  show_time("End time:          ");
+  if (pairsfile) fclose(pairsfile);
+  fclose(outfile);
+  if (g_log != stderr) fclose(g_log);
+  return 0;
+}

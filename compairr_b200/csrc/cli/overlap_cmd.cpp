@@ -1,0 +1,358 @@
+// overlap_cmd.cpp — see overlap_cmd.h.  Output formats follow src/overlap.cc:540-577 (values),
+// :908-925 (pairs header), :455-507 (pairs rows), :944-1039 (matrix layouts).
+#include "overlap_cmd.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "airr_tsv.h"
+#include "compairr_b200.h"
+
+namespace {
+
+struct RepStats {
+  std::vector<uint64_t> size, count;
+  std::vector<double> sq_count;
+  std::vector<unsigned> order;  // display order: strcmp on the repertoire id (overlap.cc:130-142,659-667)
+  uint64_t sum_size = 0, sum_count = 0;
+};
+
+RepStats rep_stats(const SeqDb& d) {
+  RepStats s;
+  const size_t r = d.rep_names.size();
+  s.size.assign(r, 0);
+  s.count.assign(r, 0);
+  s.sq_count.assign(r, 0.0);
+  for (uint64_t i = 0; i < d.n(); i++) {
+    const unsigned k = d.rep[i];
+    const uint64_t c = d.count[i];
+    s.size[k]++;
+    s.count[k] += c;
+    s.sq_count[k] += (double)(c * c);  // u64 product, then double: as overlap.cc:654
+  }
+  s.order.resize(r);
+  for (unsigned i = 0; i < r; i++) s.order[i] = i;
+  std::sort(s.order.begin(), s.order.end(),
+            [&](unsigned a, unsigned b) { return strcmp(d.rep_names[a].c_str(), d.rep_names[b].c_str()) < 0; });
+  for (unsigned k = 0; k < r; k++) {
+    s.sum_size += s.size[k];
+    s.sum_count += s.count[k];
+  }
+  return s;
+}
+
+void log_rep_table(const SeqDb& d, const RepStats& s) {
+  const size_t r = d.rep_names.size();
+  const int w1 = std::max(1, (int)(1 + floor(log10((double)r))));
+  const int w2 = std::max(9, (int)(1 + floor(log10((double)s.sum_size))));
+  const int w3 = std::max(5, (int)(1 + floor(log10((double)s.sum_count))));
+  fprintf(g_log, "Repertoires in set:\n");
+  fprintf(g_log, "%*s %*s %*s %s\n", w1, "#", w2, "Sequences", w3, "Count", "Repertoire ID");
+  for (unsigned i = 0; i < r; i++) {
+    const unsigned k = s.order[i];
+    fprintf(g_log, "%*u %*lu %*lu %s\n", w1, i + 1, w2, (unsigned long)s.size[k], w3, (unsigned long)s.count[k],
+            d.rep_names[k].c_str());
+  }
+  fprintf(g_log, "\n");
+}
+
+cb_set as_cb_set(const SeqDb& d, uint64_t first, uint64_t n) {
+  cb_set s{};
+  s.n = n;
+  s.residues = d.residues.data();
+  s.offsets = d.offsets.data() + first;
+  s.v_gene = d.v.data() + first;
+  s.j_gene = d.j.data() + first;
+  s.rep = d.rep.data() + first;
+  s.count = d.count.data() + first;
+  s.n_reps = (uint32_t)d.rep_names.size();
+  s.index_base = first;
+  return s;
+}
+
+[[noreturn]] void engine_fatal(cb_ctx* c) {
+  const std::string msg = c ? cb_last_error(c) : cb_global_error();
+  if (c) cb_destroy(c);
+  fatal(msg.c_str());
+}
+
+int64_t hamming(const uint8_t* a, const uint8_t* b, int64_t n) {
+  int64_t d = 0;
+  for (int64_t i = 0; i < n; i++) d += a[i] != b[i];
+  return d;
+}
+
+struct PairWriter {
+  const Options& o;
+  const SeqDb &d1, &d2;
+  const GeneTables& g;
+  FILE* f;
+  std::string buf;
+
+  void header() {
+    fprintf(f, "#repertoire_id_1\tsequence_id_1\tduplicate_count_1\tv_call_1\tj_call_1\t%s_1", o.seq_header);
+    for (auto& k : o.keep_names) fprintf(f, "\t%s_1", k.c_str());
+    fprintf(f, "\trepertoire_id_2\tsequence_id_2\tduplicate_count_2\tv_call_2\tj_call_2\t%s_2", o.seq_header);
+    for (auto& k : o.keep_names) fprintf(f, "\t%s_2", k.c_str());
+    if (o.distance) fprintf(f, "\tdistance");
+    fprintf(f, "\n");
+  }
+  void side(const SeqDb& d, uint64_t i) {
+    const char* alpha = o.nucleotides ? "acgt" : "ACDEFGHIKLMNPQRSTVWY";  // db.cc:73-74
+    buf += d.rep_names[d.rep[i]];
+    buf += '\t';
+    if (!d.seq_id.empty()) buf += d.seq_id[i];
+    buf += '\t';
+    buf += std::to_string(d.count[i]);
+    buf += '\t';
+    buf += g.v_names[d.v[i]];
+    buf += '\t';
+    buf += g.j_names[d.j[i]];
+    buf += '\t';
+    for (uint64_t p = d.offsets[i]; p < d.offsets[i + 1]; p++) buf += alpha[d.residues[p]];
+    if (!o.keep_names.empty()) {
+      buf += '\t';
+      buf += d.keep[i];
+    }
+  }
+  void write(const cb_pair* p, size_t n) {
+    for (size_t k = 0; k < n; k++) {
+      const uint64_t a = p[k].a, b = p[k].b;
+      side(d1, a);
+      buf += '\t';
+      side(d2, b);
+      if (o.distance) {  // Hamming if equal length, else 1 (one indel), overlap.cc:492-502
+        const int64_t l1 = (int64_t)(d1.offsets[a + 1] - d1.offsets[a]), l2 = (int64_t)(d2.offsets[b + 1] - d2.offsets[b]);
+        int64_t dist = 1;
+        if (l1 == l2) dist = hamming(d1.residues.data() + d1.offsets[a], d2.residues.data() + d2.offsets[b], l1);
+        buf += '\t';
+        buf += std::to_string(dist);
+      }
+      buf += '\n';
+      if (buf.size() > (1u << 20)) flush();
+    }
+    flush();
+  }
+  void flush() {
+    if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), f);
+    buf.clear();
+  }
+};
+
+}  // namespace
+
+void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
+  GeneTables genes;
+  SeqDb d1, d2s;
+
+  fprintf(g_log, "Immune receptor repertoire set 1\n\n");
+  read_airr_tsv(o.input1, o, o.existence, o.existence || o.pairs, "1", genes, d1);
+  fprintf(g_log, "\n");
+  const RepStats s1 = rep_stats(d1);
+  log_rep_table(d1, s1);
+  if (o.existence && d1.rep_names.size() > 1)
+    fatal("Multiple repertoires are not allowed in the first file specified on the command line with the -x or --existence command.");
+
+  fprintf(g_log, "Immune receptor repertoire set 2\n\n");
+  const bool two_sets = o.input2 && strcmp(o.input1, o.input2);
+  if (two_sets) {
+    read_airr_tsv(o.input2, o, false, o.pairs != nullptr, "2", genes, d2s);
+    fprintf(g_log, "\n");
+  } else {
+    fprintf(g_log, "Set 2 is identical to set 1\n\n");
+  }
+  const SeqDb& d2 = two_sets ? d2s : d1;
+  const RepStats s2s = two_sets ? rep_stats(d2s) : RepStats();
+  const RepStats& s2 = two_sets ? s2s : s1;
+  if (two_sets) {
+    if (d2.rep_names.empty()) fatal("Repertoire set missing repertoire_id.");
+    log_rep_table(d2, s2);
+  } else if (d2.rep_names.empty()) {
+    fatal("Repertoire set is missing repertoire_id.");
+  }
+  fprintf(g_log, "Unique V genes:    %lu\n", (unsigned long)genes.v_names.size());
+  fprintf(g_log, "Unique J genes:    %lu\n", (unsigned long)genes.j_names.size());
+
+  const uint64_t R1 = d1.rep_names.size(), R2 = d2.rep_names.size(), N1 = d1.n();
+  const int ngpu = std::min<int>(o.gpus, std::max(1, cb_device_count() - o.device));
+
+  // ---- engine: one context per GPU, set B replicated, set A sharded --------------------------
+  cb_config cfg{};
+  cfg.abi_version = CB_ABI_VERSION;
+  cfg.alphabet_size = o.alphabet_size;
+  cfg.differences = (int32_t)std::min<int64_t>(o.differences, 1 << 20);
+  cfg.indels = o.indels;
+  cfg.ignore_genes = o.ignore_genes;
+  cfg.ignore_counts = o.ignore_counts;
+  cfg.score = (int32_t)o.score;
+  cfg.mode = o.existence ? CB_MODE_EXISTENCE : CB_MODE_MATRIX;
+  cfg.no_matrix = o.no_matrix;
+  cfg.want_pairs = o.pairs != nullptr;
+  cfg.n_reps_a = (uint32_t)std::max<uint64_t>(R1, 1);
+  cfg.seed = 1;
+
+  std::vector<cb_ctx*> ctx(ngpu, nullptr);
+  for (int g = 0; g < ngpu; g++) {
+    cfg.device = o.device + g;
+    if (cb_create(&cfg, &ctx[g])) engine_fatal(nullptr);
+  }
+  const cb_set whole_b = as_cb_set(d2, 0, d2.n());
+  std::vector<cb_dset*> dev_b(ngpu, nullptr);
+
+  progress_begin(o, "Hashing sequences:");  // upload + hash + table/Bloom build + duplicate check
+  {
+    std::vector<std::thread> th;
+    std::vector<int> rc(ngpu, 0);
+    for (int g = 0; g < ngpu; g++)
+      th.emplace_back([&, g] {
+        rc[g] = cb_upload(ctx[g], &whole_b, &dev_b[g]);
+        if (!rc[g]) rc[g] = cb_build_b(ctx[g], dev_b[g]);
+      });
+    for (auto& t : th) t.join();
+    for (int g = 0; g < ngpu; g++)
+      if (rc[g]) engine_fatal(ctx[g]);
+  }
+  progress_end(o, "Hashing sequences:");
+  if (o.differences <= 2) {
+    if (two_sets) {  // duplicates in set 1 are only checked with two distinct sets (overlap.cc:846-852)
+      const cb_set whole_a = as_cb_set(d1, 0, N1);
+      cb_dset* da = nullptr;
+      uint64_t dup1 = 0;
+      if (cb_upload(ctx[0], &whole_a, &da) || cb_count_dups(ctx[0], da, &dup1)) engine_fatal(ctx[0]);
+      cb_free_set(ctx[0], da);
+      if (dup1) fprintf(g_log, "Warning: %lu duplicates detected in repertoire set 1\n", (unsigned long)dup1);
+    }
+    const uint64_t dup2 = cb_dups_b(ctx[0]);
+    if (dup2) fprintf(g_log, "Warning: %lu duplicates detected in repertoire set 2\n", (unsigned long)dup2);
+  }
+
+  // ---- analysis --------------------------------------------------------------------------------
+  std::vector<double> matrix;
+  const uint64_t rows = o.existence ? N1 : R1;
+  if (!o.no_matrix) matrix.assign(rows * R2, 0.0);
+  PairWriter pw{o, d1, d2, genes, pairsfile, {}};
+  if (o.pairs) pw.header();
+
+  progress_begin(o, "Analysing:        ");
+  // shard boundaries balanced by expected probes (cost ~ L for d=1, L^2 for d=2)
+  std::vector<uint64_t> bound(ngpu + 1, 0);
+  {
+    std::vector<double> pre(N1 + 1, 0.0);
+    for (uint64_t i = 0; i < N1; i++) {
+      const double L = (double)(d1.offsets[i + 1] - d1.offsets[i]);
+      pre[i + 1] = pre[i] + (o.differences >= 2 ? L * L : L) + 1.0;
+    }
+    for (int g = 1; g < ngpu; g++)
+      bound[g] = std::lower_bound(pre.begin(), pre.end(), pre[N1] * g / ngpu) - pre.begin();
+    bound[ngpu] = N1;
+  }
+  const uint64_t chunk = o.pairs || o.existence ? (1u << 20) : N1 + 1;  // bound host memory for pairs / -x rows
+  std::vector<std::string> errors(ngpu);
+  std::vector<std::vector<cb_pair>> pair_out(ngpu);
+  {
+    std::vector<std::thread> th;
+    for (int g = 0; g < ngpu; g++)
+      th.emplace_back([&, g] {
+        cb_ctx* c = ctx[g];
+        const bool self_dev = !two_sets;  // set A is the resident set B
+        cb_dset* da = nullptr;
+        if (bound[g + 1] == bound[g]) return;
+        if (self_dev) {
+          da = dev_b[g];
+        } else {
+          const cb_set shard = as_cb_set(d1, bound[g], bound[g + 1] - bound[g]);
+          if (cb_upload(c, &shard, &da)) { errors[g] = cb_last_error(c); return; }
+        }
+        const uint64_t base = self_dev ? bound[g] : 0;  // range inside the device set
+        for (uint64_t at = bound[g]; at < bound[g + 1]; at += chunk) {
+          const uint64_t n = std::min(chunk, bound[g + 1] - at);
+          if (cb_run(c, da, base + (at - bound[g]), n)) { errors[g] = cb_last_error(c); break; }
+          if (o.existence && !o.no_matrix) {
+            if (cb_get_matrix(c, matrix.data() + at * R2, n * R2)) { errors[g] = cb_last_error(c); break; }
+          }
+          if (o.pairs) {
+            uint64_t np = 0;
+            cb_pairs_pending(c, &np);
+            const size_t old = pair_out[g].size();
+            pair_out[g].resize(old + np);
+            size_t got = 0;
+            cb_drain_pairs(c, pair_out[g].data() + old, np, &got);
+            if (ngpu == 1) {  // single GPU: stream pairs out chunk by chunk
+              pw.write(pair_out[g].data(), pair_out[g].size());
+              pair_out[g].clear();
+            }
+          }
+        }
+        if (!self_dev) cb_free_set(c, da);
+      });
+    for (auto& t : th) t.join();
+  }
+  for (int g = 0; g < ngpu; g++)
+    if (!errors[g].empty()) {
+      fprintf(stderr, "\nError: %s\n", errors[g].c_str());
+      exit(1);
+    }
+  if (!o.existence && !o.no_matrix) {  // sum of the per-GPU partial matrices
+    std::vector<double> part(rows * R2);
+    for (int g = 0; g < ngpu; g++) {
+      if (bound[g + 1] == bound[g]) continue;
+      if (cb_get_matrix(ctx[g], part.data(), part.size())) engine_fatal(ctx[g]);
+      for (size_t k = 0; k < part.size(); k++) matrix[k] += part[k];
+    }
+  }
+  if (o.pairs && ngpu > 1)
+    for (int g = 0; g < ngpu; g++) pw.write(pair_out[g].data(), pair_out[g].size());
+  progress_end(o, "Analysing:        ");
+  for (int g = 0; g < ngpu; g++) {
+    cb_free_set(ctx[g], dev_b[g]);
+    cb_destroy(ctx[g]);
+  }
+
+  // ---- results (overlap.cc:540-577, 944-1039) ---------------------------------------------------
+  auto value = [&](uint64_t s, unsigned t) -> double {
+    const double x = matrix[R2 * s + t];
+    if (o.score == SCORE_MH) {
+      const double lx = s1.sq_count[s] / s1.count[s] / s1.count[s];
+      const double ly = s2.sq_count[t] / s2.count[t] / s2.count[t];
+      const double xy = 1.0 * s1.count[s] * s2.count[t];
+      return (2.0 * x) / ((lx + ly) * xy);
+    }
+    if (o.score == SCORE_JACCARD) {
+      const double sa = (double)s1.count[s], sb = (double)s2.count[t];
+      return x / (sa + sb - x);
+    }
+    return x;
+  };
+  if (!o.no_matrix) {
+    progress_begin(o, "Writing results:  ");
+    const uint64_t nrows = o.existence ? N1 : R1;
+    auto row_index = [&](uint64_t i) -> uint64_t { return o.existence ? i : s1.order[i]; };
+    auto row_name = [&](uint64_t i) -> const char* {
+      return o.existence ? d1.seq_id[i].c_str() : d1.rep_names[s1.order[i]].c_str();
+    };
+    if (o.alternative) {
+      fprintf(outfile, o.existence ? "#sequence_id_1\trepertoire_id_2\tmatches\n" : "#repertoire_id_1\trepertoire_id_2\tmatches\n");
+      for (uint64_t i = 0; i < nrows; i++)
+        for (unsigned j = 0; j < R2; j++)
+          fprintf(outfile, "%s\t%s\t%.10lg\n", row_name(i), d2.rep_names[s2.order[j]].c_str(),
+                  value(row_index(i), s2.order[j]));
+    } else {
+      fprintf(outfile, "#");
+      for (unsigned j = 0; j < R2; j++) fprintf(outfile, "\t%s", d2.rep_names[s2.order[j]].c_str());
+      fprintf(outfile, "\n");
+      for (uint64_t i = 0; i < nrows; i++) {
+        fprintf(outfile, "%s", row_name(i));
+        for (unsigned j = 0; j < R2; j++) fprintf(outfile, "\t%.10lg", value(row_index(i), s2.order[j]));
+        fprintf(outfile, "\n");
+      }
+    }
+    progress_end(o, "Writing results:  ");
+  }
+  fprintf(g_log, "\n");
+}

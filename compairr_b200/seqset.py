@@ -137,3 +137,43 @@ class SeqSet:
                     f.write("".join(lines))
                     lines = []
             f.write("".join(lines))
+
+
+def read_airr_tsv(path: str, nucleotides: bool = False, gene_maps=None, default_rep: str = "1",
+                  cdr3: bool = False) -> SeqSet:
+    """Minimal Python mirror of the reference reader (src/db.cc:172-901) for tests and tools:
+    header-driven columns, ids numbered in first-seen order.  The C++ CLI has the full reader."""
+    col = ("cdr3" if nucleotides else "cdr3_aa") if cdr3 else ("junction" if nucleotides else "junction_aa")
+    recs = []
+    with open(path) as f:
+        header = None
+        for line in f:
+            line = line.rstrip("\n").rstrip("\r")
+            if header is None:
+                if line.startswith("#") or line.startswith("@"):
+                    continue
+                header = {name: i for i, name in enumerate(line.split("\t"))}
+                continue
+            t = line.split("\t")
+
+            def get(name, default=""):
+                i = header.get(name)
+                return t[i] if i is not None and i < len(t) else default
+            recs.append((get("repertoire_id", default_rep) if "repertoire_id" in header else default_rep,
+                         get("sequence_id"), int(get("duplicate_count", "1") or 1), get("v_call"),
+                         get("j_call"), get(col)))
+    return SeqSet.from_records(recs, nucleotides, gene_maps)
+
+
+def read_airr_pair(path_a: str, path_b=None, nucleotides: bool = False):
+    """Both sets of a comparison with the shared V/J gene numbering (db.cc:119-125).
+    path_b None or equal to path_a is the self-comparison: returns (a, None)."""
+    maps = ({}, {})
+    a = read_airr_tsv(path_a, nucleotides, maps, default_rep="1")
+    b = None
+    if path_b is not None and path_b != path_a:
+        b = read_airr_tsv(path_b, nucleotides, maps, default_rep="2")
+    for s in (a, b):
+        if s is not None:
+            s.v_names, s.j_names = list(maps[0]), list(maps[1])
+    return a, b

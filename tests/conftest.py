@@ -13,6 +13,7 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
     # build the native pieces once if they are missing (cross-compiles without a GPU)
     need = [os.path.join(ROOT, "compairr_b200", "libcompairr_b200.so"),
+            os.path.join(ROOT, "compairr_b200", "bin", "compairr_b200"),
             os.path.join(ROOT, "oracle", "_build", "liboracle.so")]
     if not all(os.path.exists(p) for p in need):
         import __graft_entry__ as g
