@@ -57,6 +57,7 @@ SYMBOLS = [
     ("cb_set_stream", C.c_int, [P, P]),
     ("cb_upload", C.c_int, [P, C.POINTER(cb_set), C.POINTER(P)]),
     ("cb_free_set", None, [P, P]),
+    ("cb_rehash", C.c_int, [P, P]),
     ("cb_get_hashes", C.c_int, [P, P, P]),
     ("cb_build_b", C.c_int, [P, P]),
     ("cb_dups_b", C.c_uint64, [P]),
@@ -68,6 +69,7 @@ SYMBOLS = [
     ("cb_get_matrix", C.c_int, [P, P, C.c_size_t]),
     ("cb_clear_matrix", C.c_int, [P]),
     ("cb_matrix_device", P, [P]),
+    ("cb_bind_matrix", C.c_int, [P, P, C.c_uint64, C.c_uint64]),
     ("cb_set_matrix", C.c_int, [P, P, C.c_size_t]),
     ("cb_pairs_pending", C.c_int, [P, C.POINTER(C.c_uint64)]),
     ("cb_drain_pairs", C.c_int, [P, P, C.c_size_t, C.POINTER(C.c_size_t)]),

@@ -197,7 +197,7 @@ extern "C" void cb_destroy(cb_ctx* c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   cudaFree(c->d_table);
   cudaFree(c->d_bloom);
-  cudaFree(c->d_matrix);
+  if (!c->matrix_external) cudaFree(c->d_matrix);
   cudaFree(c->d_pairs);
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
@@ -328,6 +328,23 @@ extern "C" void cb_free_set(cb_ctx* c, cb_dset* s) {
     }
   }
   free_dset(s);
+}
+
+extern "C" int cb_rehash(cb_ctx* c, cb_dset* s) {
+  if (!c || !s) return fail(c, CB_ERR_INVALID, "cb_rehash: NULL argument");
+  int rc = bind(c);
+  if (rc) return rc;
+  if (s->n == 0) return CB_OK;
+  rc = ensure_ztab(c, s->longest + 2);
+  if (rc) return rc;
+  CU(c, cudaEventRecord(c->ev[0], c->stream));
+  launch_hash(s->d_meta, s->d_res, s->n, c->d_ztab, s->longest + 1, (uint32_t)c->cfg.alphabet_size,
+              c->cfg.seed, c->cfg.ignore_genes != 0, s->d_hash, c->stream);
+  CU(c, cudaGetLastError());
+  CU(c, cudaEventRecord(c->ev[1], c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  cudaEventElapsedTime(&c->stats.ms_hash_a, c->ev[0], c->ev[1]);
+  return CB_OK;
 }
 
 extern "C" int cb_get_hashes(cb_ctx* c, const cb_dset* s, uint64_t* out) {
@@ -462,6 +479,13 @@ extern "C" int cb_count_dups(cb_ctx* c, const cb_dset* s, uint64_t* out) {
 
 static int ensure_matrix(cb_ctx* c, uint64_t rows, uint64_t cols, bool reset) {
   if (c->cfg.no_matrix) return CB_OK;
+  if (c->matrix_external) {
+    if (c->rows != rows || c->cols != cols)
+      return fail(c, CB_ERR_INVALID, "bound matrix is %llu x %llu, this run needs %llu x %llu",
+                  (unsigned long long)c->rows, (unsigned long long)c->cols, (unsigned long long)rows,
+                  (unsigned long long)cols);
+    return CB_OK;
+  }
   if (c->d_matrix && c->rows == rows && c->cols == cols && !reset) return CB_OK;
   if (!c->d_matrix || c->rows * c->cols < rows * cols) {
     cudaFree(c->d_matrix);
@@ -683,6 +707,26 @@ extern "C" int cb_set_matrix(cb_ctx* c, const double* in, size_t n_values) {
   if (rc) return rc;
   CU(c, cudaMemcpyAsync(c->d_matrix, in, n_values * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
+  return CB_OK;
+}
+
+extern "C" int cb_bind_matrix(cb_ctx* c, void* device_ptr, uint64_t rows, uint64_t cols) {
+  if (!c) return CB_ERR_INVALID;
+  if (c->cfg.mode != CB_MODE_MATRIX || c->cfg.no_matrix)
+    return fail(c, CB_ERR_STATE, "cb_bind_matrix: only in matrix mode with a matrix");
+  int rc = bind(c);
+  if (rc) return rc;
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (!c->matrix_external) cudaFree(c->d_matrix);
+  c->d_matrix = nullptr;
+  c->rows = c->cols = 0;
+  c->matrix_external = false;
+  if (!device_ptr) return CB_OK;
+  if (rows != c->cfg.n_reps_a) return fail(c, CB_ERR_INVALID, "cb_bind_matrix: rows must equal n_reps_a");
+  c->d_matrix = (double*)device_ptr;
+  c->rows = rows;
+  c->cols = cols;
+  c->matrix_external = true;
   return CB_OK;
 }
 

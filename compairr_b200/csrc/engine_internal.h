@@ -51,6 +51,7 @@ struct cb_ctx {
   uint64_t dups_b = 0;
 
   double* d_matrix = nullptr;
+  bool matrix_external = false;
   uint64_t rows = 0, cols = 0;
 
   cb::PairOut* d_pairs = nullptr;

@@ -135,6 +135,9 @@ class Engine:
         self._check(cabi.lib.cb_upload(self._ctx, C.byref(cs), C.byref(h)))
         return DeviceSet(self, h, s.n, s.n_reps)
 
+    def rehash(self, d: DeviceSet):
+        self._check(cabi.lib.cb_rehash(self._ctx, d.handle))
+
     def hashes(self, d: DeviceSet) -> np.ndarray:
         out = np.zeros(d.n, dtype=np.uint64)
         self._check(cabi.lib.cb_get_hashes(self._ctx, d.handle, _ptr(out)))
@@ -173,6 +176,10 @@ class Engine:
     def set_matrix(self, m: np.ndarray):
         m = np.ascontiguousarray(m, dtype=np.float64)
         self._check(cabi.lib.cb_set_matrix(self._ctx, _ptr(m), m.size))
+
+    def bind_matrix(self, device_ptr: int, rows: int, cols: int):
+        """Accumulate into a caller-owned device buffer (e.g. a torch tensor's data_ptr())."""
+        self._check(cabi.lib.cb_bind_matrix(self._ctx, C.c_void_p(device_ptr), rows, cols))
 
     def clear_matrix(self):
         self._check(cabi.lib.cb_clear_matrix(self._ctx))

@@ -45,14 +45,6 @@ def _counts(rng, n):
     return np.maximum(np.floor(rng.pareto(1.2, n) + 1.0), 1).astype(np.uint64)
 
 
-def make_pool(seed: int, n: int):
-    rng = np.random.default_rng([seed, 0x9001])
-    lens = _lengths(rng, n)
-    res, off = _fresh(rng, lens)
-    return {"res": res, "off": off, "v": rng.integers(0, N_V, n, dtype=np.uint32),
-            "j": rng.integers(0, N_J, n, dtype=np.uint32)}
-
-
 def _derive(rng, pool, src, kind, sigma=20):
     """sequences derived from pool members src: kind 0 copy, 1 one substitution, 2 two
     substitutions, 3 one deletion, 4 one insertion -> (residues, offsets)"""
@@ -81,59 +73,80 @@ def _derive(rng, pool, src, kind, sigma=20):
     return res, off
 
 
+_POOLS = {}
+
+
+def make_pool(seed: int, n: int):
+    key = (seed, n)
+    if key not in _POOLS:
+        rng = np.random.default_rng([seed, 0x9001])
+        lens = _lengths(rng, n)
+        res, off = _fresh(rng, lens)
+        _POOLS.clear()   # keep at most one pool alive per process
+        _POOLS[key] = {"res": res, "off": off, "v": rng.integers(0, N_V, n, dtype=np.uint32),
+                       "j": rng.integers(0, N_J, n, dtype=np.uint32), "key": key}
+    return _POOLS[key]
+
+
+def _make_block(args):
+    """nr consecutive repertoires starting at r0 -> (residues, lengths, v, j, counts)"""
+    seed, r0, nr, per_rep, pool_key, k_pool, k_mut, indel_mutants = args
+    pool = make_pool(*pool_key)
+    n_pool = pool["v"].size
+    k_new = per_rep - k_pool - k_mut
+    rng = np.random.default_rng([seed, r0])
+    # pool members: without replacement inside a repertoire
+    src_pool = np.concatenate([rng.choice(n_pool, k_pool, replace=False) for _ in range(nr)]) if k_pool else np.zeros(0, np.int64)
+    src_mut = rng.integers(0, n_pool, nr * k_mut)
+    kinds_allowed = np.array([1, 2, 3, 4] if indel_mutants else [1, 2])
+    kind = np.concatenate([np.zeros(src_pool.size, np.int64), kinds_allowed[rng.integers(0, kinds_allowed.size, src_mut.size)]])
+    src = np.concatenate([src_pool, src_mut]).astype(np.int64)
+    dres, doff = _derive(rng, pool, src, kind)
+    flen = _lengths(rng, nr * k_new)
+    fres, foff = _fresh(rng, flen)
+    # per repertoire: [pool | mutants | fresh]
+    dl = np.diff(doff)
+    lens, chunks, v, j = [], [], [], []
+    for i in range(nr):
+        p0, p1 = i * k_pool, (i + 1) * k_pool
+        m0, m1 = nr * k_pool + i * k_mut, nr * k_pool + (i + 1) * k_mut
+        f0, f1 = i * k_new, (i + 1) * k_new
+        lens += [dl[p0:p1], dl[m0:m1], flen[f0:f1]]
+        chunks += [dres[doff[p0]:doff[p1]], dres[doff[m0]:doff[m1]], fres[foff[f0]:foff[f1]]]
+        v += [pool["v"][src_pool[p0:p1]], pool["v"][src_mut[i * k_mut:(i + 1) * k_mut]], rng.integers(0, N_V, k_new, dtype=np.uint32)]
+        j += [pool["j"][src_pool[p0:p1]], pool["j"][src_mut[i * k_mut:(i + 1) * k_mut]], rng.integers(0, N_J, k_new, dtype=np.uint32)]
+    return (np.concatenate(chunks), np.concatenate(lens).astype(np.int64), np.concatenate(v).astype(np.uint32),
+            np.concatenate(j).astype(np.uint32), _counts(rng, nr * per_rep))
+
+
 def make_set(seed: int, n_reps: int, per_rep: int, pool=None, pool_frac=0.2, mut_frac=0.2,
              indel_mutants=False, nucleotides=False, single_repertoire=False,
-             block_reps: int = 8) -> SeqSet:
-    """A set of n_reps repertoires with per_rep sequences each."""
+             block_reps: int = 8, workers: int = 1, first_rep: int = 0) -> SeqSet:
+    """A set of n_reps repertoires with per_rep sequences each.  Repertoire r of the set is a
+    pure function of (seed, first_rep + r, pool), so a shard of a bigger set can be generated on
+    its own (first_rep must be a multiple of block_reps)."""
     if pool is None:
         pool = make_pool(seed ^ 0x5EED, max(int(per_rep * (pool_frac + mut_frac)) * 4, 16))
     n_pool = pool["v"].size
     k_pool = min(int(per_rep * pool_frac), n_pool)
     k_mut = int(per_rep * mut_frac)
-    k_new = per_rep - k_pool - k_mut
-    parts_res, parts_len, parts_v, parts_j, parts_cnt = [], [], [], [], []
-    for r0 in range(0, n_reps, block_reps):
-        nr = min(block_reps, n_reps - r0)
-        rng = np.random.default_rng([seed, r0])
-        # pool members: without replacement inside a repertoire
-        src_pool = np.concatenate([rng.choice(n_pool, k_pool, replace=False) for _ in range(nr)]) if k_pool else np.zeros(0, np.int64)
-        src_mut = rng.integers(0, n_pool, nr * k_mut)
-        kinds_allowed = np.array([1, 2, 3, 4] if indel_mutants else [1, 2])
-        kind = np.concatenate([np.zeros(src_pool.size, np.int64), kinds_allowed[rng.integers(0, kinds_allowed.size, src_mut.size)]])
-        src = np.concatenate([src_pool, src_mut]).astype(np.int64)
-        dres, doff = _derive(rng, pool, src, kind)
-        flen = _lengths(rng, nr * k_new)
-        fres, foff = _fresh(rng, flen)
-        # interleave per repertoire: [pool | mutants | fresh] for each of the nr repertoires
-        dl = np.diff(doff)
-        lens = np.concatenate([np.concatenate([dl[i * k_pool:(i + 1) * k_pool],
-                                               dl[nr * k_pool + i * k_mut: nr * k_pool + (i + 1) * k_mut],
-                                               flen[i * k_new:(i + 1) * k_new]]) for i in range(nr)])
-        chunks = []
-        for i in range(nr):
-            chunks.append(dres[doff[i * k_pool]:doff[(i + 1) * k_pool]])
-            chunks.append(dres[doff[nr * k_pool + i * k_mut]:doff[nr * k_pool + (i + 1) * k_mut]])
-            chunks.append(fres[foff[i * k_new]:foff[(i + 1) * k_new]])
-        v = np.concatenate([np.concatenate([pool["v"][src_pool[i * k_pool:(i + 1) * k_pool]],
-                                            pool["v"][src_mut[i * k_mut:(i + 1) * k_mut]],
-                                            rng.integers(0, N_V, k_new, dtype=np.uint32)]) for i in range(nr)])
-        j = np.concatenate([np.concatenate([pool["j"][src_pool[i * k_pool:(i + 1) * k_pool]],
-                                            pool["j"][src_mut[i * k_mut:(i + 1) * k_mut]],
-                                            rng.integers(0, N_J, k_new, dtype=np.uint32)]) for i in range(nr)])
-        parts_res.append(np.concatenate(chunks))
-        parts_len.append(lens)
-        parts_v.append(v.astype(np.uint32))
-        parts_j.append(j.astype(np.uint32))
-        parts_cnt.append(_counts(rng, nr * per_rep))
-    lens = np.concatenate(parts_len)
-    res = np.concatenate(parts_res)
+    jobs = [(seed, first_rep + r0, min(block_reps, n_reps - r0), per_rep, pool["key"], k_pool, k_mut, indel_mutants)
+            for r0 in range(0, n_reps, block_reps)]
+    if workers > 1 and len(jobs) > 1:
+        import multiprocessing as mp
+        with mp.get_context("fork").Pool(min(workers, len(jobs))) as pl:
+            parts = pl.map(_make_block, jobs)
+    else:
+        parts = [_make_block(jb) for jb in jobs]
+    lens = np.concatenate([p[1] for p in parts])
+    res = np.concatenate([p[0] for p in parts])
     off = np.zeros(lens.size + 1, dtype=np.uint64)
     np.cumsum(lens, out=off[1:])
     rep = np.repeat(np.arange(n_reps, dtype=np.uint32), per_rep)
     if single_repertoire:
         rep[:] = 0
-    s = SeqSet(res, off, np.concatenate(parts_v), np.concatenate(parts_j), rep,
-               np.concatenate(parts_cnt), 1 if single_repertoire else n_reps)
+    s = SeqSet(res, off, np.concatenate([p[2] for p in parts]), np.concatenate([p[3] for p in parts]), rep,
+               np.concatenate([p[4] for p in parts]), 1 if single_repertoire else n_reps)
     return to_nucleotides(s, seed) if nucleotides else s
 
 

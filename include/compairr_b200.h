@@ -164,6 +164,9 @@ int cb_set_stream(cb_ctx *ctx, void *cuda_stream);
    (src/zobrist.cc:74-88).  The host arrays may be freed when the call returns. */
 int cb_upload(cb_ctx *ctx, const cb_set *set, cb_dset **out);
 void cb_free_set(cb_ctx *ctx, cb_dset *set);
+/* Recompute the hashes of a resident set (db_hash(), src/db.cc:903-916, on data already in
+   device memory). */
+int cb_rehash(cb_ctx *ctx, cb_dset *set);
 /* Copy the per-sequence hashes back (n entries) — for tests. */
 int cb_get_hashes(cb_ctx *ctx, const cb_dset *set, uint64_t *out);
 
@@ -203,6 +206,11 @@ int cb_clear_matrix(cb_ctx *ctx);
 /* Device pointer of the matrix (for an NCCL allreduce in the caller's process); valid until
    the next call that reallocates it (cb_run in existence mode) or cb_destroy. */
 void *cb_matrix_device(cb_ctx *ctx);
+/* Accumulate into a caller-owned DEVICE buffer of rows x cols doubles instead of the context's
+   own (matrix mode only; rows must equal n_reps_a).  Lets the caller's process run an NCCL
+   allreduce on its own allocation.  The buffer is not cleared and not freed by the engine;
+   NULL returns to the engine-owned matrix. */
+int cb_bind_matrix(cb_ctx *ctx, void *device_ptr, uint64_t rows, uint64_t cols);
 /* Host → device: overwrite the matrix (used after an external reduction). */
 int cb_set_matrix(cb_ctx *ctx, const double *in, size_t n_values);
 
