@@ -39,7 +39,7 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-POOL_SEED, POOL_N = 5, 400_000
+POOL_SEED = 5
 SEED_A, SEED_B = 2, 3
 
 
@@ -59,11 +59,12 @@ def parse():
     ap.add_argument("--sample-reps-a", type=int, default=10, help="reference sample: set-A repertoires")
     ap.add_argument("--sample-reps-b", type=int, default=50, help="reference sample: set-B repertoires")
     ap.add_argument("--workers", type=int, default=0, help="generator processes (0 = auto)")
+    ap.add_argument("--pool-n", type=int, default=4_000_000, help="size of the shared public pool")
     return ap.parse_args()
 
 
 def workload_name(a):
-    return (f"synthetic C3: B={a.reps_b}x{a.per_rep} AA, A={a.reps_a_per_gpu}x{a.per_rep} per GPU, "
+    return (f"synthetic C3: B={a.reps_b}x{a.per_rep} AA, A={a.reps_a_per_gpu}x{a.per_rep} per GPU, public pool {a.pool_n}, "
             f"-m -d {a.differences}{'' if a.no_indels or a.differences != 1 else ' -i'} -s product")
 
 
@@ -83,7 +84,7 @@ def reference_sample(a, steps, warmup):
     if not orc.have_reference():
         return None
     threads = max(1, min(os.cpu_count() or 1, 256))   # -t is capped at 256 (src/compairr.h:109)
-    pool = synth.make_pool(POOL_SEED, POOL_N)
+    pool = synth.make_pool(POOL_SEED, a.pool_n)
     indels = a.differences == 1 and not a.no_indels
     sa = synth.make_set(SEED_A, a.sample_reps_a, a.per_rep, pool=pool, indel_mutants=True, workers=n_workers(a))
     sb = synth.make_set(SEED_B, a.sample_reps_b, a.per_rep, pool=pool, indel_mutants=True, workers=n_workers(a))
@@ -226,7 +227,7 @@ def run_ours(a):
     indels = a.differences == 1 and not a.no_indels
 
     # ---- data: set B identical on every rank (rank 0 generates, the others read /dev/shm) ----------
-    pool = synth.make_pool(POOL_SEED, POOL_N)
+    pool = synth.make_pool(POOL_SEED, a.pool_n)
     t_gen = time.perf_counter()
     shm = f"/dev/shm/compairr_bench_B_{a.reps_b}x{a.per_rep}_{os.getuid()}"
     fields = ("residues", "offsets", "v_gene", "j_gene", "rep", "count")

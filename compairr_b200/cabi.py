@@ -20,7 +20,7 @@ class cb_config(C.Structure):
         ("ignore_counts", C.c_int32), ("score", C.c_int32), ("mode", C.c_int32),
         ("no_matrix", C.c_int32), ("want_pairs", C.c_int32), ("n_reps_a", C.c_uint32),
         ("seed", C.c_uint64), ("bloom_bits_per_key_x16", C.c_uint32), ("table_load_pct", C.c_uint32),
-        ("pairs_capacity", C.c_uint64), ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("pairs_capacity", C.c_uint64), ("flags", C.c_uint32), ("bloom_l2_cap_kib", C.c_uint32),
     ]
 
 
@@ -36,7 +36,7 @@ class cb_stats(C.Structure):
     _fields_ = [
         ("seeds", C.c_uint64), ("probes", C.c_uint64), ("bloom_pass", C.c_uint64),
         ("matches", C.c_uint64), ("pairs", C.c_uint64), ("table_slots", C.c_uint64),
-        ("bloom_bytes", C.c_uint64), ("ms_hash_b", C.c_float), ("ms_build_b", C.c_float),
+        ("bloom_bytes", C.c_uint64), ("bloom2_bytes", C.c_uint64), ("ms_hash_b", C.c_float), ("ms_build_b", C.c_float),
         ("ms_dups_b", C.c_float), ("ms_hash_a", C.c_float), ("ms_probe", C.c_float),
         ("ms_total_run", C.c_float), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
     ]

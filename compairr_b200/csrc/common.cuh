@@ -105,6 +105,12 @@ CB_HD uint32_t bloom_pat_hi(uint64_t h) {
   uint32_t x = (uint32_t)h;
   return (1u << ((x >> 15) & 31)) | (1u << ((x >> 20) & 31)) | (1u << ((x >> 25) & 31));
 }
+// Low-bits-per-key geometry of a capped first-level filter: one bit per half (k = 2).
+CB_HD uint32_t bloom1_pat_lo(uint64_t h) { return 1u << ((uint32_t)h & 31); }
+CB_HD uint32_t bloom1_pat_hi(uint64_t h) { return 1u << (((uint32_t)h >> 15) & 31); }
+CB_HD uint64_t bloom1_pattern(uint64_t h) {
+  return (uint64_t)bloom1_pat_lo(h) | ((uint64_t)bloom1_pat_hi(h) << 32);
+}
 CB_HD uint64_t bloom_pattern(uint64_t h) {
   return (uint64_t)bloom_pat_lo(h) | ((uint64_t)bloom_pat_hi(h) << 32);
 }

@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -151,6 +152,7 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   if (c->cfg.bloom_bits_per_key_x16 == 0) c->cfg.bloom_bits_per_key_x16 = 16 * 16;
   if (c->cfg.table_load_pct == 0 || c->cfg.table_load_pct > 90) c->cfg.table_load_pct = 50;
   if (c->cfg.pairs_capacity == 0) c->cfg.pairs_capacity = 1ull << 24;
+  if (c->cfg.bloom_l2_cap_kib == 0) c->cfg.bloom_l2_cap_kib = 40 * 1024;
   if (c->cfg.seed == 0) c->cfg.seed = 1;
   c->device = cfg->device;
 #define CU_CREATE(expr)                                                                  \
@@ -197,6 +199,7 @@ extern "C" void cb_destroy(cb_ctx* c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   cudaFree(c->d_table);
   cudaFree(c->d_bloom);
+  cudaFree(c->d_bloom2);
   if (!c->matrix_external) cudaFree(c->d_matrix);
   cudaFree(c->d_pairs);
   for (auto& ev : c->ev)
@@ -359,52 +362,67 @@ extern "C" int cb_get_hashes(cb_ctx* c, const cb_dset* s, uint64_t* out) {
 
 // ---- set B -------------------------------------------------------------------------------------
 
-static int build_table_for(cb_ctx* c, const cb_dset* s, bool with_bloom, Slot** table_out,
-                           uint64_t* slots_out, unsigned long long** bloom_out,
-                           uint32_t* blocks_out) {
-  uint64_t slots = 8;
-  while (slots * c->cfg.table_load_pct < s->n * 100) slots <<= 1;
+struct BuiltTable {
   Slot* table = nullptr;
+  uint64_t slots = 0;
   unsigned long long* bloom = nullptr;
   uint32_t blocks = 0;
-  CU(c, cudaMalloc(&table, slots * sizeof(Slot)));
-  if (with_bloom) {
-    // bits per key (fixed point /16) -> 64-bit blocks; any block count works (multiply-shift)
-    unsigned __int128 bits = (unsigned __int128)s->n * c->cfg.bloom_bits_per_key_x16 / 16;
-    uint64_t nb = (uint64_t)((bits + 63) / 64);
-    if (nb < 16) nb = 16;
-    if (nb > 0xffffffffull) nb = 0xffffffffull;
-    blocks = (uint32_t)nb;
-    cudaError_t e = cudaMalloc(&bloom, (size_t)blocks * 8);
-    if (e != cudaSuccess) {
-      cudaFree(table);
-      return fail(c, CB_ERR_NOMEM, "Bloom filter allocation: %s", cudaGetErrorString(e));
-    }
-    CU(c, cudaMemsetAsync(bloom, 0, (size_t)blocks * 8, c->stream));
-  }
-  launch_table_clear(table, slots, c->stream);
-  if (with_bloom) {
-    launch_build(s->d_hash, s->n, table, slots - 1, bloom, blocks, c->stream);
-  } else {
-    // a Bloom-less build still needs a valid pointer for the atomicOr; use a 16-block dummy
-    cudaError_t e = cudaMalloc(&bloom, 16 * 8);
-    if (e != cudaSuccess) {
-      cudaFree(table);
-      return fail(c, CB_ERR_NOMEM, "scratch allocation: %s", cudaGetErrorString(e));
-    }
-    blocks = 16;
-    launch_build(s->d_hash, s->n, table, slots - 1, bloom, blocks, c->stream);
-  }
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) {
+  bool k2 = false;
+  unsigned long long* bloom2 = nullptr;
+  uint32_t blocks2 = 0;
+  void release() {
     cudaFree(table);
     cudaFree(bloom);
-    return fail(c, CB_ERR_CUDA, "table build launch: %s", cudaGetErrorString(e));
+    cudaFree(bloom2);
+    *this = BuiltTable();
   }
-  *table_out = table;
-  *slots_out = slots;
-  *bloom_out = bloom;
-  *blocks_out = blocks;
+};
+
+static uint32_t blocks_for_bits(unsigned __int128 bits) {
+  unsigned __int128 nb = (bits + 63) / 64;
+  if (nb < 16) nb = 16;
+  if (nb > 0xffffffffull) nb = 0xffffffffull;
+  return (uint32_t)nb;
+}
+
+// Table + Bloom filter(s) over a resident set.  Filter policy (measured on B200): a
+// Bloom filter probed at random is L2-resident up to ~48 MiB; beyond that every probe is a 64-byte
+// DRAM access.  So the filter the enumeration loop tests is capped (default 40 MiB); when the cap
+// leaves fewer than 8 bits per key it switches to a 1+1-bit geometry and a second, full-size
+// filter in HBM is tested only by the first level's survivors.
+static int build_table_for(cb_ctx* c, const cb_dset* s, bool with_bloom, BuiltTable* out) {
+  BuiltTable t;
+  t.slots = 8;
+  while (t.slots * c->cfg.table_load_pct < s->n * 100) t.slots <<= 1;
+  CU(c, cudaMalloc(&t.table, t.slots * sizeof(Slot)));
+  const unsigned __int128 want_bits = (unsigned __int128)s->n * c->cfg.bloom_bits_per_key_x16 / 16;
+  const uint64_t cap_bytes = (uint64_t)c->cfg.bloom_l2_cap_kib << 10;
+  cudaError_t e = cudaSuccess;
+  if (!with_bloom) {
+    t.blocks = 16;  // the build kernel always sets a filter; give it a scratch one
+  } else if ((uint64_t)((want_bits + 7) / 8) <= cap_bytes) {
+    t.blocks = blocks_for_bits(want_bits);
+  } else {
+    t.blocks = (uint32_t)(cap_bytes / 8);
+    t.k2 = (double)cap_bytes * 8.0 / (double)s->n < 8.0;
+    const unsigned __int128 bits2 = t.k2 ? (unsigned __int128)s->n * 12 : want_bits;
+    t.blocks2 = blocks_for_bits(bits2);
+    e = cudaMalloc(&t.bloom2, (size_t)t.blocks2 * 8);
+    if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom2, 0, (size_t)t.blocks2 * 8, c->stream);
+  }
+  if (e == cudaSuccess) e = cudaMalloc(&t.bloom, (size_t)t.blocks * 8);
+  if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom, 0, (size_t)t.blocks * 8, c->stream);
+  if (e == cudaSuccess) {
+    launch_table_clear(t.table, t.slots, c->stream);
+    launch_build(s->d_hash, s->n, t.table, t.slots - 1, t.bloom, t.blocks, t.k2, t.bloom2, t.blocks2, c->stream);
+    e = cudaGetLastError();
+  }
+  if (e != cudaSuccess) {
+    t.release();
+    return fail(c, e == cudaErrorMemoryAllocation ? CB_ERR_NOMEM : CB_ERR_CUDA, "table/Bloom build: %s",
+                cudaGetErrorString(e));
+  }
+  *out = t;
   return CB_OK;
 }
 
@@ -417,10 +435,11 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
   c->b_owned = false;
   cudaFree(c->d_table);
   cudaFree(c->d_bloom);
+  cudaFree(c->d_bloom2);
   c->d_table = nullptr;
-  c->d_bloom = nullptr;
+  c->d_bloom = c->d_bloom2 = nullptr;
   c->slots = 0;
-  c->bloom_blocks = 0;
+  c->bloom_blocks = c->bloom2_blocks = 0;
   c->dups_b = 0;
   c->stats.ms_hash_b = c->stats.ms_hash_a;
   c->stats.ms_hash_a = 0;
@@ -428,8 +447,16 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
   c->stats.kernel_launches = 0;
   if (c->cfg.differences > MAXDIFF_HASH) return CB_OK;  // brute-force path: no table, no dup check
   CU(c, cudaEventRecord(c->ev[0], c->stream));
-  rc = build_table_for(c, b, true, &c->d_table, &c->slots, &c->d_bloom, &c->bloom_blocks);
+  BuiltTable bt;
+  rc = build_table_for(c, b, true, &bt);
   if (rc) return rc;
+  c->d_table = bt.table;
+  c->slots = bt.slots;
+  c->d_bloom = bt.bloom;
+  c->bloom_blocks = bt.blocks;
+  c->bloom_k2 = bt.k2;
+  c->d_bloom2 = bt.bloom2;
+  c->bloom2_blocks = bt.blocks2;
   CU(c, cudaEventRecord(c->ev[1], c->stream));
   rc = zero_counter(c, CTR_DUPS);
   if (rc) return rc;
@@ -444,6 +471,7 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
   cudaEventElapsedTime(&c->stats.ms_dups_b, c->ev[1], c->ev[2]);
   c->stats.table_slots = c->slots;
   c->stats.bloom_bytes = (uint64_t)c->bloom_blocks * 8;
+  c->stats.bloom2_bytes = (uint64_t)c->bloom2_blocks * 8;
   c->stats.kernel_launches = b->n ? 3 : 1;
   return CB_OK;
 }
@@ -456,20 +484,16 @@ extern "C" int cb_count_dups(cb_ctx* c, const cb_dset* s, uint64_t* out) {
   if (rc) return rc;
   *out = 0;
   if (s->n == 0) return CB_OK;
-  Slot* table = nullptr;
-  uint64_t slots = 0;
-  unsigned long long* bloom = nullptr;
-  uint32_t blocks = 0;
-  rc = build_table_for(c, s, false, &table, &slots, &bloom, &blocks);
+  BuiltTable bt;
+  rc = build_table_for(c, s, false, &bt);
   if (rc) return rc;
   rc = zero_counter(c, CTR_DUPS);
   if (!rc) {
-    launch_count_dups(cb_view_of(s), table, slots - 1, c->cfg.ignore_genes != 0, c->d_counters,
+    launch_count_dups(cb_view_of(s), bt.table, bt.slots - 1, c->cfg.ignore_genes != 0, c->d_counters,
                       c->stream);
     rc = read_counters(c);
   }
-  cudaFree(table);
-  cudaFree(bloom);
+  bt.release();
   if (rc) return rc;
   *out = c->h_counters[CTR_DUPS];
   return CB_OK;
@@ -556,6 +580,9 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     p.table_mask = c->slots - 1;
     p.bloom = c->d_bloom;
     p.bloom_blocks = c->bloom_blocks;
+    p.bloom_k2 = c->bloom_k2;
+    p.bloom2 = c->d_bloom2;
+    p.bloom2_blocks = c->bloom2_blocks;
     p.ztab = c->d_ztab;
     p.zrows = a->longest + 2;
     p.sigma = (uint32_t)c->cfg.alphabet_size;

@@ -46,8 +46,11 @@ struct cb_ctx {
   bool b_owned = false;
   cb::Slot* d_table = nullptr;
   uint64_t slots = 0;
-  unsigned long long* d_bloom = nullptr;
+  unsigned long long* d_bloom = nullptr;   // first level (L2-resident)
   uint32_t bloom_blocks = 0;
+  bool bloom_k2 = false;
+  unsigned long long* d_bloom2 = nullptr;  // second level (HBM), large sets only
+  uint32_t bloom2_blocks = 0;
   uint64_t dups_b = 0;
 
   double* d_matrix = nullptr;

@@ -45,10 +45,14 @@ __device__ __forceinline__ SeqMeta ld_meta(const SeqMeta* p) {
   return m;
 }
 
+
+// First-level filter test.  K2 = true: 1 bit per 32-bit half (the low-bits-per-key geometry used
+// when the filter is capped to stay L2-resident), else 3 + 3 bits.
 __device__ __forceinline__ bool bloom_test(const unsigned long long* __restrict__ bloom,
-                                           uint32_t nblocks, uint64_t h) {
+                                           uint32_t nblocks, uint64_t h, bool k2) {
   const unsigned long long w = __ldg(bloom + bloom_block(h, nblocks));
-  const uint32_t plo = bloom_pat_lo(h), phi = bloom_pat_hi(h);
+  const uint32_t plo = k2 ? bloom1_pat_lo(h) : bloom_pat_lo(h);
+  const uint32_t phi = k2 ? bloom1_pat_hi(h) : bloom_pat_hi(h);
   return (((uint32_t)w & plo) == plo) & (((uint32_t)(w >> 32) & phi) == phi);
 }
 
@@ -59,50 +63,91 @@ __device__ __forceinline__ uint64_t pack_variant(uint32_t kind, uint32_t pos1, u
          ((uint64_t)pos2 << 44);
 }
 
-// K4: walk the probe chain of hash hv; for every slot with an equal stored hash compare V/J,
-// verify the edit exactly, score, accumulate, append the pair.  Linear probing to the first
-// empty slot, every equal-hash slot is visited (overlap.cc:181-250).  Returns matches found.
-// Not inlined (keeps the enumeration loop's register footprint small) and always CALLED
-// warp-uniformly — lanes without work pass active = false.  A call from divergent code leaves
-// the warp split for the rest of the kernel (measured: 4 of 32 lanes active, profiles/r01),
-// so survivors of the Bloom test are first compacted into a per-warp queue and drained 32 at a
-// time (see variant_kernel).
-__device__ __noinline__ uint32_t table_probe(const ProbeParams* __restrict__ P, bool active,
-                                             uint64_t seed_idx, uint64_t seed_count, uint32_t slen,
-                                             uint32_t sv, uint32_t sj, uint32_t row,
-                                             const uint8_t* sres, uint64_t var, uint64_t hv) {
-  uint32_t found = 0;
-  if (!active) return 0;
+constexpr int VK_QCAP = 64;  // per-warp survivor queue entries (ring); drained 32 at a time
+
+// K4 for one lane's candidate hit: V/J compare, exact verify of the edit, score, accumulate,
+// pair append (overlap.cc:189-245).
+__device__ __forceinline__ uint32_t verify_and_record(const ProbeParams* __restrict__ P,
+                                                      uint64_t seed_idx, const SeqMeta& sm,
+                                                      uint32_t row, uint64_t var, uint64_t hit) {
+  const SeqMeta hm = ld_meta(P->b.meta + hit);
+  if (!P->ignore_genes && (hm.v != sm.v || hm.j != sm.j)) return 0;
+  const uint32_t kind = (uint32_t)(var & 0xff);
+  const uint32_t r1 = (uint32_t)(var >> 8) & 0xff, r2 = (uint32_t)(var >> 16) & 0xff;
+  const uint32_t pos1 = (uint32_t)(var >> 24) & 0xfffff, pos2 = (uint32_t)(var >> 44);
+  if (!verify_variant(P->a.res + sm.off, sm.len, P->b.res + hm.off, hm.len, kind, pos1, r1, pos2, r2))
+    return 0;
+  if (!P->no_matrix) {
+    const double sc = score_of(P->score, P->ignore_counts, sm.count, hm.count);
+    atomicAdd(P->matrix + (uint64_t)row * P->n_cols + hm.rep, sc);
+  }
+  if (P->want_pairs) {
+    const unsigned long long at = atomicAdd(P->counters + CTR_PAIRS, 1ull);
+    if (at < P->pairs_cap) {
+      PairOut po;
+      po.a = seed_idx + P->a.index_base;
+      po.b = hit + P->b.index_base;
+      P->pairs[at] = po;
+    }
+  }
+  return 1;
+}
+
+// K4: the slow path for up to 32 survivors of the first-level Bloom test, one per lane, always
+// called by the whole warp (a call from divergent code leaves the warp split for the rest of
+// the kernel — measured 4 of 32 lanes active, profiles/r01_*).  Per lane: optional second-level
+// Bloom test (the big filter in HBM), then linear probing to the first empty slot visiting every
+// slot with an equal stored hash (overlap.cc:181-250).  The chain walk is lane-divergent but
+// cheap; the expensive part — metadata + residue compare + atomics — runs re-converged, once per
+// round, for all lanes that hold a candidate.
+__device__ __noinline__ uint32_t drain32(const ProbeParams* __restrict__ P, const uint64_t* qhv,
+                                         const uint64_t* qvar, const uint32_t* qseed, uint32_t head,
+                                         uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31;
+  bool walking = lane < n;
+  const uint32_t e = (head + lane) & (VK_QCAP - 1);
+  uint64_t hv = 0, var = 0;
+  uint32_t slocal = 0;
+  if (walking) {
+    hv = qhv[e];
+    var = qvar[e];
+    slocal = qseed[e];
+  }
+  if (P->bloom2 != nullptr && walking) {
+    const unsigned long long w = __ldg(P->bloom2 + bloom_block(hv, P->bloom2_blocks));
+    const uint32_t plo = bloom_pat_lo(hv), phi = bloom_pat_hi(hv);
+    walking = (((uint32_t)w & plo) == plo) & (((uint32_t)(w >> 32) & phi) == phi);
+  }
   const uint64_t mask = P->table_mask;
+  const Slot* __restrict__ table = P->table;
   uint64_t slot = table_home(hv, mask);
-  for (;;) {
-    const Slot s = ld_slot(P->table + slot);
-    if (s.idx == SLOT_EMPTY) break;
-    if (s.hash == hv) {
-      const SeqMeta hm = ld_meta(P->b.meta + s.idx);
-      if (P->ignore_genes || (hm.v == sv && hm.j == sj)) {
-        const uint32_t kind = (uint32_t)(var & 0xff);
-        const uint32_t r1 = (uint32_t)(var >> 8) & 0xff, r2 = (uint32_t)(var >> 16) & 0xff;
-        const uint32_t pos1 = (uint32_t)(var >> 24) & 0xfffff, pos2 = (uint32_t)(var >> 44);
-        if (verify_variant(sres, slen, P->b.res + hm.off, hm.len, kind, pos1, r1, pos2, r2)) {
-          found++;
-          if (!P->no_matrix) {
-            const double sc = score_of(P->score, P->ignore_counts, seed_count, hm.count);
-            atomicAdd(P->matrix + (uint64_t)row * P->n_cols + hm.rep, sc);
-          }
-          if (P->want_pairs) {
-            const unsigned long long at = atomicAdd(P->counters + CTR_PAIRS, 1ull);
-            if (at < P->pairs_cap) {
-              PairOut po;
-              po.a = seed_idx + P->a.index_base;
-              po.b = s.idx + P->b.index_base;
-              P->pairs[at] = po;
-            }
-          }
-        }
+  const uint64_t sidx = P->a_first + slocal;
+  SeqMeta sm = {};
+  bool have_meta = false;
+  uint32_t found = 0;
+  while (__any_sync(FULL, walking)) {
+    bool cand = false;
+    uint64_t hit = 0;
+    while (walking) {
+      const Slot s = ld_slot(table + slot);
+      slot = (slot + 1) & mask;
+      if (s.idx == SLOT_EMPTY) {
+        walking = false;
+      } else if (s.hash == hv) {
+        cand = true;
+        hit = s.idx;
+        break;
       }
     }
-    slot = (slot + 1) & mask;
+    __syncwarp();
+    if (cand) {
+      if (!have_meta) {
+        sm = ld_meta(P->a.meta + sidx);
+        have_meta = true;
+      }
+      found += verify_and_record(P, sidx, sm, P->existence ? slocal : sm.rep, var, hit);
+    }
+    __syncwarp();
   }
   return found;
 }
@@ -222,7 +267,8 @@ void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st) {
 
 __global__ void __launch_bounds__(256)
 build_kernel(const uint64_t* __restrict__ hash, uint64_t n, Slot* table, uint64_t mask,
-             unsigned long long* bloom, uint32_t bloom_blocks) {
+             unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
+             uint32_t bloom2_blocks) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t h = hash[i];
@@ -236,16 +282,18 @@ build_kernel(const uint64_t* __restrict__ hash, uint64_t n, Slot* table, uint64_
       }
       slot = (slot + 1) & mask;
     }
-    atomicOr(bloom + bloom_block(h, bloom_blocks), bloom_pattern(h));
+    atomicOr(bloom + bloom_block(h, bloom_blocks), k2 ? bloom1_pattern(h) : bloom_pattern(h));
+    if (bloom2) atomicOr(bloom2 + bloom_block(h, bloom2_blocks), bloom_pattern(h));
   }
 }
 
 void launch_build(const uint64_t* hash, uint64_t n, Slot* table, uint64_t mask,
-                  unsigned long long* bloom, uint32_t bloom_blocks, cudaStream_t st) {
+                  unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
+                  uint32_t bloom2_blocks, cudaStream_t st) {
   if (n == 0) return;
   const uint64_t blocks = (n + 255) / 256;
   build_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
-      hash, n, table, mask, bloom, bloom_blocks);
+      hash, n, table, mask, bloom, bloom_blocks, k2, bloom2, bloom2_blocks);
 }
 
 // Exact duplicates: sequence i is a duplicate iff an identical sequence (same repertoire, same
@@ -326,23 +374,50 @@ void launch_count_probes(DeviceSetView a, uint64_t first, uint64_t count, uint32
 
 __global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ ProbeParams P) {
   uint32_t nmatch = 0, npass = 0;
-  // warp-uniform trip count, so the table_probe call below is made by all 32 lanes together
+  const uint32_t lane = threadIdx.x & 31;
+  const uint64_t mask = P.table_mask;
+  // warp-uniform trip count: the chain walk below re-converges with warp-wide votes
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); i0 < P.a_count;
        i0 += stride) {
-    const uint64_t i = i0 + (threadIdx.x & 31);
+    const uint64_t i = i0 + lane;
     const bool in = i < P.a_count;
     const uint64_t sidx = P.a_first + (in ? i : 0);
     const uint64_t h = P.a.hash[sidx];
-    bool pass = in;
-    if (P.use_bloom && in) pass = bloom_test(P.bloom, P.bloom_blocks, h);
-    npass += pass;
-    SeqMeta m = {};
-    if (pass) m = ld_meta(P.a.meta + sidx);
-    const uint32_t row = P.existence ? (uint32_t)i : m.rep;
-    nmatch += table_probe(&P, pass, sidx, m.count, m.len, m.v, m.j, row, P.a.res + m.off,
-                          pack_variant(VK_IDENTICAL, 0, 0, 0, 0), h);
-    __syncwarp();
+    bool walking = in;
+    if (P.use_bloom && in) {
+      walking = bloom_test(P.bloom, P.bloom_blocks, h, P.bloom_k2);
+      if (walking && P.bloom2 != nullptr) walking = bloom_test(P.bloom2, P.bloom2_blocks, h, false);
+    }
+    npass += walking;
+    uint64_t slot = table_home(h, mask);
+    SeqMeta sm = {};
+    bool have_meta = false;
+    while (__any_sync(FULL, walking)) {
+      bool cand = false;
+      uint64_t hit = 0;
+      while (walking) {
+        const Slot s = ld_slot(P.table + slot);
+        slot = (slot + 1) & mask;
+        if (s.idx == SLOT_EMPTY) {
+          walking = false;
+        } else if (s.hash == h) {
+          cand = true;
+          hit = s.idx;
+          break;
+        }
+      }
+      __syncwarp();
+      if (cand) {
+        if (!have_meta) {
+          sm = ld_meta(P.a.meta + sidx);
+          have_meta = true;
+        }
+        nmatch += verify_and_record(&P, sidx, sm, P.existence ? (uint32_t)i : sm.rep,
+                                    pack_variant(VK_IDENTICAL, 0, 0, 0, 0), hit);
+      }
+      __syncwarp();
+    }
   }
   flush_counters(P, nmatch, P.count_bloom ? npass : 0);
 }
@@ -362,8 +437,6 @@ __global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ 
 
 constexpr int VK_THREADS = 256;
 constexpr int VK_WARPS = VK_THREADS / 32;
-constexpr int VK_QCAP = 64;  // per-warp survivor queue entries (ring); drained 32 at a time
-
 __host__ __device__ inline uint32_t vk_lpad(uint32_t lmax) { return (lmax + 2 + 7) & ~7u; }
 __host__ __device__ inline size_t vk_warp_u64(uint32_t lmax, bool indels) {
   return (size_t)vk_lpad(lmax) * (indels ? 4 : 1) + 2 * VK_QCAP;  // scratch + queue hv/var
@@ -384,23 +457,8 @@ struct WarpQueue {
 };
 
 // Probe up to 32 queued survivors, one per lane; all 32 lanes make the call.
-__device__ __forceinline__ uint32_t queue_drain(const ProbeParams& P, WarpQueue& q, uint32_t lane,
-                                                uint32_t n) {
-  const bool act = lane < n;
-  const uint32_t e = (q.head + lane) & (VK_QCAP - 1);
-  uint64_t hv = 0, var = 0, sidx = P.a_first;
-  uint32_t slocal = 0;
-  SeqMeta m = {};
-  if (act) {
-    hv = q.hv[e];
-    var = q.var[e];
-    slocal = q.seed[e];
-    sidx = P.a_first + slocal;
-    m = ld_meta(P.a.meta + sidx);
-  }
-  const uint32_t row = P.existence ? slocal : m.rep;
-  const uint32_t found =
-      table_probe(&P, act, sidx, m.count, m.len, m.v, m.j, row, P.a.res + m.off, var, hv);
+__device__ __forceinline__ uint32_t queue_drain(const ProbeParams& P, WarpQueue& q, uint32_t n) {
+  const uint32_t found = drain32(&P, q.hv, q.var, q.seed, q.head, n);
   __syncwarp();
   q.head = (q.head + n) & (VK_QCAP - 1);
   q.count -= n;
@@ -418,10 +476,13 @@ __device__ __forceinline__ uint32_t queue_push(const ProbeParams& P, WarpQueue& 
     q.hv[e] = hv;
     q.var[e] = var;
     q.seed[e] = slocal;
+    // the drain will test the second-level filter (HBM): start that fetch now, towards L2
+    if (P.bloom2 != nullptr)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(P.bloom2 + bloom_block(hv, P.bloom2_blocks)));
   }
   q.count += __popc(m);
   __syncwarp();
-  return q.count >= 32 ? queue_drain(P, q, lane, 32) : 0;
+  return q.count >= 32 ? queue_drain(P, q, 32) : 0;
 }
 
 template <int SIGMA, bool INDELS, int D>
@@ -456,6 +517,7 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
   const uint32_t split_mask = P.split - 1;
   const uint32_t split_shift = 31 - __clz(P.split);
   const bool use_bloom = P.use_bloom;
+  const bool k2 = P.bloom_k2;
   uint32_t nmatch = 0, npass = 0;
 
   for (;;) {
@@ -569,7 +631,7 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
           if (use_bloom) {
 #pragma unroll
             for (int u = 0; u < 2; u++)
-              if (pass[u]) pass[u] = bloom_test(P.bloom, P.bloom_blocks, hv[u]);
+              if (pass[u]) pass[u] = bloom_test(P.bloom, P.bloom_blocks, hv[u], k2);
           }
 #pragma unroll
           for (int u = 0; u < 2; u++) {
@@ -609,7 +671,7 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
             if (use_bloom) {
 #pragma unroll
               for (int u = 0; u < 2; u++)
-                if (pass[u]) pass[u] = bloom_test(P.bloom, P.bloom_blocks, hv[u]);
+                if (pass[u]) pass[u] = bloom_test(P.bloom, P.bloom_blocks, hv[u], k2);
             }
 #pragma unroll
             for (int u = 0; u < 2; u++) {
@@ -623,7 +685,7 @@ variant_kernel(const __grid_constant__ ProbeParams P) {
     }
   }
   __syncwarp();
-  if (q.count) nmatch += queue_drain(P, q, lane, q.count);  // q.count < 32 here
+  if (q.count) nmatch += queue_drain(P, q, q.count);  // q.count < 32 here
   flush_counters(P, nmatch, P.count_bloom ? npass : 0);
 }
 

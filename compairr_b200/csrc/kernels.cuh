@@ -39,8 +39,10 @@ struct ProbeParams {
   uint64_t a_count;  // seeds in this launch
   const Slot* table;
   uint64_t table_mask;
-  const unsigned long long* bloom;
+  const unsigned long long* bloom;   // first-level filter (sized to stay L2-resident)
   uint32_t bloom_blocks;
+  uint32_t bloom2_blocks;
+  const unsigned long long* bloom2;  // second-level filter in HBM, or nullptr
   const uint64_t* ztab;  // global copy of the Zobrist table, zrows x sigma
   uint32_t zrows;        // rows staged in shared memory by the variant kernel (>= longest A + 1)
   uint32_t sigma;
@@ -57,6 +59,7 @@ struct ProbeParams {
   uint8_t want_pairs, use_bloom, count_bloom, matrix_only_pairs_off;
   int32_t differences;
   uint8_t indels;
+  uint8_t bloom_k2;    // first-level geometry: 1+1 bits instead of 3+3
 };
 
 // pack SoA upload into SeqMeta records, find the longest sequence
@@ -72,7 +75,8 @@ void launch_hash(const SeqMeta* meta, const uint8_t* res, uint64_t n, const uint
 // K2: table + Bloom build, duplicate count
 void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st);
 void launch_build(const uint64_t* hash, uint64_t n, Slot* table, uint64_t mask,
-                  unsigned long long* bloom, uint32_t bloom_blocks, cudaStream_t st);
+                  unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
+                  uint32_t bloom2_blocks, cudaStream_t st);
 void launch_count_dups(DeviceSetView s, const Slot* table, uint64_t mask, bool ignore_genes,
                        unsigned long long* counters, cudaStream_t st);
 

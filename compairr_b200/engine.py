@@ -43,6 +43,7 @@ class OverlapOptions:
     table_load_pct: int = 0
     pairs_capacity: int = 0
     flags: int = 0
+    bloom_l2_cap_kib: int = 0
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -96,6 +97,7 @@ class Engine:
         cfg.table_load_pct = opts.table_load_pct
         cfg.pairs_capacity = opts.pairs_capacity
         cfg.flags = opts.flags
+        cfg.bloom_l2_cap_kib = opts.bloom_l2_cap_kib
         self.opts = opts
         self._ctx = C.c_void_p()
         rc = cabi.lib.cb_create(C.byref(cfg), C.byref(self._ctx))

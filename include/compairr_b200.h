@@ -79,7 +79,8 @@ typedef struct cb_config {
   uint32_t table_load_pct;          /* max hash-table load in percent (default 50)               */
   uint64_t pairs_capacity;          /* device pair-buffer capacity per launch, in pairs          */
   uint32_t flags;                   /* CB_FLAG_*                                                  */
-  uint32_t reserved;
+  uint32_t bloom_l2_cap_kib;        /* first-level filter cap in KiB so it stays L2-resident     */
+                                    /* (default 40960); larger sets get a second-level HBM filter */
 } cb_config;
 
 #define CB_FLAG_NO_SMEM_TILE 1u   /* accumulate straight into the global matrix (A/B testing)    */
@@ -127,7 +128,8 @@ typedef struct cb_stats {
   uint64_t matches;         /* verified (seed, hit) matches (reference all_matches, overlap.cc:230) */
   uint64_t pairs;           /* pairs stored for cb_drain_pairs                                    */
   uint64_t table_slots;     /* hash-table slots                                                   */
-  uint64_t bloom_bytes;     /* Bloom bitmap bytes                                                 */
+  uint64_t bloom_bytes;     /* first-level Bloom bitmap bytes                                     */
+  uint64_t bloom2_bytes;    /* second-level (HBM) Bloom bitmap bytes, 0 if single-level          */
   float ms_hash_b;          /* device time, CUDA events on the engine's stream                    */
   float ms_build_b;
   float ms_dups_b;

@@ -28,7 +28,7 @@ def test_struct_layouts_match_header():
     # sizes are fixed by the header's field lists (LP64)
     assert ctypes.sizeof(cabi.cb_config) == 80
     assert ctypes.sizeof(cabi.cb_set) == 72
-    assert ctypes.sizeof(cabi.cb_stats) == 88
+    assert ctypes.sizeof(cabi.cb_stats) == 96
 
 
 def test_abi_version_and_no_cpu_fallback():

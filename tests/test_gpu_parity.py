@@ -84,3 +84,28 @@ def test_dups():
         eng.build_b(d)
         assert eng.dups_b() == orc.count_dups(a) > 0
         assert eng.count_dups(d) == orc.count_dups(a)
+
+
+@pytest.mark.parametrize("cap_kib,bpk", [(64, 16.0), (8, 16.0), (1, 4.0)])
+@pytest.mark.parametrize("d,indels", [(0, False), (1, True), (2, False)])
+def test_two_level_bloom_geometries(cap_kib, bpk, d, indels):
+    """Force the capped first-level filter (both the 3+3 and the 1+1 bit geometry) plus the
+    second-level filter on a small set: results must not depend on the filter layout."""
+    pool = synth.make_pool(31, 2000)
+    a = synth.make_set(32, 4, 1200, pool=pool, indel_mutants=True)
+    b = synth.make_set(33, 5, 1200, pool=pool, indel_mutants=True)
+    m, p, info = overlap(a, b, OverlapOptions(differences=d, indels=indels, want_pairs=True,
+                                              bloom_l2_cap_kib=cap_kib, bloom_bits_per_key=bpk))
+    mo, po, io = orc.overlap(a, b, differences=d, indels=indels, want_pairs=True)
+    assert np.array_equal(m, mo) and _pairs(p) == _pairs(po)
+    assert info["build"]["bloom_bytes"] <= max(cap_kib * 1024, 128)
+    if cap_kib <= 8:
+        assert info["build"]["bloom2_bytes"] > 0
+
+
+def test_no_bloom_flag_gives_same_result():
+    a = synth.small_dense_set(41, 3, 100)
+    b = synth.small_dense_set(42, 3, 100)
+    m0, _, _ = overlap(a, b, OverlapOptions(differences=1, indels=True))
+    m1, _, _ = overlap(a, b, OverlapOptions(differences=1, indels=True, flags=2))
+    assert np.array_equal(m0, m1)
