@@ -486,7 +486,7 @@ __device__ __forceinline__ uint32_t queue_push(const ProbeParams& P, WarpQueue& 
 }
 
 template <int SIGMA, bool INDELS, int D>
-__global__ void __launch_bounds__(VK_THREADS)
+__global__ void __launch_bounds__(VK_THREADS, 3)
 variant_kernel(const __grid_constant__ ProbeParams P) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* const z = reinterpret_cast<uint64_t*>(smem_raw);

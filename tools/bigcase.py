@@ -1,0 +1,36 @@
+"""Full-size case (B = 10^8) with the sets cached in /dev/shm so several library builds can be
+compared in one gpurun call.  usage: bigcase.py [d1|d2|both] [bpk]"""
+import sys, json, os
+sys.path.insert(0, ".")
+import numpy as np
+from compairr_b200 import Engine, OverlapOptions, synth
+from compairr_b200.seqset import SeqSet
+F = ("residues", "offsets", "v_gene", "j_gene", "rep", "count")
+def cached(name, make):
+    d = f"/dev/shm/cbig_{name}"
+    if os.path.isdir(d):
+        arr = {f: np.load(f"{d}/{f}.npy") for f in F}
+        return SeqSet(arr["residues"], arr["offsets"], arr["v_gene"], arr["j_gene"], arr["rep"], arr["count"], int(arr["rep"].max()) + 1)
+    s = make(); os.makedirs(d)
+    for f in F: np.save(f"{d}/{f}.npy", getattr(s, f))
+    return s
+pool = None
+def mk(seed, reps):
+    global pool
+    pool = pool or synth.make_pool(5, 4_000_000)
+    return synth.make_set(seed, reps, 100000, pool=pool, indel_mutants=True, workers=14)
+b = cached("b", lambda: mk(3, 1000)); a = cached("a", lambda: mk(2, 100))
+which = sys.argv[1] if len(sys.argv) > 1 else "both"
+bpk = float(sys.argv[2]) if len(sys.argv) > 2 else 16.0
+for d, ind in [(1, True), (2, False)]:
+    if which not in ("both", f"d{d}"): continue
+    with Engine(OverlapOptions(differences=d, indels=ind, bloom_bits_per_key=bpk), n_reps_a=a.n_reps) as eng:
+        db = eng.upload(b); eng.build_b(db); sb = eng.stats(); da = eng.upload(a)
+        n = a.n if d == 1 else 200000
+        best = None
+        for _ in range(2):
+            eng.clear_matrix(); eng.run(da, 0, n); s = eng.stats()
+            if best is None or s["ms_probe"] < best["ms_probe"]: best = s
+        print(json.dumps({"tag": os.environ.get("TAG", ""), "d": d, "ms_probe": round(best["ms_probe"], 2), "Gprobes_s": round(best["probes"] / best["ms_probe"] / 1e6, 1),
+                          "pass_pct": round(100 * best["bloom_pass"] / best["probes"], 2), "matches": best["matches"], "f1_MiB": sb["bloom_bytes"] >> 20, "f2_MiB": sb["bloom2_bytes"] >> 20,
+                          "ms_build": round(sb["ms_build_b"], 1), "ms_dups": round(sb["ms_dups_b"], 1)}), flush=True)
