@@ -1,0 +1,140 @@
+// device_utils.cuh — device-side helpers shared by kernels.cu and variant.cu.
+#pragma once
+#include "kernels.cuh"
+
+namespace cb {
+
+static constexpr unsigned FULL = 0xffffffffu;
+
+__device__ __forceinline__ Slot ld_slot(const Slot* p) {
+  const ulonglong2 v = __ldg(reinterpret_cast<const ulonglong2*>(p));  // one 128-bit load
+  Slot s;
+  s.hash = v.x;
+  s.idx = v.y;
+  return s;
+}
+
+__device__ __forceinline__ SeqMeta ld_meta(const SeqMeta* p) {
+  const ulonglong2 lo = __ldg(reinterpret_cast<const ulonglong2*>(p));
+  const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
+  SeqMeta m;
+  m.off = lo.x;
+  m.count = lo.y;
+  m.len = hi.x;
+  m.v = hi.y;
+  m.j = hi.z;
+  m.rep = hi.w;
+  return m;
+}
+
+// Filter word test.  K2 = true: 1 bit per 32-bit half (the low-bits-per-key geometry of a
+// first-level filter capped to stay L2-resident), else 3 + 3 bits.
+__device__ __forceinline__ bool bloom_word_test(unsigned long long w, uint64_t h, bool k2) {
+  const uint32_t plo = k2 ? bloom1_pat_lo(h) : bloom_pat_lo(h);
+  const uint32_t phi = k2 ? bloom1_pat_hi(h) : bloom_pat_hi(h);
+  return (((uint32_t)w & plo) == plo) & (((uint32_t)(w >> 32) & phi) == phi);
+}
+
+__device__ __forceinline__ bool bloom_test(const unsigned long long* __restrict__ bloom,
+                                           uint32_t nblocks, uint64_t h, bool k2) {
+  return bloom_word_test(__ldg(bloom + bloom_block(h, nblocks)), h, k2);
+}
+
+// Variant descriptor in 31 bits: kind(3) | res1(5) | res2(5) | pos1(9) | pos2(9).  Positions up to
+// 511, which the shared-memory budget of the variant kernels enforces anyway.
+constexpr uint32_t VAR_MAX_POS = 511;
+__device__ __forceinline__ uint32_t pack_var(uint32_t kind, uint32_t pos1, uint32_t r1, uint32_t pos2,
+                                             uint32_t r2) {
+  return kind | (r1 << 3) | (r2 << 8) | (pos1 << 13) | (pos2 << 22);
+}
+
+// K4 accumulate: shared-memory row tile when this match belongs to the CTA's current row, else
+// the global matrix.  Both are f64 atomics; integer-valued summands stay exact and order-free.
+__device__ __forceinline__ void accumulate(const ProbeParams* __restrict__ P, double* tile,
+                                           uint32_t tile_row, uint32_t row, uint32_t col, double sc) {
+  if (tile != nullptr && row == tile_row)
+    atomicAdd(tile + col, sc);
+  else
+    atomicAdd(P->matrix + (uint64_t)row * P->n_cols + col, sc);
+}
+
+// K4 for one lane's candidate hit: V/J compare, exact verify of the edit, score, accumulate,
+// pair append (overlap.cc:189-245).
+__device__ __forceinline__ uint32_t verify_and_record(const ProbeParams* __restrict__ P,
+                                                      uint64_t seed_idx, const SeqMeta& sm,
+                                                      uint32_t row, uint32_t var, uint64_t hit,
+                                                      double* tile, uint32_t tile_row) {
+  const SeqMeta hm = ld_meta(P->b.meta + hit);
+  if (!P->ignore_genes && (hm.v != sm.v || hm.j != sm.j)) return 0;
+  const uint32_t kind = var & 7, r1 = (var >> 3) & 31, r2 = (var >> 8) & 31;
+  const uint32_t pos1 = (var >> 13) & 511, pos2 = (var >> 22) & 511;
+  if (!verify_variant(P->a.res + sm.off, sm.len, P->b.res + hm.off, hm.len, kind, pos1, r1, pos2, r2))
+    return 0;
+  if (!P->no_matrix)
+    accumulate(P, tile, tile_row, row, hm.rep, score_of(P->score, P->ignore_counts, sm.count, hm.count));
+  if (P->want_pairs) {
+    const unsigned long long at = atomicAdd(P->counters + CTR_PAIRS, 1ull);
+    if (at < P->pairs_cap) {
+      PairOut po;
+      po.a = seed_idx + P->a.index_base;
+      po.b = hit + P->b.index_base;
+      P->pairs[at] = po;
+    }
+  }
+  return 1;
+}
+
+// Linear probing for up to 32 (hash, variant, seed) candidates, one per lane, executed by the
+// whole warp: lane-divergent chain walk (cheap: one 128-bit load per step, to the first empty
+// slot, visiting every slot with an equal stored hash, overlap.cc:181-250), then — re-converged by
+// warp votes, once per round — metadata, V/J, exact verify, score, atomics for every lane that
+// holds a candidate.
+__device__ __forceinline__ uint32_t probe_chains(const ProbeParams* __restrict__ P, bool walking,
+                                                 uint64_t hv, uint32_t var, uint64_t sidx,
+                                                 uint32_t exist_row, double* tile, uint32_t tile_row) {
+  const uint64_t mask = P->table_mask;
+  const Slot* __restrict__ table = P->table;
+  uint64_t slot = table_home(hv, mask);
+  SeqMeta sm = {};
+  bool have_meta = false;
+  uint32_t found = 0;
+  while (__any_sync(FULL, walking)) {
+    bool cand = false;
+    uint64_t hit = 0;
+    while (walking) {
+      const Slot s = ld_slot(table + slot);
+      slot = (slot + 1) & mask;
+      if (s.idx == SLOT_EMPTY) {
+        walking = false;
+      } else if (s.hash == hv) {
+        cand = true;
+        hit = s.idx;
+        break;
+      }
+    }
+    __syncwarp();
+    if (cand) {
+      if (!have_meta) {
+        sm = ld_meta(P->a.meta + sidx);
+        have_meta = true;
+      }
+      found += verify_and_record(P, sidx, sm, P->existence ? exist_row : sm.rep, var, hit, tile, tile_row);
+    }
+    __syncwarp();
+  }
+  return found;
+}
+
+__device__ __forceinline__ void flush_counters(const ProbeParams& P, uint32_t nmatch, uint32_t npass) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    nmatch += __shfl_xor_sync(FULL, nmatch, o);
+    npass += __shfl_xor_sync(FULL, npass, o);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    if (nmatch) atomicAdd(P.counters + CTR_MATCHES, (unsigned long long)nmatch);
+    if (npass) atomicAdd(P.counters + CTR_BLOOM_PASS, (unsigned long long)npass);
+  }
+}
+
+}  // namespace cb

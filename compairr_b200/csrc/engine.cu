@@ -535,6 +535,8 @@ static int ensure_pairs(cb_ctx* c, uint64_t cap) {
 extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count) {
   if (!c || !a) return fail(c, CB_ERR_INVALID, "cb_run: NULL argument");
   if (!c->b) return fail(c, CB_ERR_STATE, "cb_run: set B has not been built (cb_build_b / cb_set_b)");
+  if (count >= 0xffffffffull)
+    return fail(c, CB_ERR_LIMIT, "cb_run: at most 2^32-1 sequences per call; run the set in chunks");
   if (first > a->n || count > a->n - first)
     return fail(c, CB_ERR_INVALID, "cb_run: range [%llu, +%llu) outside the set (%llu sequences)",
                 (unsigned long long)first, (unsigned long long)count, (unsigned long long)a->n);
@@ -593,6 +595,9 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     p.pairs_cap = c->pairs_cap;
     p.counters = c->d_counters;
     p.lmax = a->longest;
+    // one matrix row in shared memory per CTA (d=1 kernel) when it is small enough
+    p.tile_cols = (!existence && !c->cfg.no_matrix && !(c->cfg.flags & CB_FLAG_NO_SMEM_TILE) && cols <= 4096)
+                      ? (uint32_t)cols : 0;
     p.score = c->cfg.score;
     p.ignore_counts = c->cfg.ignore_counts != 0;
     p.ignore_genes = c->cfg.ignore_genes != 0;

@@ -53,6 +53,7 @@ struct ProbeParams {
   uint64_t pairs_cap;
   unsigned long long* counters;
   uint32_t lmax;   // longest seed in the launch (sizes the per-warp scratch)
+  uint32_t tile_cols;  // > 0: CTAs keep one matrix row (n_cols doubles) in shared memory
   uint32_t split;  // d=2: work items per seed
   int32_t score;
   uint8_t ignore_counts, ignore_genes, existence, no_matrix;

@@ -42,7 +42,7 @@ class OverlapOptions:
     bloom_bits_per_key: float = 0.0
     table_load_pct: int = 0
     pairs_capacity: int = 0
-    flags: int = 0
+    flags: int = int(__import__("os").environ.get("CB_FLAGS", "0"))
     bloom_l2_cap_kib: int = 0
 
 
