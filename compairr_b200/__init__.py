@@ -8,7 +8,7 @@ Layout (only what the path needs):
   seqset.py        sequence sets in structure-of-arrays form, AIRR TSV <-> arrays
   synth.py         seeded synthetic repertoires
 """
-from .seqset import SeqSet, encode_sequences, AA_ALPHABET, NT_ALPHABET  # noqa: F401
+from .seqset import SeqSet, NarrowSet, encode_sequences, AA_ALPHABET, NT_ALPHABET  # noqa: F401
 from .engine import Engine, OverlapOptions, overlap, SCORES  # noqa: F401
 
 __all__ = ["SeqSet", "Engine", "OverlapOptions", "overlap", "SCORES", "encode_sequences"]

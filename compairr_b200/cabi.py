@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libcompairr_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 
 class cb_config(C.Structure):
@@ -28,6 +28,18 @@ class cb_set(C.Structure):
     _fields_ = [
         ("n", C.c_uint64), ("residues", C.c_void_p), ("offsets", C.c_void_p),
         ("v_gene", C.c_void_p), ("j_gene", C.c_void_p), ("rep", C.c_void_p), ("count", C.c_void_p),
+        ("n_reps", C.c_uint32), ("longest", C.c_uint32), ("index_base", C.c_uint64),
+    ]
+
+
+class cb_col(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("width", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class cb_set_cols(C.Structure):
+    _fields_ = [
+        ("n", C.c_uint64), ("residues", C.c_void_p), ("offsets", cb_col), ("lengths", cb_col),
+        ("v_gene", cb_col), ("j_gene", cb_col), ("rep", cb_col), ("count", cb_col),
         ("n_reps", C.c_uint32), ("longest", C.c_uint32), ("index_base", C.c_uint64),
     ]
 
@@ -56,6 +68,7 @@ SYMBOLS = [
     ("cb_last_error", C.c_char_p, [P]),
     ("cb_set_stream", C.c_int, [P, P]),
     ("cb_upload", C.c_int, [P, C.POINTER(cb_set), C.POINTER(P)]),
+    ("cb_upload_cols", C.c_int, [P, C.POINTER(cb_set_cols), C.POINTER(P)]),
     ("cb_free_set", None, [P, P]),
     ("cb_rehash", C.c_int, [P, P]),
     ("cb_get_hashes", C.c_int, [P, P, P]),
@@ -64,7 +77,9 @@ SYMBOLS = [
     ("cb_count_dups", C.c_int, [P, P, C.POINTER(C.c_uint64)]),
     ("cb_run", C.c_int, [P, P, C.c_uint64, C.c_uint64]),
     ("cb_set_b", C.c_int, [P, C.POINTER(cb_set)]),
+    ("cb_set_b_cols", C.c_int, [P, C.POINTER(cb_set_cols)]),
     ("cb_run_a", C.c_int, [P, C.POINTER(cb_set)]),
+    ("cb_run_a_cols", C.c_int, [P, C.POINTER(cb_set_cols)]),
     ("cb_matrix_dims", C.c_int, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("cb_get_matrix", C.c_int, [P, P, C.c_size_t]),
     ("cb_clear_matrix", C.c_int, [P]),

@@ -244,25 +244,25 @@ static int bucket_sort(cb_ctx* c, DeviceSetView v, uint64_t first, uint64_t n, u
   void* tmp = nullptr;
   unsigned long long* d_gmax = nullptr;
   auto cleanup = [&]() {
-    cudaFree(k_in); cudaFree(k_out); cudaFree(u_keys); cudaFree(u_cnt);
-    cudaFree(i_in); cudaFree(d_nruns); cudaFree(tmp); cudaFree(d_gmax);
+    cb_dfree(k_in); cb_dfree(k_out); cb_dfree(u_keys); cb_dfree(u_cnt);
+    cb_dfree(i_in); cb_dfree(d_nruns); cb_dfree(tmp); cb_dfree(d_gmax);
   };
 #define BCU2(expr)                                                                           \
   do {                                                                                       \
     cudaError_t e__ = (expr);                                                                \
     if (e__ != cudaSuccess) {                                                                \
       cleanup();                                                                             \
-      cudaFree(i_out);                                                                       \
+      cb_dfree(i_out);                                                                       \
       std::string m__ = std::string(#expr) + ": " + cudaGetErrorString(e__);                 \
       return cb_fail(c, e__ == cudaErrorMemoryAllocation ? CB_ERR_NOMEM : CB_ERR_CUDA, "%s", \
                      m__.c_str());                                                           \
     }                                                                                        \
   } while (0)
-  BCU2(cudaMalloc(&k_in, n * 8));
-  BCU2(cudaMalloc(&k_out, n * 8));
-  BCU2(cudaMalloc(&i_in, n * 4));
-  BCU2(cudaMalloc(&i_out, n * 4));
-  BCU2(cudaMalloc(&d_gmax, 8));
+  BCU2(cb_dmalloc(&k_in, n * 8));
+  BCU2(cb_dmalloc(&k_out, n * 8));
+  BCU2(cb_dmalloc(&i_in, n * 4));
+  BCU2(cb_dmalloc(&i_out, n * 4));
+  BCU2(cb_dmalloc(&d_gmax, 8));
   BCU2(cudaMemsetAsync(d_gmax, 0, 8, st));
   const uint64_t blocks = (n + 255) / 256;
   bucket_key_kernel<<<(unsigned)std::min<uint64_t>(blocks, 148 * 16), 256, 0, st>>>(
@@ -270,17 +270,17 @@ static int bucket_sort(cb_ctx* c, DeviceSetView v, uint64_t first, uint64_t n, u
   BCU2(cudaGetLastError());
   size_t tmp_bytes = 0;
   BCU2(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k_in, k_out, i_in, i_out, (int64_t)n, 0, 64, st));
-  BCU2(cudaMalloc(&tmp, tmp_bytes));
+  BCU2(cb_dmalloc(&tmp, tmp_bytes));
   BCU2(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k_in, k_out, i_in, i_out, (int64_t)n, 0, 64, st));
-  cudaFree(tmp);
+  cb_dfree(tmp);
   tmp = nullptr;
   // run-length encode the sorted keys -> bucket directory
-  BCU2(cudaMalloc(&u_keys, n * 8));
-  BCU2(cudaMalloc(&u_cnt, n * 8));
-  BCU2(cudaMalloc(&d_nruns, 8));
+  BCU2(cb_dmalloc(&u_keys, n * 8));
+  BCU2(cb_dmalloc(&u_cnt, n * 8));
+  BCU2(cb_dmalloc(&d_nruns, 8));
   tmp_bytes = 0;
   BCU2(cub::DeviceRunLengthEncode::Encode(nullptr, tmp_bytes, k_out, u_keys, u_cnt, d_nruns, (int64_t)n, st));
-  BCU2(cudaMalloc(&tmp, tmp_bytes));
+  BCU2(cb_dmalloc(&tmp, tmp_bytes));
   BCU2(cub::DeviceRunLengthEncode::Encode(tmp, tmp_bytes, k_out, u_keys, u_cnt, d_nruns, (int64_t)n, st));
   uint64_t nruns = 0;
   unsigned long long gmax = 0;
@@ -289,7 +289,7 @@ static int bucket_sort(cb_ctx* c, DeviceSetView v, uint64_t first, uint64_t n, u
   BCU2(cudaStreamSynchronize(st));
   if (gmax >= (1ull << 22)) {
     cleanup();
-    cudaFree(i_out);
+    cb_dfree(i_out);
     return cb_fail(c, CB_ERR_LIMIT, "more than 2^22 distinct V or J genes on the d>=3 path");
   }
   keys.resize(nruns);
@@ -326,9 +326,9 @@ static int cb_build_brute_b(cb_ctx* c, cb_dset* b) {
   }
   if (v.n == 0) return CB_OK;
   uint64_t *d_starts = nullptr, *d_poff = nullptr;
-  BCU(c, cudaMalloc(packed, std::max<uint64_t>((*pack_off)[nb], 1) * 4));
-  BCU(c, cudaMalloc(&d_starts, (nb + 1) * 8));
-  BCU(c, cudaMalloc(&d_poff, (nb + 1) * 8));
+  BCU(c, cb_dmalloc(packed, std::max<uint64_t>((*pack_off)[nb], 1) * 4));
+  BCU(c, cb_dmalloc(&d_starts, (nb + 1) * 8));
+  BCU(c, cb_dmalloc(&d_poff, (nb + 1) * 8));
   BCU(c, cudaMemcpyAsync(d_starts, starts->data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
   BCU(c, cudaMemcpyAsync(d_poff, pack_off->data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
   const uint64_t blocks = (v.n + 255) / 256;
@@ -336,8 +336,8 @@ static int cb_build_brute_b(cb_ctx* c, cb_dset* b) {
       v.meta, v.res, *order, d_starts, d_poff, (uint32_t)nb, v.n, *packed);
   BCU(c, cudaGetLastError());
   BCU(c, cudaStreamSynchronize(st));
-  cudaFree(d_starts);
-  cudaFree(d_poff);
+  cb_dfree(d_starts);
+  cb_dfree(d_poff);
   return CB_OK;
 }
 
@@ -409,7 +409,7 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
       tiles += (uint64_t)J.tiles_a * J.tiles_b;
     }
     BruteJoin* d_joins = nullptr;
-    BCU(c, cudaMalloc(&d_joins, js.size() * sizeof(BruteJoin)));
+    BCU(c, cb_dmalloc(&d_joins, js.size() * sizeof(BruteJoin)));
     BCU(c, cudaMemcpyAsync(d_joins, js.data(), js.size() * sizeof(BruteJoin), cudaMemcpyHostToDevice, st));
     BruteLaunch L{};
     L.a = cb_view_of(a);
@@ -456,8 +456,8 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
       }
       (*launches)++;
     }
-    cudaFree(d_joins);
+    cb_dfree(d_joins);
   }
-  cudaFree(a_order);
+  cb_dfree(a_order);
   return ret;
 }

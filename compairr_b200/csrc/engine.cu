@@ -32,11 +32,23 @@ int cb_fail(cb_ctx* c, int code, const char* fmt, ...) {
   return code;
 }
 #define fail cb_fail
+#define ensure_ztab cb_ensure_ztab
 
-static int bind(cb_ctx* c) {
+static thread_local cudaStream_t g_alloc_stream = nullptr;
+
+cudaError_t cb_dmalloc_raw(void** p, size_t bytes) {
+  *p = nullptr;
+  return cudaMallocAsync(p, bytes ? bytes : 1, g_alloc_stream);
+}
+
+cudaError_t cb_dfree(void* p) { return p ? cudaFreeAsync(p, g_alloc_stream) : cudaSuccess; }
+
+int cb_bind_device(cb_ctx* c) {
   CU(c, cudaSetDevice(c->device));
+  g_alloc_stream = c->stream;
   return CB_OK;
 }
+#define bind cb_bind_device
 
 static int read_counters(cb_ctx* c) {
   CU(c, cudaMemcpyAsync(c->h_counters, c->d_counters, CTR_COUNT * sizeof(unsigned long long),
@@ -52,7 +64,7 @@ static int zero_counter(cb_ctx* c, int which) {
 
 // Zobrist table for positions 0..rows-1.  Values depend only on (seed, position, residue), so
 // growing the table never changes a hash that was already computed.
-static int ensure_ztab(cb_ctx* c, uint32_t rows) {
+int cb_ensure_ztab(cb_ctx* c, uint32_t rows) {
   if (rows <= c->zrows) return CB_OK;
   rows = (rows + 15) & ~15u;
   const uint32_t sigma = (uint32_t)c->cfg.alphabet_size;
@@ -60,15 +72,15 @@ static int ensure_ztab(cb_ctx* c, uint32_t rows) {
   for (uint32_t p = 0; p < rows; p++)
     for (uint32_t r = 0; r < sigma; r++) h[(size_t)p * sigma + r] = zobrist_gen(c->cfg.seed, p, r);
   uint64_t* d = nullptr;
-  CU(c, cudaMalloc(&d, h.size() * sizeof(uint64_t)));
+  CU(c, cb_dmalloc(&d, h.size() * sizeof(uint64_t)));
   cudaError_t e = cudaMemcpyAsync(d, h.data(), h.size() * sizeof(uint64_t),
                                   cudaMemcpyHostToDevice, c->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
   if (e != cudaSuccess) {
-    cudaFree(d);
+    cb_dfree(d);
     return fail(c, CB_ERR_CUDA, "Zobrist table upload: %s", cudaGetErrorString(e));
   }
-  if (c->d_ztab) cudaFree(c->d_ztab);
+  if (c->d_ztab) cb_dfree(c->d_ztab);
   c->d_ztab = d;
   c->zrows = rows;
   return CB_OK;
@@ -168,10 +180,18 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   cudaDeviceProp prop;
   CU_CREATE(cudaGetDeviceProperties(&prop, c->device));
   c->sm_count = prop.multiProcessorCount;
+  {
+    cudaMemPool_t pool;
+    CU_CREATE(cudaDeviceGetDefaultMemPool(&pool, c->device));
+    uint64_t keep = ~0ull;  // never hand cached blocks back to the driver between calls
+    CU_CREATE(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+  }
   CU_CREATE(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+  CU_CREATE(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
+  g_alloc_stream = c->stream;
   for (auto& ev : c->ev) CU_CREATE(cudaEventCreate(&ev));
-  CU_CREATE(cudaMalloc(&c->d_counters, CTR_COUNT * sizeof(unsigned long long)));
+  CU_CREATE(cb_dmalloc(&c->d_counters, CTR_COUNT * sizeof(unsigned long long)));
   CU_CREATE(cudaMemset(c->d_counters, 0, CTR_COUNT * sizeof(unsigned long long)));
   CU_CREATE(cudaMallocHost(&c->h_counters, CTR_COUNT * sizeof(unsigned long long)));
 #undef CU_CREATE
@@ -179,32 +199,41 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   return CB_OK;
 }
 
-static void free_dset(cb_dset* s) {
+void cb_free_dset(cb_dset* s) {
   if (!s) return;
-  cudaFree(s->d_meta);
-  cudaFree(s->d_res);
-  cudaFree(s->d_hash);
-  cudaFree(s->d_order);
-  cudaFree(s->d_packed);
+  cb_dfree(s->d_meta);
+  cb_dfree(s->d_res);
+  cb_dfree(s->d_hash);
+  cb_dfree(s->d_order);
+  cb_dfree(s->d_packed);
   delete s;
 }
 
 extern "C" void cb_destroy(cb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
+  g_alloc_stream = c->stream ? c->stream : c->own_stream;
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
-  if (c->b_owned) free_dset(c->b);
-  cudaFree(c->d_ztab);
-  cudaFree(c->d_counters);
+  if (c->stream && c->stream != c->own_stream) cudaStreamSynchronize(c->stream);
+  if (c->b_owned) cb_free_dset(c->b);
+  cb_dfree(c->d_ztab);
+  cb_dfree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
-  cudaFree(c->d_table);
-  cudaFree(c->d_bloom);
-  cudaFree(c->d_bloom2);
-  if (!c->matrix_external) cudaFree(c->d_matrix);
-  cudaFree(c->d_pairs);
+  cb_dfree(c->d_table);
+  cb_dfree(c->d_bloom);
+  cb_dfree(c->d_bloom2);
+  if (!c->matrix_external) cb_dfree(c->d_matrix);
+  cb_dfree(c->d_pairs);
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
+  if (g_alloc_stream) cudaStreamSynchronize(g_alloc_stream);
+  {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
+  }
+  g_alloc_stream = nullptr;
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
 }
 
@@ -212,125 +241,25 @@ extern "C" const char* cb_last_error(const cb_ctx* c) { return c ? c->err.c_str(
 
 extern "C" int cb_set_stream(cb_ctx* c, void* s) {
   if (!c) return CB_ERR_INVALID;
+  cudaStreamSynchronize(c->stream);
   c->stream = s ? (cudaStream_t)s : c->own_stream;
+  g_alloc_stream = c->stream;
   return CB_OK;
 }
 
-// ---- upload + hash -----------------------------------------------------------------------------
-
-extern "C" int cb_upload(cb_ctx* c, const cb_set* set, cb_dset** out) {
-  if (!c || !set || !out) return fail(c, CB_ERR_INVALID, "cb_upload: NULL argument");
-  *out = nullptr;
-  if (set->n && (!set->residues || !set->offsets))
-    return fail(c, CB_ERR_INVALID, "cb_upload: residues/offsets are NULL");
-  if (set->n && !c->cfg.ignore_genes && (!set->v_gene || !set->j_gene))
-    return fail(c, CB_ERR_INVALID, "cb_upload: v_gene/j_gene are NULL but ignore_genes is off");
-  if (set->n && !c->cfg.ignore_counts && !set->count)
-    return fail(c, CB_ERR_INVALID, "cb_upload: count is NULL but ignore_counts is off");
-  if (set->n >= 0xffffffffull && c->cfg.differences > MAXDIFF_HASH)
-    return fail(c, CB_ERR_LIMIT, "cb_upload: more than 2^32-1 sequences in one set");
-  int rc = bind(c);
-  if (rc) return rc;
-  cb_dset* s = new (std::nothrow) cb_dset;
-  if (!s) return fail(c, CB_ERR_NOMEM, "cb_upload: out of host memory");
-  s->n = set->n;
-  s->index_base = set->index_base;
-  s->n_reps = set->n_reps;
-  const uint64_t n = set->n;
-  if (n == 0) {
-    *out = s;
-    return CB_OK;
-  }
-  const uint64_t off_base = set->offsets[0];
-  s->res_bytes = set->offsets[n] - off_base;
-
-  uint64_t* t_off = nullptr;
-  uint32_t *t_v = nullptr, *t_j = nullptr, *t_rep = nullptr;
-  uint64_t* t_cnt = nullptr;
-  auto cleanup = [&]() {
-    cudaFree(t_off);
-    cudaFree(t_v);
-    cudaFree(t_j);
-    cudaFree(t_rep);
-    cudaFree(t_cnt);
-  };
-#define CU_UP(expr)                                                                          \
-  do {                                                                                       \
-    cudaError_t e__ = (expr);                                                                \
-    if (e__ != cudaSuccess) {                                                                \
-      cleanup();                                                                             \
-      free_dset(s);                                                                          \
-      return fail(c, e__ == cudaErrorMemoryAllocation ? CB_ERR_NOMEM : CB_ERR_CUDA, "%s: %s", \
-                  #expr, cudaGetErrorString(e__));                                           \
-    }                                                                                        \
-  } while (0)
-  const bool genes = !c->cfg.ignore_genes && set->v_gene && set->j_gene;
-  CU_UP(cudaMalloc(&s->d_res, s->res_bytes + 16));
-  CU_UP(cudaMalloc(&s->d_meta, n * sizeof(SeqMeta)));
-  CU_UP(cudaMalloc(&s->d_hash, n * sizeof(uint64_t)));
-  CU_UP(cudaMalloc(&t_off, (n + 1) * sizeof(uint64_t)));
-  if (genes) {
-    CU_UP(cudaMalloc(&t_v, n * sizeof(uint32_t)));
-    CU_UP(cudaMalloc(&t_j, n * sizeof(uint32_t)));
-  }
-  if (set->rep) CU_UP(cudaMalloc(&t_rep, n * sizeof(uint32_t)));
-  if (set->count) CU_UP(cudaMalloc(&t_cnt, n * sizeof(uint64_t)));
-  cudaStream_t st = c->stream;
-  CU_UP(cudaMemcpyAsync(s->d_res, set->residues + off_base, s->res_bytes, cudaMemcpyHostToDevice, st));
-  CU_UP(cudaMemcpyAsync(t_off, set->offsets, (n + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  if (genes) {
-    CU_UP(cudaMemcpyAsync(t_v, set->v_gene, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-    CU_UP(cudaMemcpyAsync(t_j, set->j_gene, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-  }
-  if (set->rep)
-    CU_UP(cudaMemcpyAsync(t_rep, set->rep, n * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-  if (set->count)
-    CU_UP(cudaMemcpyAsync(t_cnt, set->count, n * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-  CU_UP(cudaMemsetAsync(c->d_counters + CTR_MAXLEN, 0, sizeof(unsigned long long), st));
-  launch_pack_meta(t_off, t_v, t_j, t_rep, t_cnt, n, off_base, s->d_meta, c->d_counters, st);
-  CU_UP(cudaGetLastError());
-  CU_UP(cudaMemcpyAsync(c->h_counters, c->d_counters, CTR_COUNT * sizeof(unsigned long long),
-                        cudaMemcpyDeviceToHost, st));
-  CU_UP(cudaStreamSynchronize(st));
-  cleanup();
-  t_off = nullptr;
-  t_v = t_j = t_rep = nullptr;
-  t_cnt = nullptr;
-  s->longest = (uint32_t)c->h_counters[CTR_MAXLEN];
-  if (s->longest >= (1u << 20)) {
-    free_dset(s);
-    return fail(c, CB_ERR_LIMIT, "cb_upload: sequence longer than 2^20 residues");
-  }
-  rc = ensure_ztab(c, s->longest + 2);
-  if (rc) {
-    free_dset(s);
-    return rc;
-  }
-  CU_UP(cudaEventRecord(c->ev[0], st));
-  launch_hash(s->d_meta, s->d_res, n, c->d_ztab, s->longest + 1,
-              (uint32_t)c->cfg.alphabet_size, c->cfg.seed, c->cfg.ignore_genes != 0, s->d_hash, st);
-  CU_UP(cudaGetLastError());
-  CU_UP(cudaEventRecord(c->ev[1], st));
-  CU_UP(cudaStreamSynchronize(st));
-  float ms = 0;
-  cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
-  c->stats.ms_hash_a = ms;  // the caller decides whether this was set A or set B
-#undef CU_UP
-  *out = s;
-  return CB_OK;
-}
+// ---- upload + hash: see upload.cu ----------------------------------------------------------------
 
 extern "C" void cb_free_set(cb_ctx* c, cb_dset* s) {
   if (!s) return;
   if (c) {
-    cudaSetDevice(c->device);
+    cb_bind_device(c);
     cudaStreamSynchronize(c->stream);
     if (c->b == s) {
       c->b = nullptr;
       c->b_owned = false;
     }
   }
-  free_dset(s);
+  cb_free_dset(s);
 }
 
 extern "C" int cb_rehash(cb_ctx* c, cb_dset* s) {
@@ -362,22 +291,6 @@ extern "C" int cb_get_hashes(cb_ctx* c, const cb_dset* s, uint64_t* out) {
 
 // ---- set B -------------------------------------------------------------------------------------
 
-struct BuiltTable {
-  Slot* table = nullptr;
-  uint64_t slots = 0;
-  unsigned long long* bloom = nullptr;
-  uint32_t blocks = 0;
-  bool k2 = false;
-  unsigned long long* bloom2 = nullptr;
-  uint32_t blocks2 = 0;
-  void release() {
-    cudaFree(table);
-    cudaFree(bloom);
-    cudaFree(bloom2);
-    *this = BuiltTable();
-  }
-};
-
 static uint32_t blocks_for_bits(unsigned __int128 bits) {
   unsigned __int128 nb = (bits + 63) / 64;
   if (nb < 16) nb = 16;
@@ -385,17 +298,17 @@ static uint32_t blocks_for_bits(unsigned __int128 bits) {
   return (uint32_t)nb;
 }
 
-// Table + Bloom filter(s) over a resident set.  Filter policy (measured on B200): a
-// Bloom filter probed at random is L2-resident up to ~48 MiB; beyond that every probe is a 64-byte
-// DRAM access.  So the filter the enumeration loop tests is capped (default 40 MiB); when the cap
+// Table + Bloom filter(s) sized for n keys.  Filter policy (measured on B200): a Bloom
+// filter probed at random is L2-resident up to ~48 MiB; beyond that every probe is a 64-byte DRAM
+// access.  So the filter the enumeration loop tests is capped (default 40 MiB); when the cap
 // leaves fewer than 8 bits per key it switches to a 1+1-bit geometry and a second, full-size
 // filter in HBM is tested only by the first level's survivors.
-static int build_table_for(cb_ctx* c, const cb_dset* s, bool with_bloom, BuiltTable* out) {
+int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
   BuiltTable t;
   t.slots = 8;
-  while (t.slots * c->cfg.table_load_pct < s->n * 100) t.slots <<= 1;
-  CU(c, cudaMalloc(&t.table, t.slots * sizeof(Slot)));
-  const unsigned __int128 want_bits = (unsigned __int128)s->n * c->cfg.bloom_bits_per_key_x16 / 16;
+  while (t.slots * c->cfg.table_load_pct < n * 100) t.slots <<= 1;
+  CU(c, cb_dmalloc(&t.table, t.slots * sizeof(Slot)));
+  const unsigned __int128 want_bits = (unsigned __int128)n * c->cfg.bloom_bits_per_key_x16 / 16;
   const uint64_t cap_bytes = (uint64_t)c->cfg.bloom_l2_cap_kib << 10;
   cudaError_t e = cudaSuccess;
   if (!with_bloom) {
@@ -404,61 +317,66 @@ static int build_table_for(cb_ctx* c, const cb_dset* s, bool with_bloom, BuiltTa
     t.blocks = blocks_for_bits(want_bits);
   } else {
     t.blocks = (uint32_t)(cap_bytes / 8);
-    t.k2 = (double)cap_bytes * 8.0 / (double)s->n < 8.0;
-    const unsigned __int128 bits2 = t.k2 ? (unsigned __int128)s->n * 12 : want_bits;
+    t.k2 = (double)cap_bytes * 8.0 / (double)n < 8.0;
+    const unsigned __int128 bits2 = t.k2 ? (unsigned __int128)n * 12 : want_bits;
     t.blocks2 = blocks_for_bits(bits2);
-    e = cudaMalloc(&t.bloom2, (size_t)t.blocks2 * 8);
+    e = cb_dmalloc(&t.bloom2, (size_t)t.blocks2 * 8);
     if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom2, 0, (size_t)t.blocks2 * 8, c->stream);
   }
-  if (e == cudaSuccess) e = cudaMalloc(&t.bloom, (size_t)t.blocks * 8);
+  if (e == cudaSuccess) e = cb_dmalloc(&t.bloom, (size_t)t.blocks * 8);
   if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom, 0, (size_t)t.blocks * 8, c->stream);
   if (e == cudaSuccess) {
     launch_table_clear(t.table, t.slots, c->stream);
-    launch_build(s->d_hash, s->n, t.table, t.slots - 1, t.bloom, t.blocks, t.k2, t.bloom2, t.blocks2, c->stream);
     e = cudaGetLastError();
   }
   if (e != cudaSuccess) {
     t.release();
-    return fail(c, e == cudaErrorMemoryAllocation ? CB_ERR_NOMEM : CB_ERR_CUDA, "table/Bloom build: %s",
+    return fail(c, e == cudaErrorMemoryAllocation ? CB_ERR_NOMEM : CB_ERR_CUDA, "table/Bloom allocation: %s",
                 cudaGetErrorString(e));
   }
   *out = t;
   return CB_OK;
 }
 
-extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
-  if (!c || !b) return fail(c, CB_ERR_INVALID, "cb_build_b: NULL argument");
-  int rc = bind(c);
+// Insert sequences [first, first + n) (hashes at d_hash[first..]) into the table and filter(s).
+void cb_table_insert(cb_ctx* c, const BuiltTable& t, const uint64_t* d_hash, uint64_t first, uint64_t n) {
+  launch_build(d_hash + first, first, n, t.table, t.slots - 1, t.bloom, t.blocks, t.k2, t.bloom2, t.blocks2,
+               c->stream);
+}
+
+static int build_table_for(cb_ctx* c, const cb_dset* s, bool with_bloom, BuiltTable* out) {
+  int rc = cb_table_alloc(c, s->n, with_bloom, out);
   if (rc) return rc;
-  if (c->b_owned && c->b != b) free_dset(c->b);
+  cb_table_insert(c, *out, s->d_hash, 0, s->n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    out->release();
+    return fail(c, CB_ERR_CUDA, "table build launch: %s", cudaGetErrorString(e));
+  }
+  return CB_OK;
+}
+
+// Make t the context's set-B structure and count the exact duplicates (dup2).
+int cb_adopt_table(cb_ctx* c, cb_dset* b, BuiltTable& t, bool owned) {
+  if (c->b_owned && c->b != b) cb_free_dset(c->b);
   c->b = b;
-  c->b_owned = false;
-  cudaFree(c->d_table);
-  cudaFree(c->d_bloom);
-  cudaFree(c->d_bloom2);
-  c->d_table = nullptr;
-  c->d_bloom = c->d_bloom2 = nullptr;
-  c->slots = 0;
-  c->bloom_blocks = c->bloom2_blocks = 0;
+  c->b_owned = owned;
+  cb_dfree(c->d_table);
+  cb_dfree(c->d_bloom);
+  cb_dfree(c->d_bloom2);
+  c->d_table = t.table;
+  c->slots = t.slots;
+  c->d_bloom = t.bloom;
+  c->bloom_blocks = t.blocks;
+  c->bloom_k2 = t.k2;
+  c->d_bloom2 = t.bloom2;
+  c->bloom2_blocks = t.blocks2;
+  t = BuiltTable();
   c->dups_b = 0;
-  c->stats.ms_hash_b = c->stats.ms_hash_a;
-  c->stats.ms_hash_a = 0;
-  c->stats.ms_build_b = c->stats.ms_dups_b = 0;
-  c->stats.kernel_launches = 0;
-  if (c->cfg.differences > MAXDIFF_HASH) return CB_OK;  // brute-force path: no table, no dup check
-  CU(c, cudaEventRecord(c->ev[0], c->stream));
-  BuiltTable bt;
-  rc = build_table_for(c, b, true, &bt);
-  if (rc) return rc;
-  c->d_table = bt.table;
-  c->slots = bt.slots;
-  c->d_bloom = bt.bloom;
-  c->bloom_blocks = bt.blocks;
-  c->bloom_k2 = bt.k2;
-  c->d_bloom2 = bt.bloom2;
-  c->bloom2_blocks = bt.blocks2;
+  c->stats.ms_dups_b = 0;
+  if (!c->d_table) return CB_OK;
   CU(c, cudaEventRecord(c->ev[1], c->stream));
-  rc = zero_counter(c, CTR_DUPS);
+  int rc = zero_counter(c, CTR_DUPS);
   if (rc) return rc;
   launch_count_dups(cb_view_of(b), c->d_table, c->slots - 1, c->cfg.ignore_genes != 0, c->d_counters,
                     c->stream);
@@ -467,12 +385,34 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
   rc = read_counters(c);
   if (rc) return rc;
   c->dups_b = c->h_counters[CTR_DUPS];
-  cudaEventElapsedTime(&c->stats.ms_build_b, c->ev[0], c->ev[1]);
   cudaEventElapsedTime(&c->stats.ms_dups_b, c->ev[1], c->ev[2]);
   c->stats.table_slots = c->slots;
   c->stats.bloom_bytes = (uint64_t)c->bloom_blocks * 8;
   c->stats.bloom2_bytes = (uint64_t)c->bloom2_blocks * 8;
-  c->stats.kernel_launches = b->n ? 3 : 1;
+  return CB_OK;
+}
+
+extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
+  if (!c || !b) return fail(c, CB_ERR_INVALID, "cb_build_b: NULL argument");
+  int rc = bind(c);
+  if (rc) return rc;
+  c->stats.ms_hash_b = c->stats.ms_hash_a;
+  c->stats.ms_hash_a = 0;
+  c->stats.ms_build_b = c->stats.ms_dups_b = 0;
+  c->stats.kernel_launches = 0;
+  BuiltTable bt;
+  if (c->cfg.differences <= MAXDIFF_HASH) {  // the brute-force path has no table and no dup check
+    CU(c, cudaEventRecord(c->ev[0], c->stream));
+    rc = build_table_for(c, b, true, &bt);
+    if (rc) return rc;
+    CU(c, cudaEventRecord(c->ev[6], c->stream));
+  }
+  rc = cb_adopt_table(c, b, bt, c->b == b ? c->b_owned : false);
+  if (rc) return rc;
+  if (c->d_table) {
+    cudaEventElapsedTime(&c->stats.ms_build_b, c->ev[0], c->ev[6]);
+    c->stats.kernel_launches = b->n ? 3 : 1;
+  }
   return CB_OK;
 }
 
@@ -512,9 +452,9 @@ static int ensure_matrix(cb_ctx* c, uint64_t rows, uint64_t cols, bool reset) {
   }
   if (c->d_matrix && c->rows == rows && c->cols == cols && !reset) return CB_OK;
   if (!c->d_matrix || c->rows * c->cols < rows * cols) {
-    cudaFree(c->d_matrix);
+    cb_dfree(c->d_matrix);
     c->d_matrix = nullptr;
-    CU(c, cudaMalloc(&c->d_matrix, std::max<uint64_t>(rows * cols, 1) * sizeof(double)));
+    CU(c, cb_dmalloc(&c->d_matrix, std::max<uint64_t>(rows * cols, 1) * sizeof(double)));
   }
   c->rows = rows;
   c->cols = cols;
@@ -524,10 +464,10 @@ static int ensure_matrix(cb_ctx* c, uint64_t rows, uint64_t cols, bool reset) {
 
 static int ensure_pairs(cb_ctx* c, uint64_t cap) {
   if (c->pairs_cap >= cap) return CB_OK;
-  cudaFree(c->d_pairs);
+  cb_dfree(c->d_pairs);
   c->d_pairs = nullptr;
   c->pairs_cap = 0;
-  CU(c, cudaMalloc(&c->d_pairs, cap * sizeof(PairOut)));
+  CU(c, cb_dmalloc(&c->d_pairs, cap * sizeof(PairOut)));
   c->pairs_cap = cap;
   return CB_OK;
 }
@@ -681,32 +621,6 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
   return CB_OK;
 }
 
-extern "C" int cb_set_b(cb_ctx* c, const cb_set* b) {
-  cb_dset* d = nullptr;
-  int rc = cb_upload(c, b, &d);
-  if (rc) return rc;
-  rc = cb_build_b(c, d);
-  if (rc) {
-    free_dset(d);
-    if (c->b == d) c->b = nullptr;
-    return rc;
-  }
-  c->b_owned = true;
-  return CB_OK;
-}
-
-extern "C" int cb_run_a(cb_ctx* c, const cb_set* a) {
-  cb_dset* d = nullptr;
-  int rc = cb_upload(c, a, &d);
-  if (rc) return rc;
-  const float ms_hash = c->stats.ms_hash_a;
-  rc = cb_run(c, d, 0, d->n);
-  c->stats.ms_hash_a = ms_hash;
-  cudaStreamSynchronize(c->stream);
-  free_dset(d);
-  return rc;
-}
-
 // ---- results -----------------------------------------------------------------------------------
 
 extern "C" int cb_matrix_dims(const cb_ctx* c, uint64_t* rows, uint64_t* cols) {
@@ -749,7 +663,7 @@ extern "C" int cb_bind_matrix(cb_ctx* c, void* device_ptr, uint64_t rows, uint64
   int rc = bind(c);
   if (rc) return rc;
   CU(c, cudaStreamSynchronize(c->stream));
-  if (!c->matrix_external) cudaFree(c->d_matrix);
+  if (!c->matrix_external) cb_dfree(c->d_matrix);
   c->d_matrix = nullptr;
   c->rows = c->cols = 0;
   c->matrix_external = false;

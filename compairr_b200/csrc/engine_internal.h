@@ -27,12 +27,38 @@ struct cb_dset {
   std::vector<uint64_t> pack_off;      // n_buckets + 1 word offsets into d_packed
 };
 
+// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with an unlimited
+// release threshold: repeated set-B builds and set-A uploads reuse cached blocks instead of paying
+// cudaMalloc/cudaFree of multi-GB buffers every call (that was ~100 ms per bench step).  Ordered
+// on the stream of the context bound to the calling thread (cb_bind_device).
+cudaError_t cb_dmalloc_raw(void** p, size_t bytes);
+template <typename T>
+static inline cudaError_t cb_dmalloc(T** p, size_t bytes) { return cb_dmalloc_raw(reinterpret_cast<void**>(p), bytes); }
+cudaError_t cb_dfree(void* p);
+
+struct BuiltTable {
+  cb::Slot* table = nullptr;
+  uint64_t slots = 0;
+  unsigned long long* bloom = nullptr;
+  uint32_t blocks = 0;
+  bool k2 = false;
+  unsigned long long* bloom2 = nullptr;
+  uint32_t blocks2 = 0;
+  void release() {
+    cb_dfree(table);
+    cb_dfree(bloom);
+    cb_dfree(bloom2);
+    *this = BuiltTable();
+  }
+};
+
 struct cb_ctx {
   cb_config cfg{};
   int device = 0;
   int sm_count = 148;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // H2D side of the pipelined upload
   cudaEvent_t ev[8]{};
   std::string err;
 
@@ -74,6 +100,14 @@ cb::DeviceSetView cb_view_of(const cb_dset* s);
       return cb_fail((c), e__ == cudaErrorMemoryAllocation ? CB_ERR_NOMEM : CB_ERR_CUDA,   \
                      "%s: %s", #expr, cudaGetErrorString(e__));                            \
   } while (0)
+
+// engine.cu
+int cb_bind_device(cb_ctx* c);
+int cb_ensure_ztab(cb_ctx* c, uint32_t rows);
+int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out);
+void cb_table_insert(cb_ctx* c, const BuiltTable& t, const uint64_t* d_hash, uint64_t first, uint64_t n);
+int cb_adopt_table(cb_ctx* c, cb_dset* b, BuiltTable& t, bool owned);  // sets ctx fields, counts dups
+void cb_free_dset(cb_dset* s);
 
 // brute.cu
 int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bool pairs_only,

@@ -23,22 +23,49 @@ namespace cb {
 // pack_meta
 // ---------------------------------------------------------------------------------------------
 
+__device__ __forceinline__ uint64_t col_load(const void* p, uint32_t w, uint64_t i) {
+  switch (w) {
+    case 1: return reinterpret_cast<const uint8_t*>(p)[i];
+    case 2: return reinterpret_cast<const uint16_t*>(p)[i];
+    case 4: return reinterpret_cast<const uint32_t*>(p)[i];
+    default: return reinterpret_cast<const uint64_t*>(p)[i];
+  }
+}
+
+// Lengths of any width -> u64 (input of the device prefix sum that turns lengths into offsets).
+__global__ void __launch_bounds__(256) widen_kernel(const void* __restrict__ src, uint32_t w, uint64_t n,
+                                                    uint64_t* __restrict__ dst) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    dst[i] = col_load(src, w, i);
+}
+
+void launch_widen(const void* src, uint32_t w, uint64_t n, uint64_t* dst, cudaStream_t st) {
+  if (n == 0) return;
+  const uint64_t blocks = (n + 255) / 256;
+  widen_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(src, w, n, dst);
+}
+
+// One chunk of the upload: columns of caller-chosen widths -> SeqMeta records.  starts[i] is the
+// first residue of sequence i: either offsets[i] - off_sub (offsets mode) or scan[i] + res_add
+// (lengths mode, scan = exclusive prefix sum of the chunk's lengths).
 __global__ void __launch_bounds__(256)
-pack_meta_kernel(const uint64_t* __restrict__ offsets, const uint32_t* __restrict__ v,
-                 const uint32_t* __restrict__ j, const uint32_t* __restrict__ rep,
-                 const uint64_t* __restrict__ count, uint64_t n, uint64_t off_base,
-                 SeqMeta* __restrict__ out, unsigned long long* counters) {
+pack_meta_kernel(PackCols k, uint64_t n, SeqMeta* __restrict__ out, unsigned long long* counters) {
   uint32_t mymax = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t o0 = offsets[i], o1 = offsets[i + 1];
     SeqMeta m;
-    m.off = o0 - off_base;
-    m.len = (uint32_t)(o1 - o0);
-    m.count = count ? count[i] : 1ull;
-    m.v = v ? v[i] : 0u;
-    m.j = j ? j[i] : 0u;
-    m.rep = rep ? rep[i] : 0u;
+    if (k.lengths) {
+      m.off = k.starts[i] + k.res_add;
+      m.len = (uint32_t)col_load(k.lengths, k.len_w, i);
+    } else {
+      const uint64_t o0 = k.starts[i], o1 = k.starts[i + 1];
+      m.off = o0 - k.off_sub;
+      m.len = (uint32_t)(o1 - o0);
+    }
+    m.count = k.count ? col_load(k.count, k.count_w, i) : 1ull;
+    m.v = k.v ? (uint32_t)col_load(k.v, k.v_w, i) : 0u;
+    m.j = k.j ? (uint32_t)col_load(k.j, k.j_w, i) : 0u;
+    m.rep = k.rep ? (uint32_t)col_load(k.rep, k.rep_w, i) : 0u;
     out[i] = m;
     mymax = max(mymax, m.len);
   }
@@ -47,13 +74,11 @@ pack_meta_kernel(const uint64_t* __restrict__ offsets, const uint32_t* __restric
   if ((threadIdx.x & 31) == 0 && mymax) atomicMax(counters + CTR_MAXLEN, (unsigned long long)mymax);
 }
 
-void launch_pack_meta(const uint64_t* offsets, const uint32_t* v, const uint32_t* j,
-                      const uint32_t* rep, const uint64_t* count, uint64_t n, uint64_t off_base,
-                      SeqMeta* out, unsigned long long* counters, cudaStream_t st) {
+void launch_pack_meta(const PackCols& k, uint64_t n, SeqMeta* out, unsigned long long* counters,
+                      cudaStream_t st) {
   if (n == 0) return;
   const uint64_t blocks = (n + 255) / 256;
-  pack_meta_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
-      offsets, v, j, rep, count, n, off_base, out, counters);
+  pack_meta_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(k, n, out, counters);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -77,7 +102,8 @@ hash_kernel(const SeqMeta* __restrict__ meta, const uint8_t* __restrict__ res, u
     const SeqMeta m = ld_meta(meta + i);
     uint64_t h = ignore_genes ? 0ull : vj_hash(seed, m.v, m.j);
     const uint8_t* s = res + m.off;
-    for (uint32_t p = 0; p < m.len; p++) {
+    const uint32_t len = m.len <= zrows ? m.len : 0;  // longer than the table: rehashed later
+    for (uint32_t p = 0; p < len; p++) {
       const uint32_t r = __ldg(s + p);
       h ^= ZSMEM ? zs[p * sigma + r] : __ldg(ztab + p * sigma + r);
     }
@@ -120,7 +146,7 @@ void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st) {
 }
 
 __global__ void __launch_bounds__(256)
-build_kernel(const uint64_t* __restrict__ hash, uint64_t n, Slot* table, uint64_t mask,
+build_kernel(const uint64_t* __restrict__ hash, uint64_t idx_base, uint64_t n, Slot* table, uint64_t mask,
              unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
              uint32_t bloom2_blocks) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
@@ -129,7 +155,8 @@ build_kernel(const uint64_t* __restrict__ hash, uint64_t n, Slot* table, uint64_
     uint64_t slot = table_home(h, mask);
     for (;;) {
       const unsigned long long prev = atomicCAS(
-          reinterpret_cast<unsigned long long*>(&table[slot].idx), SLOT_EMPTY, (unsigned long long)i);
+          reinterpret_cast<unsigned long long*>(&table[slot].idx), SLOT_EMPTY,
+          (unsigned long long)(idx_base + i));
       if (prev == SLOT_EMPTY) {
         table[slot].hash = h;
         break;
@@ -141,13 +168,13 @@ build_kernel(const uint64_t* __restrict__ hash, uint64_t n, Slot* table, uint64_
   }
 }
 
-void launch_build(const uint64_t* hash, uint64_t n, Slot* table, uint64_t mask,
+void launch_build(const uint64_t* hash, uint64_t idx_base, uint64_t n, Slot* table, uint64_t mask,
                   unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
                   uint32_t bloom2_blocks, cudaStream_t st) {
   if (n == 0) return;
   const uint64_t blocks = (n + 255) / 256;
   build_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
-      hash, n, table, mask, bloom, bloom_blocks, k2, bloom2, bloom2_blocks);
+      hash, idx_base, n, table, mask, bloom, bloom_blocks, k2, bloom2, bloom2_blocks);
 }
 
 // Exact duplicates: sequence i is a duplicate iff an identical sequence (same repertoire, same

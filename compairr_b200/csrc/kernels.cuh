@@ -63,10 +63,21 @@ struct ProbeParams {
   uint8_t bloom_k2;    // first-level geometry: 1+1 bits instead of 3+3
 };
 
-// pack SoA upload into SeqMeta records, find the longest sequence
-void launch_pack_meta(const uint64_t* offsets, const uint32_t* v, const uint32_t* j,
-                      const uint32_t* rep, const uint64_t* count, uint64_t n, uint64_t off_base,
-                      SeqMeta* out, unsigned long long* counters, cudaStream_t st);
+// pack one uploaded chunk of columns into SeqMeta records, track the longest sequence
+struct PackCols {
+  const uint64_t* starts;  // offsets (n+1) or exclusive scan of lengths (n)
+  const void* lengths;     // non-null selects lengths mode
+  const void* v;
+  const void* j;
+  const void* rep;
+  const void* count;
+  uint64_t off_sub;        // offsets mode: subtracted from every offset
+  uint64_t res_add;        // lengths mode: residue index of the chunk's first sequence
+  uint32_t len_w, v_w, j_w, rep_w, count_w;
+};
+void launch_widen(const void* src, uint32_t w, uint64_t n, uint64_t* dst, cudaStream_t st);
+void launch_pack_meta(const PackCols& k, uint64_t n, SeqMeta* out, unsigned long long* counters,
+                      cudaStream_t st);
 
 // K1: batched Zobrist hashing
 void launch_hash(const SeqMeta* meta, const uint8_t* res, uint64_t n, const uint64_t* ztab,
@@ -75,7 +86,7 @@ void launch_hash(const SeqMeta* meta, const uint8_t* res, uint64_t n, const uint
 
 // K2: table + Bloom build, duplicate count
 void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st);
-void launch_build(const uint64_t* hash, uint64_t n, Slot* table, uint64_t mask,
+void launch_build(const uint64_t* hash, uint64_t idx_base, uint64_t n, Slot* table, uint64_t mask,
                   unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
                   uint32_t bloom2_blocks, cudaStream_t st);
 void launch_count_dups(DeviceSetView s, const Slot* table, uint64_t mask, bool ignore_genes,

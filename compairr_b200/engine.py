@@ -65,6 +65,27 @@ def _cb_set(s: SeqSet) -> cabi.cb_set:
     return cs
 
 
+def _col(a: Optional[np.ndarray]) -> cabi.cb_col:
+    c = cabi.cb_col()
+    if a is not None:
+        c.data = a.ctypes.data
+        c.width = a.dtype.itemsize
+    return c
+
+
+def _cb_set_cols(s) -> cabi.cb_set_cols:
+    """s: a NarrowSet (seqset.py) — lengths instead of offsets, smallest lossless dtypes."""
+    cs = cabi.cb_set_cols()
+    cs.n = s.n
+    cs.residues = s.residues.ctypes.data
+    cs.lengths = _col(s.lengths)
+    cs.v_gene, cs.j_gene, cs.rep, cs.count = _col(s.v_gene), _col(s.j_gene), _col(s.rep), _col(s.count)
+    cs.n_reps = s.n_reps
+    cs.longest = s.longest
+    cs.index_base = s.index_base
+    return cs
+
+
 class DeviceSet:
     """A sequence set resident on the GPU (cb_dset)."""
 
@@ -131,10 +152,15 @@ class Engine:
         self._check(cabi.lib.cb_set_stream(self._ctx, C.c_void_p(cuda_stream_ptr)))
 
     # -- sets
-    def upload(self, s: SeqSet) -> DeviceSet:
-        cs = _cb_set(s)
+    def upload(self, s) -> DeviceSet:
+        """s: SeqSet (reference-width columns) or NarrowSet (caller-chosen widths)."""
         h = C.c_void_p()
-        self._check(cabi.lib.cb_upload(self._ctx, C.byref(cs), C.byref(h)))
+        if hasattr(s, "lengths") and not isinstance(s, SeqSet):
+            cs = _cb_set_cols(s)
+            self._check(cabi.lib.cb_upload_cols(self._ctx, C.byref(cs), C.byref(h)))
+        else:
+            cs = _cb_set(s)
+            self._check(cabi.lib.cb_upload(self._ctx, C.byref(cs), C.byref(h)))
         return DeviceSet(self, h, s.n, s.n_reps)
 
     def rehash(self, d: DeviceSet):
@@ -148,9 +174,13 @@ class Engine:
     def build_b(self, d: DeviceSet):
         self._check(cabi.lib.cb_build_b(self._ctx, d.handle))
 
-    def set_b(self, s: SeqSet):
-        cs = _cb_set(s)
-        self._check(cabi.lib.cb_set_b(self._ctx, C.byref(cs)))
+    def set_b(self, s):
+        if isinstance(s, SeqSet):
+            cs = _cb_set(s)
+            self._check(cabi.lib.cb_set_b(self._ctx, C.byref(cs)))
+        else:
+            cs = _cb_set_cols(s)
+            self._check(cabi.lib.cb_set_b_cols(self._ctx, C.byref(cs)))
 
     def dups_b(self) -> int:
         return int(cabi.lib.cb_dups_b(self._ctx))
@@ -163,9 +193,13 @@ class Engine:
     def run(self, d: DeviceSet, first: int = 0, count: Optional[int] = None):
         self._check(cabi.lib.cb_run(self._ctx, d.handle, first, d.n - first if count is None else count))
 
-    def run_a(self, s: SeqSet):
-        cs = _cb_set(s)
-        self._check(cabi.lib.cb_run_a(self._ctx, C.byref(cs)))
+    def run_a(self, s):
+        if isinstance(s, SeqSet):
+            cs = _cb_set(s)
+            self._check(cabi.lib.cb_run_a(self._ctx, C.byref(cs)))
+        else:
+            cs = _cb_set_cols(s)
+            self._check(cabi.lib.cb_run_a_cols(self._ctx, C.byref(cs)))
 
     # -- results
     def matrix(self) -> np.ndarray:

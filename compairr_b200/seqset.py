@@ -139,6 +139,47 @@ class SeqSet:
             f.write("".join(lines))
 
 
+def _smallest_uint(a: np.ndarray, choices=(np.uint8, np.uint16, np.uint32, np.uint64)):
+    mx = int(a.max()) if a.size else 0
+    for t in choices:
+        if mx <= np.iinfo(t).max:
+            return np.ascontiguousarray(a, dtype=t)
+    raise ValueError("value out of range")
+
+
+@dataclass
+class NarrowSet:
+    """The same set with lengths instead of offsets and the smallest lossless column types
+    (cb_set_cols): fewer bytes across PCIe.  Sequences must be contiguous in `residues`."""
+    residues: np.ndarray
+    lengths: np.ndarray
+    v_gene: np.ndarray
+    j_gene: np.ndarray
+    rep: np.ndarray
+    count: np.ndarray
+    n_reps: int
+    longest: int
+    index_base: int = 0
+
+    @property
+    def n(self) -> int:
+        return int(self.lengths.shape[0])
+
+    @staticmethod
+    def from_seqset(s: "SeqSet") -> "NarrowSet":
+        off = s.offsets
+        lens = np.diff(off)
+        a, b = int(off[0]), int(off[-1])
+        return NarrowSet(np.ascontiguousarray(s.residues[a:b]), _smallest_uint(lens, (np.uint8, np.uint16, np.uint32)),
+                         _smallest_uint(s.v_gene, (np.uint8, np.uint16, np.uint32)),
+                         _smallest_uint(s.j_gene, (np.uint8, np.uint16, np.uint32)),
+                         _smallest_uint(s.rep, (np.uint8, np.uint16, np.uint32)),
+                         _smallest_uint(s.count), s.n_reps, int(lens.max()) if lens.size else 0, s.index_base)
+
+    def nbytes(self) -> int:
+        return sum(x.nbytes for x in (self.residues, self.lengths, self.v_gene, self.j_gene, self.rep, self.count))
+
+
 def read_airr_tsv(path: str, nucleotides: bool = False, gene_maps=None, default_rep: str = "1",
                   cdr3: bool = False) -> SeqSet:
     """Minimal Python mirror of the reference reader (src/db.cc:172-901) for tests and tools:

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 1
+#define CB_ABI_VERSION 2
 
 typedef enum cb_status {
   CB_OK = 0,
@@ -114,6 +114,33 @@ typedef struct cb_set {
   uint64_t index_base;
 } cb_set;
 
+/*
+ * The same set with caller-chosen column widths, for hosts that keep narrower types than the
+ * reference's seqinfo_s (fewer bytes over PCIe): every per-sequence column is a pointer plus an
+ * element width in bytes (1, 2, 4 or 8; data == NULL means "absent").  Sequence boundaries are
+ * given EITHER as n+1 offsets (width 8) OR as n lengths (width 1, 2 or 4); with lengths the
+ * sequences are contiguous in `residues` starting at byte 0.
+ */
+typedef struct cb_col {
+  const void *data;
+  uint32_t width;
+  uint32_t reserved;
+} cb_col;
+
+typedef struct cb_set_cols {
+  uint64_t n;
+  const uint8_t *residues;
+  cb_col offsets;   /* n+1 entries, width 8, or absent */
+  cb_col lengths;   /* n entries, width 1/2/4, or absent */
+  cb_col v_gene;
+  cb_col j_gene;
+  cb_col rep;
+  cb_col count;
+  uint32_t n_reps;
+  uint32_t longest;
+  uint64_t index_base;
+} cb_set_cols;
+
 /* A matching pair: reference struct pair_s (src/overlap.cc:55-58). */
 typedef struct cb_pair {
   uint64_t a;   /* sequence index in set A */
@@ -165,6 +192,7 @@ int cb_set_stream(cb_ctx *ctx, void *cuda_stream);
 /* Copy a set to the GPU and hash it: replaces db_hash() (src/db.cc:903-916) → zobrist_hash()
    (src/zobrist.cc:74-88).  The host arrays may be freed when the call returns. */
 int cb_upload(cb_ctx *ctx, const cb_set *set, cb_dset **out);
+int cb_upload_cols(cb_ctx *ctx, const cb_set_cols *set, cb_dset **out);
 void cb_free_set(cb_ctx *ctx, cb_dset *set);
 /* Recompute the hashes of a resident set (db_hash(), src/db.cc:903-916, on data already in
    device memory). */
@@ -192,10 +220,13 @@ int cb_count_dups(cb_ctx *ctx, const cb_dset *set, uint64_t *out);
    overlap.cc:799-825).  May be called repeatedly (chunks / shards). */
 int cb_run(cb_ctx *ctx, const cb_dset *a, uint64_t first, uint64_t count);
 
-/* Convenience = cb_upload + cb_build_b (host arrays → built set B). */
+/* Host arrays → built set B in one call.  The copy is chunked and pipelined: while chunk k+1
+   crosses PCIe, chunk k is packed, hashed and inserted into the table and the Bloom filter(s). */
 int cb_set_b(cb_ctx *ctx, const cb_set *b);
-/* Convenience = cb_upload + cb_run(all) + cb_free_set (host arrays → matrix contribution). */
+int cb_set_b_cols(cb_ctx *ctx, const cb_set_cols *b);
+/* Host arrays → matrix contribution: upload (pipelined with hashing) + cb_run(all) + free. */
 int cb_run_a(cb_ctx *ctx, const cb_set *a);
+int cb_run_a_cols(cb_ctx *ctx, const cb_set_cols *a);
 
 /* ---- results ------------------------------------------------------------------------------- */
 

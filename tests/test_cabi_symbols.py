@@ -28,6 +28,7 @@ def test_struct_layouts_match_header():
     # sizes are fixed by the header's field lists (LP64)
     assert ctypes.sizeof(cabi.cb_config) == 80
     assert ctypes.sizeof(cabi.cb_set) == 72
+    assert ctypes.sizeof(cabi.cb_set_cols) == 16 + 6 * 16 + 16
     assert ctypes.sizeof(cabi.cb_stats) == 96
 
 

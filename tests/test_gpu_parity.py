@@ -109,3 +109,38 @@ def test_no_bloom_flag_gives_same_result():
     m0, _, _ = overlap(a, b, OverlapOptions(differences=1, indels=True))
     m1, _, _ = overlap(a, b, OverlapOptions(differences=1, indels=True, flags=2))
     assert np.array_equal(m0, m1)
+
+
+@pytest.mark.parametrize("d,indels", [(0, False), (1, True), (2, False), (3, False)])
+def test_narrow_columns_and_one_call_api(d, indels):
+    """cb_set_b_cols / cb_run_a_cols (lengths + narrow dtypes, pipelined upload + fused build)
+    give the same matrix, pairs and duplicate count as the reference-width path."""
+    from compairr_b200 import Engine, NarrowSet
+    pool = synth.make_pool(51, 3000)
+    a = synth.make_set(52, 5, 2000, pool=pool, indel_mutants=True)
+    b = synth.make_set(53, 6, 2000, pool=pool, indel_mutants=True)
+    mo, po, io = orc.overlap(a, b, differences=d, indels=indels, want_pairs=True)
+    for conv in (lambda s: s, NarrowSet.from_seqset):
+        with Engine(OverlapOptions(differences=d, indels=indels, want_pairs=True), n_reps_a=a.n_reps) as eng:
+            eng.set_b(conv(b))
+            eng.run_a(conv(a))
+            assert np.array_equal(eng.matrix(), mo)
+            assert _pairs(eng.drain_pairs()) == _pairs(po)
+            if d <= 2:
+                assert eng.dups_b() == orc.count_dups(b)
+
+
+def test_upload_of_a_slice_and_long_sequences():
+    """A shard (offsets not starting at 0, index_base) and sequences longer than the 64 Zobrist
+    rows the pipelined upload starts with (forces the re-hash / re-insert path)."""
+    from compairr_b200 import Engine, NarrowSet
+    a = synth.small_dense_set(61, 3, 200, alphabet="ACGT", min_len=60, max_len=90, nucleotides=True)
+    b = synth.small_dense_set(61, 3, 200, alphabet="ACGT", min_len=60, max_len=90, nucleotides=True)
+    b.residues[::7] = (b.residues[::7] + 1) % 4   # same sequences with scattered substitutions
+    mo, po, _ = orc.overlap(a, b, differences=1, indels=True, want_pairs=True)
+    with Engine(OverlapOptions(differences=1, indels=True, want_pairs=True, nucleotides=True), n_reps_a=a.n_reps) as eng:
+        eng.set_b(NarrowSet.from_seqset(b))
+        eng.run_a(a.slice(0, 250))
+        eng.run_a(NarrowSet.from_seqset(a.slice(250, a.n - 250)))
+        assert np.array_equal(eng.matrix(), mo)
+        assert _pairs(eng.drain_pairs()) == _pairs(po)
