@@ -164,7 +164,7 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   if (c->cfg.bloom_bits_per_key_x16 == 0) c->cfg.bloom_bits_per_key_x16 = 16 * 16;
   if (c->cfg.table_load_pct == 0 || c->cfg.table_load_pct > 90) c->cfg.table_load_pct = 50;
   if (c->cfg.pairs_capacity == 0) c->cfg.pairs_capacity = 1ull << 24;
-  if (c->cfg.bloom_l2_cap_kib == 0) c->cfg.bloom_l2_cap_kib = 40 * 1024;
+  if (c->cfg.bloom_l2_cap_kib == 0) c->cfg.bloom_l2_cap_kib = 48 * 1024;
   if (c->cfg.seed == 0) c->cfg.seed = 1;
   c->device = cfg->device;
 #define CU_CREATE(expr)                                                                  \
@@ -180,6 +180,15 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   cudaDeviceProp prop;
   CU_CREATE(cudaGetDeviceProperties(&prop, c->device));
   c->sm_count = prop.multiProcessorCount;
+  c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
+  c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
+  if (c->l2_persist_max > 0) {
+    const size_t want = std::min<size_t>(c->l2_persist_max, (size_t)c->cfg.bloom_l2_cap_kib << 10);
+    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
+      cudaGetLastError();
+      c->l2_persist_max = 0;
+    }
+  }
   {
     cudaMemPool_t pool;
     CU_CREATE(cudaDeviceGetDefaultMemPool(&pool, c->device));
@@ -555,8 +564,27 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
       const uint64_t want_items = (uint64_t)c->sm_count * 64 * 4;
       while (p.split < 64 && count * p.split < want_items) p.split <<= 1;
     }
+    // Keep the first-level Bloom filter resident in L2 while the probe kernel runs: every probe
+    // reads it, everything else the kernel touches (second-level filter, table, metadata) is
+    // touched once.  Persisting-L2 access window over the filter, streaming for the rest.
+    bool window = false;
+    if (c->d_bloom2 && c->l2_persist_max > 0 && !getenv("CB_NO_L2_WINDOW")) {
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.base_ptr = c->d_bloom;
+      av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)c->bloom_blocks * 8, c->l2_window_max);
+      av.accessPolicyWindow.hitRatio = 1.0f;
+      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+      window = cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
+      if (!window) cudaGetLastError();
+    }
     const char* kerr = nullptr;
     launches = launch_probe(p, c->sm_count, c->stream, &kerr);
+    if (window) {
+      cudaStreamAttrValue av{};
+      av.accessPolicyWindow.num_bytes = 0;
+      cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
+    }
     if (launches < 0) return fail(c, CB_ERR_LIMIT, "cb_run: %s", kerr ? kerr : "launch failed");
     CU(c, cudaGetLastError());
   } else {

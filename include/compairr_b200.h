@@ -80,7 +80,7 @@ typedef struct cb_config {
   uint64_t pairs_capacity;          /* device pair-buffer capacity per launch, in pairs          */
   uint32_t flags;                   /* CB_FLAG_*                                                  */
   uint32_t bloom_l2_cap_kib;        /* first-level filter cap in KiB so it stays L2-resident     */
-                                    /* (default 40960); larger sets get a second-level HBM filter */
+                                    /* (default 49152); larger sets get a second-level HBM filter */
 } cb_config;
 
 #define CB_FLAG_NO_SMEM_TILE 1u   /* accumulate straight into the global matrix (A/B testing)    */
