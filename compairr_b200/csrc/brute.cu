@@ -21,38 +21,26 @@
 #include <string>
 #include <vector>
 
+#include "device_utils.cuh"
 #include "engine_internal.h"
 
 using namespace cb;
 
 namespace cb {
 
-static constexpr unsigned FULLM = 0xffffffffu;
+static constexpr unsigned FULLM = FULL;
 constexpr int BK_THREADS = 256;
 constexpr int BK_TA = 128;  // set-A sequences per tile
 
-__device__ __forceinline__ SeqMeta ld_meta2(const SeqMeta* p) {
-  const ulonglong2 lo = __ldg(reinterpret_cast<const ulonglong2*>(p));
-  const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-  SeqMeta m;
-  m.off = lo.x;
-  m.count = lo.y;
-  m.len = hi.x;
-  m.v = hi.y;
-  m.j = hi.z;
-  m.rep = hi.w;
-  return m;
-}
-
 // bucket key: injective in (len, v, j); len < 2^20, v and j < 2^22 (checked on the host)
 __global__ void __launch_bounds__(256)
-bucket_key_kernel(const SeqMeta* __restrict__ meta, uint64_t first, uint64_t n, bool ignore_genes,
+bucket_key_kernel(const SeqRec* __restrict__ meta, uint64_t first, uint64_t n, bool ignore_genes,
                   uint64_t* __restrict__ keys, uint32_t* __restrict__ idx,
                   unsigned long long* __restrict__ gene_max) {
   uint32_t gm = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
-    const SeqMeta m = ld_meta2(meta + first + i);
+    const SeqMeta m = ld_meta(meta + first + i);
     uint64_t k = (uint64_t)m.len << 44;
     if (!ignore_genes) {
       k |= ((uint64_t)(m.v & 0x3fffff) << 22) | (m.j & 0x3fffff);
@@ -69,7 +57,7 @@ bucket_key_kernel(const SeqMeta* __restrict__ meta, uint64_t first, uint64_t n, 
 // Pack the sequences of a bucket-sorted order into words, word-major inside each bucket:
 // word k of the s-th sequence of a bucket lives at pack_off[bucket] + k * bucket_n + s.
 __global__ void __launch_bounds__(256)
-pack_words_kernel(const SeqMeta* __restrict__ meta, const uint8_t* __restrict__ res,
+pack_words_kernel(const SeqRec* __restrict__ meta, const uint8_t* __restrict__ res,
                   const uint32_t* __restrict__ order, const uint64_t* __restrict__ bstart,
                   const uint64_t* __restrict__ pack_off, uint32_t n_buckets, uint64_t n,
                   uint32_t* __restrict__ packed) {
@@ -83,7 +71,7 @@ pack_words_kernel(const SeqMeta* __restrict__ meta, const uint8_t* __restrict__ 
     }
     const uint64_t bn = bstart[lo + 1] - bstart[lo];
     const uint64_t s = i - bstart[lo];
-    const SeqMeta m = ld_meta2(meta + order[i]);
+    const SeqMeta m = ld_meta(meta + order[i]);
     const uint32_t words = (m.len + 3) >> 2;
     const uint8_t* r = res + m.off;
     for (uint32_t k = 0; k < words; k++) {
@@ -156,7 +144,7 @@ __global__ void __launch_bounds__(BK_THREADS) brute_kernel(const __grid_constant
     for (uint32_t i = threadIdx.x; i < an * Wrt; i += BK_THREADS) {
       const uint32_t a = i / Wrt, k = i - a * Wrt;
       const uint32_t seq = P.a_order[J.a_start + a0 + a];
-      const SeqMeta m = ld_meta2(P.a.meta + seq);
+      const SeqMeta m = ld_meta(P.a.meta + seq);
       uint32_t w = 0;
       for (uint32_t bb = 0; bb < 4; bb++) {
         const uint32_t p = k * 4 + bb;
@@ -192,8 +180,8 @@ __global__ void __launch_bounds__(BK_THREADS) brute_kernel(const __grid_constant
         if (diff <= (uint32_t)P.differences) {
           const uint32_t seed = a_idx[a];
           const uint32_t hit = P.b_order[J.b_start + b0 + b];
-          const SeqMeta am = ld_meta2(P.a.meta + seed);
-          const SeqMeta bm = ld_meta2(P.b.meta + hit);
+          const SeqMeta am = ld_meta(P.a.meta + seed);
+          const SeqMeta bm = ld_meta(P.b.meta + hit);
           nmatch++;
           if (!P.no_matrix) {
             const uint64_t row = P.existence ? (uint64_t)seed - P.a_first : am.rep;

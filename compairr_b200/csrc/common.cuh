@@ -27,27 +27,56 @@ namespace cb {
 // ---- device data layout -------------------------------------------------------------------
 
 // One 32-byte record per sequence = exactly one L2/DRAM sector, so a verify touches one sector
-// for all of (offset, length, V, J, repertoire, count) instead of six (reference AoS seqinfo_s,
-// db.cc:77-88, is 56 B).
-struct alignas(32) SeqMeta {
-  uint64_t off;    // first residue in the residue arena
-  uint64_t count;  // duplicate_count
+// for all of (offset, length, V, J, repertoire, count, next) instead of seven arrays (reference AoS
+// seqinfo_s, db.cc:77-88, is 56 B).  `next` chains the occurrences of one distinct
+// (sequence, V, J): identical set-B sequences share ONE table slot and hang off it as a list.
+struct alignas(32) SeqRec {  // memory format
+  uint64_t off_len;  // first residue in the arena (low 40 bits) | length (high 24 bits)
+  uint64_t count;    // duplicate_count
+  uint32_t v;
+  uint32_t j;
+  uint32_t rep;
+  uint32_t next;     // next occurrence of the same (sequence, V, J) in set B, SEQ_NIL = end
+};
+static_assert(sizeof(SeqRec) == 32, "SeqRec must be one 32-byte sector");
+constexpr uint32_t SEQ_NIL = 0xffffffffu;
+constexpr uint32_t SEQ_MAX_LEN = (1u << 24) - 1;
+
+struct SeqMeta {  // register format
+  uint64_t off;
+  uint64_t count;
   uint32_t len;
   uint32_t v;
   uint32_t j;
   uint32_t rep;
+  uint32_t next;
 };
-static_assert(sizeof(SeqMeta) == 32, "SeqMeta must be one 32-byte sector");
+
+CB_HD uint64_t pack_off_len(uint64_t off, uint32_t len) { return (off & ((1ull << 40) - 1)) | ((uint64_t)len << 40); }
+CB_HD SeqMeta unpack_rec(uint64_t off_len, uint64_t count, uint32_t v, uint32_t j, uint32_t rep, uint32_t next) {
+  SeqMeta m;
+  m.off = off_len & ((1ull << 40) - 1);
+  m.len = (uint32_t)(off_len >> 40);
+  m.count = count;
+  m.v = v;
+  m.j = j;
+  m.rep = rep;
+  m.next = next;
+  return m;
+}
 
 // Open-addressing slot, probed with one 128-bit load (reference keeps three arrays:
-// hash_values / hash_data / hash_occupied bitmap, hashtable.h:22-29).  "Empty" lives in the
-// index word, so a stored hash may legitimately be any 64-bit value including 0.
+// hash_values / hash_data / hash_occupied bitmap, hashtable.h:22-29).  One slot per DISTINCT
+// (sequence, V, J) of set B; idx is the head of its occurrence list.  "Empty" lives in the index
+// word, so a stored hash may legitimately be any 64-bit value including 0; SLOT_LOCKED marks a
+// slot whose owner is still publishing its hash during the build.
 struct alignas(16) Slot {
   uint64_t hash;
   uint64_t idx;
 };
 static_assert(sizeof(Slot) == 16, "Slot must be 16 bytes");
 constexpr uint64_t SLOT_EMPTY = ~0ull;
+constexpr uint64_t SLOT_LOCKED = ~0ull - 1;
 
 enum VariantKind : uint32_t {  // same numbering as mutation_kind_enum, variants.h:24-31
   VK_IDENTICAL = 0,

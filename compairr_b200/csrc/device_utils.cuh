@@ -14,17 +14,10 @@ __device__ __forceinline__ Slot ld_slot(const Slot* p) {
   return s;
 }
 
-__device__ __forceinline__ SeqMeta ld_meta(const SeqMeta* p) {
+__device__ __forceinline__ SeqMeta ld_meta(const SeqRec* p) {
   const ulonglong2 lo = __ldg(reinterpret_cast<const ulonglong2*>(p));
   const uint4 hi = __ldg(reinterpret_cast<const uint4*>(p) + 1);
-  SeqMeta m;
-  m.off = lo.x;
-  m.count = lo.y;
-  m.len = hi.x;
-  m.v = hi.y;
-  m.j = hi.z;
-  m.rep = hi.w;
-  return m;
+  return unpack_rec(lo.x, lo.y, hi.x, hi.y, hi.z, hi.w);
 }
 
 // Filter word test.  K2 = true: 1 bit per 32-bit half (the low-bits-per-key geometry of a
@@ -58,30 +51,39 @@ __device__ __forceinline__ void accumulate(const ProbeParams* __restrict__ P, do
     atomicAdd(P->matrix + (uint64_t)row * P->n_cols + col, sc);
 }
 
-// K4 for one lane's candidate hit: V/J compare, exact verify of the edit, score, accumulate,
-// pair append (overlap.cc:189-245).
+// K4 for one lane's candidate group (one distinct set-B sequence with its occurrence list): V/J
+// compare and exact verify of the edit ONCE against the head, then score + accumulate + pair
+// append for every occurrence (overlap.cc:189-245).
 __device__ __forceinline__ uint32_t verify_and_record(const ProbeParams* __restrict__ P,
                                                       uint64_t seed_idx, const SeqMeta& sm,
-                                                      uint32_t row, uint32_t var, uint64_t hit,
+                                                      uint32_t row, uint32_t var, uint64_t head,
                                                       double* tile, uint32_t tile_row) {
-  const SeqMeta hm = ld_meta(P->b.meta + hit);
+  SeqMeta hm = ld_meta(P->b.meta + head);
   if (!P->ignore_genes && (hm.v != sm.v || hm.j != sm.j)) return 0;
   const uint32_t kind = var & 7, r1 = (var >> 3) & 31, r2 = (var >> 8) & 31;
   const uint32_t pos1 = (var >> 13) & 511, pos2 = (var >> 22) & 511;
   if (!verify_variant(P->a.res + sm.off, sm.len, P->b.res + hm.off, hm.len, kind, pos1, r1, pos2, r2))
     return 0;
-  if (!P->no_matrix)
-    accumulate(P, tile, tile_row, row, hm.rep, score_of(P->score, P->ignore_counts, sm.count, hm.count));
-  if (P->want_pairs) {
-    const unsigned long long at = atomicAdd(P->counters + CTR_PAIRS, 1ull);
-    if (at < P->pairs_cap) {
-      PairOut po;
-      po.a = seed_idx + P->a.index_base;
-      po.b = hit + P->b.index_base;
-      P->pairs[at] = po;
+  uint32_t found = 0;
+  uint64_t node = head;
+  for (;;) {
+    found++;
+    if (!P->no_matrix)
+      accumulate(P, tile, tile_row, row, hm.rep, score_of(P->score, P->ignore_counts, sm.count, hm.count));
+    if (P->want_pairs) {
+      const unsigned long long at = atomicAdd(P->counters + CTR_PAIRS, 1ull);
+      if (at < P->pairs_cap) {
+        PairOut po;
+        po.a = seed_idx + P->a.index_base;
+        po.b = node + P->b.index_base;
+        P->pairs[at] = po;
+      }
     }
+    if (hm.next == SEQ_NIL) break;
+    node = hm.next;
+    hm = ld_meta(P->b.meta + node);
   }
-  return 1;
+  return found;
 }
 
 // Linear probing for up to 32 (hash, variant, seed) candidates, one per lane, executed by the

@@ -182,13 +182,7 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
   c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
   c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
-  if (c->l2_persist_max > 0) {
-    const size_t want = std::min<size_t>(c->l2_persist_max, (size_t)c->cfg.bloom_l2_cap_kib << 10);
-    if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) != cudaSuccess) {
-      cudaGetLastError();
-      c->l2_persist_max = 0;
-    }
-  }
+
   {
     cudaMemPool_t pool;
     CU_CREATE(cudaDeviceGetDefaultMemPool(&pool, c->device));
@@ -348,15 +342,15 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
 }
 
 // Insert sequences [first, first + n) (hashes at d_hash[first..]) into the table and filter(s).
-void cb_table_insert(cb_ctx* c, const BuiltTable& t, const uint64_t* d_hash, uint64_t first, uint64_t n) {
-  launch_build(d_hash + first, first, n, t.table, t.slots - 1, t.bloom, t.blocks, t.k2, t.bloom2, t.blocks2,
-               c->stream);
+void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n) {
+  launch_build(s->d_meta, s->d_res, s->d_hash, first, n, c->cfg.ignore_genes != 0, t.table, t.slots - 1,
+               t.bloom, t.blocks, t.k2, t.bloom2, t.blocks2, c->stream);
 }
 
-static int build_table_for(cb_ctx* c, const cb_dset* s, bool with_bloom, BuiltTable* out) {
+static int build_table_for(cb_ctx* c, cb_dset* s, bool with_bloom, BuiltTable* out) {
   int rc = cb_table_alloc(c, s->n, with_bloom, out);
   if (rc) return rc;
-  cb_table_insert(c, *out, s->d_hash, 0, s->n);
+  cb_table_insert(c, *out, s, 0, s->n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     out->release();
@@ -381,14 +375,25 @@ int cb_adopt_table(cb_ctx* c, cb_dset* b, BuiltTable& t, bool owned) {
   c->d_bloom2 = t.bloom2;
   c->bloom2_blocks = t.blocks2;
   t = BuiltTable();
+  // Persisting-L2 carve-out only while a two-level filter is live: it is taken away from normal
+  // accesses, which hurts the single-filter (L2-resident) case.
+  if (c->l2_persist_max > 0) {
+    const size_t want = c->d_bloom2 ? std::min<size_t>(c->l2_persist_max, (size_t)c->bloom_blocks * 8) : 0;
+    if (want != c->l2_persist_set) {
+      if (want == 0) cudaCtxResetPersistingL2Cache();
+      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
+        c->l2_persist_set = want;
+      else
+        cudaGetLastError();
+    }
+  }
   c->dups_b = 0;
   c->stats.ms_dups_b = 0;
   if (!c->d_table) return CB_OK;
   CU(c, cudaEventRecord(c->ev[1], c->stream));
   int rc = zero_counter(c, CTR_DUPS);
   if (rc) return rc;
-  launch_count_dups(cb_view_of(b), c->d_table, c->slots - 1, c->cfg.ignore_genes != 0, c->d_counters,
-                    c->stream);
+  launch_count_dups(cb_view_of(b), c->d_counters, c->stream);
   CU(c, cudaGetLastError());
   CU(c, cudaEventRecord(c->ev[2], c->stream));
   rc = read_counters(c);
@@ -427,19 +432,23 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
 
 extern "C" uint64_t cb_dups_b(const cb_ctx* c) { return c ? c->dups_b : 0; }
 
-extern "C" int cb_count_dups(cb_ctx* c, const cb_dset* s, uint64_t* out) {
+extern "C" int cb_count_dups(cb_ctx* c, cb_dset* s, uint64_t* out) {
   if (!c || !s || !out) return fail(c, CB_ERR_INVALID, "cb_count_dups: NULL argument");
   int rc = bind(c);
   if (rc) return rc;
   *out = 0;
   if (s->n == 0) return CB_OK;
+  if (s == c->b && c->d_table) {  // its occurrence lists are the live set-B structure: already counted
+    *out = c->dups_b;
+    return CB_OK;
+  }
+  if (s->n >= 0xffffffffull) return fail(c, CB_ERR_LIMIT, "more than 2^32-1 sequences in one set");
   BuiltTable bt;
   rc = build_table_for(c, s, false, &bt);
   if (rc) return rc;
   rc = zero_counter(c, CTR_DUPS);
   if (!rc) {
-    launch_count_dups(cb_view_of(s), bt.table, bt.slots - 1, c->cfg.ignore_genes != 0, c->d_counters,
-                      c->stream);
+    launch_count_dups(cb_view_of(s), c->d_counters, c->stream);
     rc = read_counters(c);
   }
   bt.release();
@@ -568,7 +577,7 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     // reads it, everything else the kernel touches (second-level filter, table, metadata) is
     // touched once.  Persisting-L2 access window over the filter, streaming for the rest.
     bool window = false;
-    if (c->d_bloom2 && c->l2_persist_max > 0 && !getenv("CB_NO_L2_WINDOW")) {
+    if (c->d_bloom2 && c->l2_persist_set > 0 && !getenv("CB_NO_L2_WINDOW")) {
       cudaStreamAttrValue av{};
       av.accessPolicyWindow.base_ptr = c->d_bloom;
       av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)c->bloom_blocks * 8, c->l2_window_max);

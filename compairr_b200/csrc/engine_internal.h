@@ -16,7 +16,7 @@ struct cb_dset {
   uint64_t res_bytes = 0;
   uint32_t n_reps = 0;
   uint32_t longest = 0;
-  cb::SeqMeta* d_meta = nullptr;
+  cb::SeqRec* d_meta = nullptr;
   uint8_t* d_res = nullptr;
   uint64_t* d_hash = nullptr;
   // d >= 3 only (set B): bucket order by (length[, V, J]), packed words, host bucket directory
@@ -58,6 +58,7 @@ struct cb_ctx {
   int sm_count = 148;
   size_t l2_persist_max = 0;  // persisting-L2 carve-out granted (0 = unavailable)
   size_t l2_window_max = 0;
+  size_t l2_persist_set = 0;  // carve-out currently configured on the device
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D side of the pipelined upload
@@ -107,7 +108,7 @@ cb::DeviceSetView cb_view_of(const cb_dset* s);
 int cb_bind_device(cb_ctx* c);
 int cb_ensure_ztab(cb_ctx* c, uint32_t rows);
 int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out);
-void cb_table_insert(cb_ctx* c, const BuiltTable& t, const uint64_t* d_hash, uint64_t first, uint64_t n);
+void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n);
 int cb_adopt_table(cb_ctx* c, cb_dset* b, BuiltTable& t, bool owned);  // sets ctx fields, counts dups
 void cb_free_dset(cb_dset* s);
 

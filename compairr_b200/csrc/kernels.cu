@@ -49,32 +49,36 @@ void launch_widen(const void* src, uint32_t w, uint64_t n, uint64_t* dst, cudaSt
 // first residue of sequence i: either offsets[i] - off_sub (offsets mode) or scan[i] + res_add
 // (lengths mode, scan = exclusive prefix sum of the chunk's lengths).
 __global__ void __launch_bounds__(256)
-pack_meta_kernel(PackCols k, uint64_t n, SeqMeta* __restrict__ out, unsigned long long* counters) {
+pack_meta_kernel(PackCols k, uint64_t n, SeqRec* __restrict__ out, unsigned long long* counters) {
   uint32_t mymax = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
        i += (uint64_t)gridDim.x * blockDim.x) {
-    SeqMeta m;
+    uint64_t off, len;
     if (k.lengths) {
-      m.off = k.starts[i] + k.res_add;
-      m.len = (uint32_t)col_load(k.lengths, k.len_w, i);
+      off = k.starts[i] + k.res_add;
+      len = col_load(k.lengths, k.len_w, i);
     } else {
       const uint64_t o0 = k.starts[i], o1 = k.starts[i + 1];
-      m.off = o0 - k.off_sub;
-      m.len = (uint32_t)(o1 - o0);
+      off = o0 - k.off_sub;
+      len = o1 - o0;
     }
+    const uint32_t len32 = len > SEQ_MAX_LEN ? SEQ_MAX_LEN : (uint32_t)len;  // over-long: caught by the host
+    SeqRec m;
+    m.off_len = pack_off_len(off, len32);
     m.count = k.count ? col_load(k.count, k.count_w, i) : 1ull;
     m.v = k.v ? (uint32_t)col_load(k.v, k.v_w, i) : 0u;
     m.j = k.j ? (uint32_t)col_load(k.j, k.j_w, i) : 0u;
     m.rep = k.rep ? (uint32_t)col_load(k.rep, k.rep_w, i) : 0u;
+    m.next = SEQ_NIL;
     out[i] = m;
-    mymax = max(mymax, m.len);
+    mymax = max(mymax, len32);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mymax = max(mymax, __shfl_xor_sync(FULL, mymax, o));
   if ((threadIdx.x & 31) == 0 && mymax) atomicMax(counters + CTR_MAXLEN, (unsigned long long)mymax);
 }
 
-void launch_pack_meta(const PackCols& k, uint64_t n, SeqMeta* out, unsigned long long* counters,
+void launch_pack_meta(const PackCols& k, uint64_t n, SeqRec* out, unsigned long long* counters,
                       cudaStream_t st) {
   if (n == 0) return;
   const uint64_t blocks = (n + 255) / 256;
@@ -88,7 +92,7 @@ void launch_pack_meta(const PackCols& k, uint64_t n, SeqMeta* out, unsigned long
 
 template <bool ZSMEM>
 __global__ void __launch_bounds__(256)
-hash_kernel(const SeqMeta* __restrict__ meta, const uint8_t* __restrict__ res, uint64_t n,
+hash_kernel(const SeqRec* __restrict__ meta, const uint8_t* __restrict__ res, uint64_t n,
             const uint64_t* __restrict__ ztab, uint32_t zrows, uint32_t sigma, uint64_t seed,
             bool ignore_genes, uint64_t* __restrict__ out) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -111,7 +115,7 @@ hash_kernel(const SeqMeta* __restrict__ meta, const uint8_t* __restrict__ res, u
   }
 }
 
-void launch_hash(const SeqMeta* meta, const uint8_t* res, uint64_t n, const uint64_t* ztab,
+void launch_hash(const SeqRec* meta, const uint8_t* res, uint64_t n, const uint64_t* ztab,
                  uint32_t zrows, uint32_t sigma, uint64_t seed, bool ignore_genes, uint64_t* out,
                  cudaStream_t st) {
   if (n == 0) return;
@@ -145,85 +149,109 @@ void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st) {
                                                                                         slots);
 }
 
+// Plain (coherent) loads for data other threads of the same kernel are publishing.
+__device__ __forceinline__ uint64_t ld_volatile_u64(const uint64_t* p) {
+  return *reinterpret_cast<const volatile uint64_t*>(p);
+}
+__device__ __forceinline__ SeqMeta ld_meta_plain(const SeqRec* p) {
+  const ulonglong2 lo = *reinterpret_cast<const ulonglong2*>(p);
+  const uint4 hi = *(reinterpret_cast<const uint4*>(p) + 1);
+  return unpack_rec(lo.x, lo.y, hi.x, hi.y, hi.z, hi.w);
+}
+
+// One thread per set-B sequence.  Identical (sequence, V, J) share ONE slot: the first arrival
+// owns the slot (claims it with a CAS on the index word, publishes the hash, sets the filters),
+// later arrivals verify they really are the same sequence and push themselves onto the slot's
+// occurrence list (atomicExch of the head, SeqRec.next = old head).  So probe chains never walk
+// clusters of duplicates, the exact verify runs once per distinct sequence, and the filters hold
+// distinct keys only.  The reference inserts every sequence into its own slot
+// (overlap.cc:63-128); the set of (seed, hit) matches is the same.
 __global__ void __launch_bounds__(256)
-build_kernel(const uint64_t* __restrict__ hash, uint64_t idx_base, uint64_t n, Slot* table, uint64_t mask,
+build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __restrict__ hash,
+             uint64_t first, uint64_t n, bool ignore_genes, Slot* table, uint64_t mask,
              unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
              uint32_t bloom2_blocks) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n;
-       i += (uint64_t)gridDim.x * blockDim.x) {
+  for (uint64_t t = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; t < n;
+       t += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t i = first + t;
     const uint64_t h = hash[i];
     uint64_t slot = table_home(h, mask);
+    SeqMeta me;
+    bool have_me = false;
     for (;;) {
-      const unsigned long long prev = atomicCAS(
-          reinterpret_cast<unsigned long long*>(&table[slot].idx), SLOT_EMPTY,
-          (unsigned long long)(idx_base + i));
-      if (prev == SLOT_EMPTY) {
-        table[slot].hash = h;
-        break;
+      unsigned long long* idxp = reinterpret_cast<unsigned long long*>(&table[slot].idx);
+      uint64_t idx = ld_volatile_u64(&table[slot].idx);
+      if (idx == SLOT_EMPTY) {
+        idx = atomicCAS(idxp, SLOT_EMPTY, SLOT_LOCKED);
+        if (idx == SLOT_EMPTY) {  // we own the slot: publish hash, then ourselves as the head
+          *reinterpret_cast<volatile uint64_t*>(&table[slot].hash) = h;
+          meta[i].next = SEQ_NIL;  // a set may be built more than once
+          __threadfence();
+          atomicExch(idxp, (unsigned long long)i);
+          atomicOr(bloom + bloom_block(h, bloom_blocks), k2 ? bloom1_pattern(h) : bloom_pattern(h));
+          if (bloom2) atomicOr(bloom2 + bloom_block(h, bloom2_blocks), bloom_pattern(h));
+          break;
+        }
+      }
+      while (idx == SLOT_LOCKED) idx = ld_volatile_u64(&table[slot].idx);  // owner is publishing
+      if (ld_volatile_u64(&table[slot].hash) == h) {
+        if (!have_me) {
+          me = ld_meta_plain(meta + i);
+          have_me = true;
+        }
+        const SeqMeta o = ld_meta_plain(meta + idx);
+        bool same = o.len == me.len && (ignore_genes || (o.v == me.v && o.j == me.j));
+        for (uint32_t p = 0; p < me.len && same; p++) same = res[me.off + p] == res[o.off + p];
+        if (same) {
+          const unsigned long long old = atomicExch(idxp, (unsigned long long)i);
+          meta[i].next = (uint32_t)old;
+          break;
+        }
       }
       slot = (slot + 1) & mask;
     }
-    atomicOr(bloom + bloom_block(h, bloom_blocks), k2 ? bloom1_pattern(h) : bloom_pattern(h));
-    if (bloom2) atomicOr(bloom2 + bloom_block(h, bloom2_blocks), bloom_pattern(h));
   }
 }
 
-void launch_build(const uint64_t* hash, uint64_t idx_base, uint64_t n, Slot* table, uint64_t mask,
-                  unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
-                  uint32_t bloom2_blocks, cudaStream_t st) {
+void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, uint64_t first, uint64_t n,
+                  bool ignore_genes, Slot* table, uint64_t mask, unsigned long long* bloom,
+                  uint32_t bloom_blocks, bool k2, unsigned long long* bloom2, uint32_t bloom2_blocks,
+                  cudaStream_t st) {
   if (n == 0) return;
   const uint64_t blocks = (n + 255) / 256;
   build_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
-      hash, idx_base, n, table, mask, bloom, bloom_blocks, k2, bloom2, bloom2_blocks);
+      meta, res, hash, first, n, ignore_genes, table, mask, bloom, bloom_blocks, k2, bloom2, bloom2_blocks);
 }
 
-// Exact duplicates: sequence i is a duplicate iff an identical sequence (same repertoire, same
-// V/J unless -g, same residues) with a SMALLER index is in its probe chain.  Sum over groups of
-// (size - 1) — the same number the serial reference counts (overlap.cc:63-128, 865-873).
-__global__ void __launch_bounds__(256)
-dups_kernel(DeviceSetView s, const Slot* __restrict__ table, uint64_t mask, bool ignore_genes,
-            unsigned long long* counters) {
+// Exact duplicates (overlap.cc:63-128, 865-873): sequence i is a duplicate iff another occurrence
+// of the same (sequence, V, J) FURTHER DOWN its list has the same repertoire.  Summed over a
+// group that is (members per repertoire - 1) per repertoire — the number the serial reference
+// counts, independent of insertion order.
+__global__ void __launch_bounds__(256) dups_kernel(DeviceSetView s, unsigned long long* counters) {
   uint32_t dups = 0;
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < s.n;
        i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t h = s.hash[i];
-    uint64_t slot = table_home(h, mask);
-    bool have_meta = false, dup = false;
-    SeqMeta m;
-    for (;;) {
-      const Slot sl = ld_slot(table + slot);
-      if (sl.idx == SLOT_EMPTY) break;
-      if (sl.hash == h && sl.idx < i) {
-        if (!have_meta) {
-          m = ld_meta(s.meta + i);
-          have_meta = true;
-        }
-        const SeqMeta o = ld_meta(s.meta + sl.idx);
-        if (o.rep == m.rep && o.len == m.len && (ignore_genes || (o.v == m.v && o.j == m.j))) {
-          bool same = true;
-          for (uint32_t p = 0; p < m.len && same; p++)
-            same = s.res[m.off + p] == s.res[o.off + p];
-          if (same) {
-            dup = true;
-            break;
-          }
-        }
+    const uint4 hi = __ldg(reinterpret_cast<const uint4*>(s.meta + i) + 1);  // v, j, rep, next
+    const uint32_t rep = hi.z;
+    uint32_t node = hi.w;
+    while (node != SEQ_NIL) {
+      const uint4 o = __ldg(reinterpret_cast<const uint4*>(s.meta + node) + 1);
+      if (o.z == rep) {
+        dups++;
+        break;
       }
-      slot = (slot + 1) & mask;
+      node = o.w;
     }
-    dups += dup;
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) dups += __shfl_xor_sync(FULL, dups, o);
   if ((threadIdx.x & 31) == 0 && dups) atomicAdd(counters + CTR_DUPS, (unsigned long long)dups);
 }
 
-void launch_count_dups(DeviceSetView s, const Slot* table, uint64_t mask, bool ignore_genes,
-                       unsigned long long* counters, cudaStream_t st) {
+void launch_count_dups(DeviceSetView s, unsigned long long* counters, cudaStream_t st) {
   if (s.n == 0) return;
   const uint64_t blocks = (s.n + 255) / 256;
-  dups_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
-      s, table, mask, ignore_genes, counters);
+  dups_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(s, counters);
 }
 
 // Bookkeeping: closed-form number of variants for a range of seeds (SURVEY section 8d "unit of work").

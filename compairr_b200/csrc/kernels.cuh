@@ -25,7 +25,7 @@ enum Counter : int {
 };
 
 struct DeviceSetView {
-  const SeqMeta* meta;
+  const SeqRec* meta;
   const uint8_t* res;
   const uint64_t* hash;
   uint64_t n;
@@ -76,21 +76,22 @@ struct PackCols {
   uint32_t len_w, v_w, j_w, rep_w, count_w;
 };
 void launch_widen(const void* src, uint32_t w, uint64_t n, uint64_t* dst, cudaStream_t st);
-void launch_pack_meta(const PackCols& k, uint64_t n, SeqMeta* out, unsigned long long* counters,
+void launch_pack_meta(const PackCols& k, uint64_t n, SeqRec* out, unsigned long long* counters,
                       cudaStream_t st);
 
 // K1: batched Zobrist hashing
-void launch_hash(const SeqMeta* meta, const uint8_t* res, uint64_t n, const uint64_t* ztab,
+void launch_hash(const SeqRec* meta, const uint8_t* res, uint64_t n, const uint64_t* ztab,
                  uint32_t zrows, uint32_t sigma, uint64_t seed, bool ignore_genes, uint64_t* out,
                  cudaStream_t st);
 
 // K2: table + Bloom build, duplicate count
 void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st);
-void launch_build(const uint64_t* hash, uint64_t idx_base, uint64_t n, Slot* table, uint64_t mask,
-                  unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
-                  uint32_t bloom2_blocks, cudaStream_t st);
-void launch_count_dups(DeviceSetView s, const Slot* table, uint64_t mask, bool ignore_genes,
-                       unsigned long long* counters, cudaStream_t st);
+// Inserts sequences [first, first + n) of the set; writes their SeqRec.next links.
+void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, uint64_t first, uint64_t n,
+                  bool ignore_genes, Slot* table, uint64_t mask, unsigned long long* bloom,
+                  uint32_t bloom_blocks, bool k2, unsigned long long* bloom2, uint32_t bloom2_blocks,
+                  cudaStream_t st);
+void launch_count_dups(DeviceSetView s, unsigned long long* counters, cudaStream_t st);
 
 // K3+K4: enumerate variants, Bloom, probe, verify, accumulate.  Returns launches made, <0 on
 // a configuration the kernels cannot take (message in *err).

@@ -105,8 +105,8 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
     return cb_fail(c, CB_ERR_INVALID, "upload: v_gene/j_gene are NULL but ignore_genes is off");
   if (h.n && !c->cfg.ignore_counts && !h.count.data)
     return cb_fail(c, CB_ERR_INVALID, "upload: count is NULL but ignore_counts is off");
-  if (h.n >= 0xffffffffull && c->cfg.differences > MAXDIFF_HASH)
-    return cb_fail(c, CB_ERR_LIMIT, "upload: more than 2^32-1 sequences in one set on the d>=3 path");
+  if (h.n >= 0xffffffffull)
+    return cb_fail(c, CB_ERR_LIMIT, "upload: more than 2^32-1 sequences in one set");
   int rc = cb_bind_device(c);
   if (rc) return rc;
   cb_dset* s = new (std::nothrow) cb_dset;
@@ -155,7 +155,7 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
   } while (0)
 
   UP(cb_dmalloc(&s->d_res, s->res_bytes + 16));
-  UP(cb_dmalloc(&s->d_meta, n * sizeof(SeqMeta)));
+  UP(cb_dmalloc(&s->d_meta, n * sizeof(SeqRec)));
   UP(cb_dmalloc(&s->d_hash, n * sizeof(uint64_t)));
   for (auto& b : st) {
     UP(cb_dmalloc(&b.starts, (chunk + 1) * 8));
@@ -230,7 +230,7 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
     launch_pack_meta(pc, cn, s->d_meta + first, c->d_counters, ks);
     launch_hash(s->d_meta + first, s->d_res, cn, c->d_ztab, zrows_used, sigma, c->cfg.seed,
                 c->cfg.ignore_genes != 0, s->d_hash + first, ks);
-    if (table) cb_table_insert(c, *table, s->d_hash, first, cn);
+    if (table) cb_table_insert(c, *table, s, first, cn);
     UP(cudaGetLastError());
     UP(cudaEventRecord(b.consumed, ks));
   }
@@ -246,6 +246,10 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
   if (s->longest >= (1u << 20)) {
     cb_free_dset(s);
     return cb_fail(c, CB_ERR_LIMIT, "upload: sequence longer than 2^20 residues");
+  }
+  if (s->res_bytes >= (1ull << 40)) {
+    cb_free_dset(s);
+    return cb_fail(c, CB_ERR_LIMIT, "upload: more than 2^40 residues in one set");
   }
   if (s->longest > zrows_used) {
     // a sequence was longer than the Zobrist rows we had: extend the table (same values for the
@@ -266,7 +270,7 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
       }
       table->release();
       *table = fresh;
-      cb_table_insert(c, *table, s->d_hash, 0, n);
+      cb_table_insert(c, *table, s, 0, n);
     }
     UP(cudaGetLastError());
     UP(cudaStreamSynchronize(ks));

@@ -30,10 +30,15 @@ constexpr int VK_QCAP = 64;  // ring entries per queue per warp
 constexpr int VK_U = 2;      // probes per lane per step
 constexpr int VK_WB = 8;     // seeds per warp batch (d = 1)
 
-struct Ring {
-  uint64_t* hv;
-  uint32_t* var;
-  uint32_t* seed;  // seed number relative to a_first
+// Per-warp shared-memory block, addressed from ONE base pointer to keep the register footprint of
+// the enumeration loop small (separate pointers per array pushed the kernels over their 80-register
+// budget and the queue counters into local memory):
+//   [0, 1024)     queue 1: hv[64] u64 | var[64] u32 | seed[64] u32
+//   [1024, 2048)  queue 2: same
+//   [2048, ...)   seed scratch: zo[lpad] (+ pre[lpad], sm[lpad], sp[lpad] with indels), u64 each
+constexpr uint32_t VK_Q_BYTES = VK_QCAP * 16;
+
+struct Ring {  // queue state; the arrays live at wb + which * VK_Q_BYTES
   uint32_t head, count;
 };
 
@@ -45,24 +50,33 @@ struct Pend {  // one batch of first-level survivors whose second-level words ar
 };
 
 struct WarpCtx {
+  unsigned char* wb;  // per-warp block
   Ring q1, q2;
   Pend pd;
-  double* tile;
-  const uint32_t* tile_row;  // shared-memory word holding the row the tile belongs to
   uint32_t lane;
   uint32_t nmatch, npass;
-  bool two_level, k2, use_bloom;
 };
 
-__device__ __forceinline__ void ring_push(Ring& q, uint32_t lane, bool pass, uint64_t hv, uint32_t var,
-                                          uint32_t seed) {
+__device__ __forceinline__ uint64_t* q_hv(unsigned char* wb, int which) {
+  return reinterpret_cast<uint64_t*>(wb + which * VK_Q_BYTES);
+}
+__device__ __forceinline__ uint32_t* q_var(unsigned char* wb, int which) {
+  return reinterpret_cast<uint32_t*>(wb + which * VK_Q_BYTES + VK_QCAP * 8);
+}
+__device__ __forceinline__ uint32_t* q_seed(unsigned char* wb, int which) {
+  return reinterpret_cast<uint32_t*>(wb + which * VK_Q_BYTES + VK_QCAP * 12);
+}
+
+template <int WHICH>
+__device__ __forceinline__ void ring_push(WarpCtx& c, bool pass, uint64_t hv, uint32_t var, uint32_t seed) {
+  Ring& q = WHICH ? c.q2 : c.q1;
   const unsigned m = __ballot_sync(FULL, pass);
   if (m == 0) return;
   if (pass) {
-    const uint32_t e = (q.head + q.count + __popc(m & ((1u << lane) - 1))) & (VK_QCAP - 1);
-    q.hv[e] = hv;
-    q.var[e] = var;
-    q.seed[e] = seed;
+    const uint32_t e = (q.head + q.count + __popc(m & ((1u << c.lane) - 1))) & (VK_QCAP - 1);
+    q_hv(c.wb, WHICH)[e] = hv;
+    q_var(c.wb, WHICH)[e] = var;
+    q_seed(c.wb, WHICH)[e] = seed;
   }
   q.count += __popc(m);
   __syncwarp();
@@ -70,25 +84,23 @@ __device__ __forceinline__ void ring_push(Ring& q, uint32_t lane, bool pass, uin
 
 // Table stage for n <= 32 queued candidates; called by the whole warp.  Out of line: it is rare
 // (< 1 % of probes reach it) and keeping it out of the enumeration loop keeps that loop lean.
-__device__ __noinline__ uint32_t drain_table(const ProbeParams* __restrict__ P, const uint64_t* qhv,
-                                             const uint32_t* qvar, const uint32_t* qseed, uint32_t head,
-                                             uint32_t n, double* tile, uint32_t tile_row) {
+__device__ __noinline__ uint32_t drain_table(const ProbeParams* __restrict__ P, unsigned char* wb,
+                                             uint32_t head, uint32_t n) {
   const uint32_t lane = threadIdx.x & 31;
   const bool act = lane < n;
   const uint32_t e = (head + lane) & (VK_QCAP - 1);
   uint64_t hv = 0;
   uint32_t var = 0, slocal = 0;
   if (act) {
-    hv = qhv[e];
-    var = qvar[e];
-    slocal = qseed[e];
+    hv = q_hv(wb, 1)[e];
+    var = q_var(wb, 1)[e];
+    slocal = q_seed(wb, 1)[e];
   }
-  return probe_chains(P, act, hv, var, P->a_first + slocal, slocal, tile, tile_row);
+  return probe_chains(P, act, hv, var, P->a_first + slocal, slocal, nullptr, 0);
 }
 
 __device__ __forceinline__ void q2_drain(const ProbeParams& P, WarpCtx& c, uint32_t n) {
-  const uint32_t row = c.tile ? *c.tile_row : 0u;
-  c.nmatch += drain_table(&P, c.q2.hv, c.q2.var, c.q2.seed, c.q2.head, n, c.tile, row);
+  c.nmatch += drain_table(&P, c.wb, c.q2.head, n);
   __syncwarp();
   c.q2.head = (c.q2.head + n) & (VK_QCAP - 1);
   c.q2.count -= n;
@@ -98,13 +110,13 @@ __device__ __forceinline__ void q2_drain(const ProbeParams& P, WarpCtx& c, uint3
 // request theirs.
 __device__ __forceinline__ void f2_stage(const ProbeParams& P, WarpCtx& c, uint32_t n) {
   const bool pass2 = c.pd.valid && bloom_word_test(c.pd.w, c.pd.hv, false);
-  ring_push(c.q2, c.lane, pass2, c.pd.hv, c.pd.var, c.pd.seed);
+  ring_push<1>(c, pass2, c.pd.hv, c.pd.var, c.pd.seed);
   c.pd.valid = c.lane < n;
   if (c.pd.valid) {
     const uint32_t e = (c.q1.head + c.lane) & (VK_QCAP - 1);
-    c.pd.hv = c.q1.hv[e];
-    c.pd.var = c.q1.var[e];
-    c.pd.seed = c.q1.seed[e];
+    c.pd.hv = q_hv(c.wb, 0)[e];
+    c.pd.var = q_var(c.wb, 0)[e];
+    c.pd.seed = q_seed(c.wb, 0)[e];
     c.pd.w = __ldg(P.bloom2 + bloom_block(c.pd.hv, P.bloom2_blocks));
   }
   __syncwarp();
@@ -113,35 +125,40 @@ __device__ __forceinline__ void f2_stage(const ProbeParams& P, WarpCtx& c, uint3
   if (c.q2.count >= 32) q2_drain(P, c, 32);
 }
 
+__device__ __forceinline__ bool is_two_level(const ProbeParams& P) { return P.bloom2 != nullptr && P.use_bloom; }
+
 // One lane-step's verdicts into the pipeline.
 __device__ __forceinline__ void submit(const ProbeParams& P, WarpCtx& c, bool pass, uint64_t hv,
                                        uint32_t var, uint32_t seed) {
   c.npass += pass;
-  if (c.two_level) {
-    ring_push(c.q1, c.lane, pass, hv, var, seed);
+  if (is_two_level(P)) {
+    ring_push<0>(c, pass, hv, var, seed);
     if (c.q1.count >= 32) f2_stage(P, c, 32);
   } else {
-    ring_push(c.q2, c.lane, pass, hv, var, seed);
+    ring_push<1>(c, pass, hv, var, seed);
     if (c.q2.count >= 32) q2_drain(P, c, 32);
   }
 }
 
 __device__ __forceinline__ void finish(const ProbeParams& P, WarpCtx& c) {
   __syncwarp();
-  if (c.two_level) {
+  if (is_two_level(P)) {
     f2_stage(P, c, c.q1.count);  // tests the batch in flight, requests the tail of Q1
     f2_stage(P, c, 0);           // tests the tail
   }
   while (c.q2.count) q2_drain(P, c, c.q2.count < 32 ? c.q2.count : 32);
 }
 
-// Per-warp scratch for one seed.
+// Per-warp scratch for one seed, addressed from the per-warp block.
 template <int SIGMA, bool INDELS>
 struct SeedScratch {
-  uint64_t* zo;   // Z(p, s[p])
-  uint64_t* pre;  // xor_{q<p} Z(q, s[q])              INDELS only: prefix/suffix scans replace the
-  uint64_t* sm;   // xor_{q>=p} Z(q-1, s[q])           serial incremental walks of
-  uint64_t* sp;   // xor_{q>=p} Z(q+1, s[q])           variants.cc:311-324,341-353
+  uint64_t* zo;    // Z(p, s[p]); the scans follow at multiples of lpad:
+  uint32_t lpad;   //   pre[p] = xor_{q<p} Z(q, s[q])        INDELS only: prefix/suffix scans replace the
+                   //   sm[p]  = xor_{q>=p} Z(q-1, s[q])     serial incremental walks of
+                   //   sp[p]  = xor_{q>=p} Z(q+1, s[q])     variants.cc:311-324,341-353
+  __device__ __forceinline__ uint64_t* pre() const { return zo + lpad; }
+  __device__ __forceinline__ uint64_t* sm() const { return zo + 2 * lpad; }
+  __device__ __forceinline__ uint64_t* sp() const { return zo + 3 * lpad; }
 };
 
 // Fill zo[] (and the three scans) for the seed whose residues are at sres[0..L).  Returns VJ.
@@ -161,10 +178,10 @@ __device__ __forceinline__ uint64_t prepare_seed(const uint64_t* __restrict__ z,
       const uint64_t y = __shfl_up_sync(FULL, x, o);
       if ((int)lane >= o) x ^= y;
     }
-    if (p < L) s.pre[p + 1] = carry ^ x;
+    if (p < L) s.pre()[p + 1] = carry ^ x;
     carry ^= __shfl_sync(FULL, x, 31);
   }
-  if (lane == 0) s.pre[0] = 0ull;
+  if (lane == 0) s.pre()[0] = 0ull;
   uint64_t cm = 0, cp = 0;
   for (uint32_t base = 0; base < L; base += 32) {  // suffix XORs, walking from the end
     const uint32_t t = base + lane;
@@ -183,15 +200,15 @@ __device__ __forceinline__ uint64_t prepare_seed(const uint64_t* __restrict__ z,
       }
     }
     if (ok) {
-      s.sm[q] = cm ^ xm;
-      s.sp[q] = cp ^ xp;
+      s.sm()[q] = cm ^ xm;
+      s.sp()[q] = cp ^ xp;
     }
     cm ^= __shfl_sync(FULL, xm, 31);
     cp ^= __shfl_sync(FULL, xp, 31);
   }
   if (lane == 0) {
-    s.sm[L] = 0ull;
-    s.sp[L] = 0ull;
+    s.sm()[L] = 0ull;
+    s.sp()[L] = 0ull;
   }
   __syncwarp();
   return h ^ carry;  // h = VJ ^ pre[L]
@@ -227,25 +244,25 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
           t -= nsub;
           if (t < L) {  // deletion of residue t: only at the start of a run, only if L > 1
             pass[u] = (L > 1) && (t == 0 || sres[t] != sres[t - 1]);
-            hv[u] = vjh ^ s.pre[t] ^ s.sm[t + 1];
+            hv[u] = vjh ^ s.pre()[t] ^ s.sm()[t + 1];
             var[u] = pack_var(VK_DELETION, t, 0, 0, 0);
           } else {  // insertion of residue r before seed position pos
             t -= L;
             const uint32_t pos = t / SIGMA, r = t - pos * SIGMA;
             pass[u] = (pos == 0) || (r != sres[pos - 1]);
-            hv[u] = vjh ^ s.pre[pos] ^ z[pos * SIGMA + r] ^ s.sp[pos];
+            hv[u] = vjh ^ s.pre()[pos] ^ z[pos * SIGMA + r] ^ s.sp()[pos];
             var[u] = pack_var(VK_INSERTION, pos, r, 0, 0);
           }
         }
       }
     }
-    if (c.use_bloom) {
+    if (P.use_bloom) {
       unsigned long long w[VK_U];
 #pragma unroll
       for (int u = 0; u < VK_U; u++)  // all loads first: VK_U sectors in flight per lane
         w[u] = pass[u] ? __ldg(P.bloom + bloom_block(hv[u], P.bloom_blocks)) : 0ull;
 #pragma unroll
-      for (int u = 0; u < VK_U; u++) pass[u] = pass[u] && bloom_word_test(w[u], hv[u], c.k2);
+      for (int u = 0; u < VK_U; u++) pass[u] = pass[u] && bloom_word_test(w[u], hv[u], P.bloom_k2);
     }
 #pragma unroll
     for (int u = 0; u < VK_U; u++) submit(P, c, pass[u], hv[u], var[u], slocal);
@@ -284,13 +301,13 @@ __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const 
           var[u] = var_iv | (w << 8) | (j << 22);
         }
       }
-      if (c.use_bloom) {
+      if (P.use_bloom) {
         unsigned long long w[VK_U];
 #pragma unroll
         for (int u = 0; u < VK_U; u++)
           w[u] = pass[u] ? __ldg(P.bloom + bloom_block(hv[u], P.bloom_blocks)) : 0ull;
 #pragma unroll
-        for (int u = 0; u < VK_U; u++) pass[u] = pass[u] && bloom_word_test(w[u], hv[u], c.k2);
+        for (int u = 0; u < VK_U; u++) pass[u] = pass[u] && bloom_word_test(w[u], hv[u], P.bloom_k2);
       }
 #pragma unroll
       for (int u = 0; u < VK_U; u++) submit(P, c, pass[u], hv[u], var[u], slocal);
@@ -303,55 +320,34 @@ __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const 
 struct VkLayout {
   uint32_t lpad;        // per-seed scratch entries (>= lmax + 2, multiple of 8)
   size_t z_u64;         // Zobrist rows
-  size_t warp_u64;      // per warp: scratch arrays + two queue hash arrays
-  size_t tile_u64;      // matrix row tile
+  size_t warp_bytes;    // per-warp block: two queues + seed scratch
   size_t blk_u64;       // staged seed batches, all warps: metas (4 u64 each) + hashes
   size_t res_per_warp;  // bytes of staged residues per warp
-  size_t warp_u32;      // per warp: two queues' var + seed
-  size_t blk_res;       // staged residues, bytes
   size_t total;
 };
 
 __host__ __device__ inline VkLayout vk_layout(uint32_t zrows, uint32_t sigma, uint32_t lmax, bool indels,
-                                              uint32_t tile_cols, bool staged) {
+                                              bool staged) {
   VkLayout l;
   l.lpad = (lmax + 2 + 7) & ~7u;
   l.z_u64 = (size_t)zrows * sigma;
-  l.warp_u64 = (size_t)l.lpad * (indels ? 4 : 1) + 2 * VK_QCAP;
-  l.tile_u64 = (tile_cols + 3) & ~3u;  // keeps the staged block 32-byte aligned
+  l.warp_bytes = 2 * VK_Q_BYTES + (size_t)l.lpad * (indels ? 4 : 1) * 8;
   l.blk_u64 = staged ? (size_t)VK_WARPS * VK_WB * 5 : 0;
-  l.warp_u32 = 4 * VK_QCAP;
   l.res_per_warp = staged ? (((size_t)VK_WB * lmax + 15) & ~(size_t)15) : l.lpad;
-  l.blk_res = (size_t)VK_WARPS * l.res_per_warp;
-  l.total = (l.z_u64 + VK_WARPS * l.warp_u64 + l.tile_u64 + l.blk_u64) * 8 + (VK_WARPS * l.warp_u32 + 4) * 4 + l.blk_res;
+  l.total = l.z_u64 * 8 + VK_WARPS * l.warp_bytes + l.blk_u64 * 8 + VK_WARPS * l.res_per_warp;
   return l;
 }
 
 template <int SIGMA, bool INDELS>
 __device__ __forceinline__ void carve_warp(const VkLayout& l, unsigned char* smem, uint32_t warp, uint32_t lane,
-                                           const ProbeParams& P, uint64_t*& z, SeedScratch<SIGMA, INDELS>& s,
-                                           WarpCtx& c, uint64_t*& blk, uint32_t*& words, uint8_t*& bytes) {
+                                           uint64_t*& z, SeedScratch<SIGMA, INDELS>& s, WarpCtx& c,
+                                           uint64_t*& blk, uint8_t*& bytes) {
   z = reinterpret_cast<uint64_t*>(smem);
-  uint64_t* wb = z + l.z_u64 + warp * l.warp_u64;
-  s.zo = wb;
-  s.pre = s.zo + l.lpad;
-  s.sm = s.pre + l.lpad;
-  s.sp = s.sm + l.lpad;
-  uint64_t* qh = wb + (size_t)l.lpad * (INDELS ? 4 : 1);
-  c.q1.hv = qh;
-  c.q2.hv = qh + VK_QCAP;
-  uint64_t* after = z + l.z_u64 + VK_WARPS * l.warp_u64;
-  c.tile = l.tile_u64 ? reinterpret_cast<double*>(after) : nullptr;
-  blk = after + l.tile_u64;
-  uint32_t* w32 = reinterpret_cast<uint32_t*>(blk + l.blk_u64);
-  uint32_t* mine = w32 + warp * l.warp_u32;
-  c.q1.var = mine;
-  c.q1.seed = mine + VK_QCAP;
-  c.q2.var = mine + 2 * VK_QCAP;
-  c.q2.seed = mine + 3 * VK_QCAP;
-  words = w32 + VK_WARPS * l.warp_u32;  // 4 control words
-  c.tile_row = words + 2;
-  bytes = reinterpret_cast<uint8_t*>(words + 4);
+  c.wb = smem + l.z_u64 * 8 + warp * l.warp_bytes;
+  s.zo = reinterpret_cast<uint64_t*>(c.wb + 2 * VK_Q_BYTES);
+  s.lpad = l.lpad;
+  blk = reinterpret_cast<uint64_t*>(smem + l.z_u64 * 8 + VK_WARPS * l.warp_bytes);
+  bytes = reinterpret_cast<uint8_t*>(blk + l.blk_u64);
   c.q1.head = c.q1.count = c.q2.head = c.q2.count = 0;
   c.pd.valid = false;
   c.pd.hv = 0;
@@ -359,9 +355,6 @@ __device__ __forceinline__ void carve_warp(const VkLayout& l, unsigned char* sme
   c.pd.var = c.pd.seed = 0;
   c.lane = lane;
   c.nmatch = c.npass = 0;
-  c.two_level = P.bloom2 != nullptr && P.use_bloom;
-  c.k2 = P.bloom_k2;
-  c.use_bloom = P.use_bloom;
 }
 
 // ---- d = 1 -------------------------------------------------------------------------------------------
@@ -377,16 +370,15 @@ template <int SIGMA, bool INDELS>
 __global__ void __launch_bounds__(VK_THREADS, 3) variant1_kernel(const __grid_constant__ ProbeParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const VkLayout lay = vk_layout(P.zrows, SIGMA, P.lmax, INDELS, 0, true);
+  const VkLayout lay = vk_layout(P.zrows, SIGMA, P.lmax, INDELS, true);
   uint64_t* z;
   SeedScratch<SIGMA, INDELS> sc;
   WarpCtx c;
   uint64_t* blk;
-  uint32_t* ctl;
   uint8_t* bytes;
-  carve_warp<SIGMA, INDELS>(lay, smem_raw, warp, lane, P, z, sc, c, blk, ctl, bytes);
+  carve_warp<SIGMA, INDELS>(lay, smem_raw, warp, lane, z, sc, c, blk, bytes);
   uint64_t* const my = blk + warp * (VK_WB * 5);                 // this warp's staging area
-  SeqMeta* const b_meta = reinterpret_cast<SeqMeta*>(my);        // VK_WB records of 32 B
+  SeqRec* const b_meta = reinterpret_cast<SeqRec*>(my);          // VK_WB records of 32 B
   uint64_t* const b_hash = my + VK_WB * 4;
   uint8_t* const b_res = bytes + warp * lay.res_per_warp;
 
@@ -407,18 +399,20 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant1_kernel(const __grid_co
           __ldg(reinterpret_cast<const uint4*>(P.a.meta + P.a_first + first) + lane);
     if (lane >= 16 && lane < 16 + nb) b_hash[lane - 16] = __ldg(P.a.hash + P.a_first + first + (lane - 16));
     __syncwarp();
-    const uint64_t res0 = b_meta[0].off;
-    const uint32_t res_n = (uint32_t)(b_meta[nb - 1].off + b_meta[nb - 1].len - res0);
+    const uint64_t res0 = b_meta[0].off_len & ((1ull << 40) - 1);
+    const uint64_t last = b_meta[nb - 1].off_len;
+    const uint32_t res_n = (uint32_t)((last & ((1ull << 40) - 1)) + (last >> 40) - res0);
     for (uint32_t i = lane; i < res_n; i += 32) b_res[i] = __ldg(P.a.res + res0 + i);
     __syncwarp();
 
     for (uint32_t k = 0; k < nb; k++) {
-      const SeqMeta m = b_meta[k];
+      const uint64_t off_len = b_meta[k].off_len;  // the enumeration needs only offset and length
+      const uint32_t L = (uint32_t)(off_len >> 40);
       const uint64_t h = b_hash[k];
-      const uint8_t* sres = b_res + (uint32_t)(m.off - res0);
+      const uint8_t* sres = b_res + (uint32_t)((off_len & ((1ull << 40) - 1)) - res0);
       __syncwarp();  // all lanes are done with the previous seed's scratch
-      const uint64_t vjh = prepare_seed<SIGMA, INDELS>(z, sres, m.len, h, lane, sc);
-      phase_a<SIGMA, INDELS>(P, c, z, sres, sc, m.len, h, vjh, (uint32_t)(first + k));
+      const uint64_t vjh = prepare_seed<SIGMA, INDELS>(z, sres, L, h, lane, sc);
+      phase_a<SIGMA, INDELS>(P, c, z, sres, sc, L, h, vjh, (uint32_t)(first + k));
     }
   }
   finish(P, c);
@@ -431,15 +425,14 @@ template <int SIGMA>
 __global__ void __launch_bounds__(VK_THREADS, 3) variant2_kernel(const __grid_constant__ ProbeParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const VkLayout lay = vk_layout(P.zrows, SIGMA, P.lmax, false, 0, false);
+  const VkLayout lay = vk_layout(P.zrows, SIGMA, P.lmax, false, false);
   uint64_t* z;
   SeedScratch<SIGMA, false> sc;
   WarpCtx c;
   uint64_t* blk;
-  uint32_t* ctl;
   uint8_t* bytes;
-  carve_warp<SIGMA, false>(lay, smem_raw, warp, lane, P, z, sc, c, blk, ctl, bytes);
-  uint8_t* const sres = bytes + warp * lay.lpad;
+  carve_warp<SIGMA, false>(lay, smem_raw, warp, lane, z, sc, c, blk, bytes);
+  uint8_t* const sres = bytes + warp * lay.res_per_warp;
 
   for (uint32_t i = threadIdx.x; i < P.zrows * SIGMA; i += VK_THREADS) z[i] = P.ztab[i];
   __syncthreads();
@@ -455,14 +448,15 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant2_kernel(const __grid_co
     const uint32_t slocal = (uint32_t)(item >> split_shift);
     const uint32_t part = (uint32_t)item & split_mask;
     const uint64_t sidx = P.a_first + slocal;
-    const SeqMeta m = ld_meta(P.a.meta + sidx);  // same address in all lanes: one broadcast
+    const uint64_t off_len = __ldg(&P.a.meta[sidx].off_len);  // same address in all lanes: one broadcast
+    const uint32_t L = (uint32_t)(off_len >> 40);
     const uint64_t h = __ldg(P.a.hash + sidx);
     __syncwarp();
-    for (uint32_t p = lane; p < m.len; p += 32) sres[p] = __ldg(P.a.res + m.off + p);
+    for (uint32_t p = lane; p < L; p += 32) sres[p] = __ldg(P.a.res + (off_len & ((1ull << 40) - 1)) + p);
     __syncwarp();
-    prepare_seed<SIGMA, false>(z, sres, m.len, h, lane, sc);
-    if (part == 0) phase_a<SIGMA, false>(P, c, z, sres, sc, m.len, h, 0, slocal);
-    phase_b<SIGMA, false>(P, c, z, sres, sc, m.len, h, slocal, part, P.split);
+    prepare_seed<SIGMA, false>(z, sres, L, h, lane, sc);
+    if (part == 0) phase_a<SIGMA, false>(P, c, z, sres, sc, L, h, 0, slocal);
+    phase_b<SIGMA, false>(P, c, z, sres, sc, L, h, slocal, part, P.split);
   }
   finish(P, c);
   flush_counters(P, c.nmatch, P.count_bloom ? c.npass : 0);
@@ -502,7 +496,7 @@ int launch_variant_kernels(const ProbeParams& p, int sm_count, cudaStream_t st, 
     return -1;
   }
   if (p.differences == 1) {
-    const size_t smem = vk_layout(p.zrows, p.sigma, p.lmax, p.indels, 0, true).total;
+    const size_t smem = vk_layout(p.zrows, p.sigma, p.lmax, p.indels, true).total;
     const uint64_t blocks = ((p.a_count + VK_WB - 1) / VK_WB + VK_WARPS - 1) / VK_WARPS;
     if (p.sigma == 20)
       return p.indels ? launch_one(variant1_kernel<20, true>, p, smem, blocks, sm_count, st, err)
@@ -510,7 +504,7 @@ int launch_variant_kernels(const ProbeParams& p, int sm_count, cudaStream_t st, 
     return p.indels ? launch_one(variant1_kernel<4, true>, p, smem, blocks, sm_count, st, err)
                     : launch_one(variant1_kernel<4, false>, p, smem, blocks, sm_count, st, err);
   }
-  const size_t smem = vk_layout(p.zrows, p.sigma, p.lmax, false, 0, false).total;
+  const size_t smem = vk_layout(p.zrows, p.sigma, p.lmax, false, false).total;
   const uint64_t ctas = (p.a_count * p.split + VK_WARPS - 1) / VK_WARPS;
   return p.sigma == 20 ? launch_one(variant2_kernel<20>, p, smem, ctas, sm_count, st, err)
                        : launch_one(variant2_kernel<4>, p, smem, ctas, sm_count, st, err);

@@ -210,7 +210,7 @@ int cb_build_b(cb_ctx *ctx, cb_dset *b);
 /* Exact duplicates found while building (reference dup2, overlap.cc:861-873). */
 uint64_t cb_dups_b(const cb_ctx *ctx);
 /* Replaces check_duplicates() (overlap.cc:579-605) for an arbitrary resident set (dup1). */
-int cb_count_dups(cb_ctx *ctx, const cb_dset *set, uint64_t *out);
+int cb_count_dups(cb_ctx *ctx, cb_dset *set, uint64_t *out);
 
 /* ---- set A: enumerate, probe, verify, accumulate ------------------------------------------- */
 
