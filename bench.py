@@ -297,15 +297,25 @@ def run_ours(a):
 
     kernel_ms, launches = [], 0
 
+    debug = bool(os.environ.get("BENCH_DEBUG"))
+
     def step_resident():
         nonlocal launches
         n = 0
+        t0 = time.perf_counter()
         eng.rehash(db); n += 1
+        t1 = time.perf_counter()
         eng.build_b(db); n += eng.stats()["kernel_launches"]
+        sb = eng.stats()
+        t2 = time.perf_counter()
         eng.rehash(da); n += 1
         matrix.zero_(); n += 1
         eng.run(da)
         st = eng.stats()
+        t3 = time.perf_counter()
+        if debug and rank == 0:
+            print(f"[step] rehashB {1e3*(t1-t0):.1f} build {1e3*(t2-t1):.1f} (dev {sb['ms_build_b']:.1f} + dups {sb['ms_dups_b']:.1f}) "
+                  f"run {1e3*(t3-t2):.1f} (probe {st['ms_probe']:.1f})", file=sys.stderr, flush=True)
         n += st["kernel_launches"] + 1          # + the probe-count bookkeeping kernel
         if world > 1:
             dist.all_reduce(matrix)
@@ -350,7 +360,7 @@ def run_ours(a):
             dist.all_reduce(mt)
             m = mt.cpu().numpy()
         return m
-    for _ in range(min(a.warmup, 2)):
+    for _ in range(a.warmup):
         step_e2e()
     sync_all()
     t0e = time.perf_counter()

@@ -68,15 +68,15 @@ CB_HD SeqMeta unpack_rec(uint64_t off_len, uint64_t count, uint32_t v, uint32_t 
 // Open-addressing slot, probed with one 128-bit load (reference keeps three arrays:
 // hash_values / hash_data / hash_occupied bitmap, hashtable.h:22-29).  One slot per DISTINCT
 // (sequence, V, J) of set B; idx is the head of its occurrence list.  "Empty" lives in the index
-// word, so a stored hash may legitimately be any 64-bit value including 0; SLOT_LOCKED marks a
-// slot whose owner is still publishing its hash during the build.
+// word, so a stored hash may legitimately be any 64-bit value including 0.  The index word is
+// (low 32 bits of the hash) << 32 | head index; sequence indices are < 2^32 - 1, so an occupied
+// slot can never look like SLOT_EMPTY.
 struct alignas(16) Slot {
   uint64_t hash;
   uint64_t idx;
 };
 static_assert(sizeof(Slot) == 16, "Slot must be 16 bytes");
 constexpr uint64_t SLOT_EMPTY = ~0ull;
-constexpr uint64_t SLOT_LOCKED = ~0ull - 1;
 
 enum VariantKind : uint32_t {  // same numbering as mutation_kind_enum, variants.h:24-31
   VK_IDENTICAL = 0,

@@ -110,7 +110,7 @@ __device__ __forceinline__ uint32_t probe_chains(const ProbeParams* __restrict__
         walking = false;
       } else if (s.hash == hv) {
         cand = true;
-        hit = s.idx;
+        hit = (uint32_t)s.idx;  // low half = head of the occurrence list (high half = hash tag)
         break;
       }
     }

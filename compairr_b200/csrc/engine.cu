@@ -227,6 +227,9 @@ extern "C" void cb_destroy(cb_ctx* c) {
   cb_dfree(c->d_bloom2);
   if (!c->matrix_external) cb_dfree(c->d_matrix);
   cb_dfree(c->d_pairs);
+  cb_dfree(c->d_gq_hv);
+  cb_dfree(c->d_gq_vs);
+  cb_dfree(c->d_overflow);
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   if (g_alloc_stream) cudaStreamSynchronize(g_alloc_stream);
@@ -310,10 +313,8 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
   BuiltTable t;
   t.slots = 8;
   while (t.slots * c->cfg.table_load_pct < n * 100) t.slots <<= 1;
-  CU(c, cb_dmalloc(&t.table, t.slots * sizeof(Slot)));
   const unsigned __int128 want_bits = (unsigned __int128)n * c->cfg.bloom_bits_per_key_x16 / 16;
   const uint64_t cap_bytes = (uint64_t)c->cfg.bloom_l2_cap_kib << 10;
-  cudaError_t e = cudaSuccess;
   if (!with_bloom) {
     t.blocks = 16;  // the build kernel always sets a filter; give it a scratch one
   } else if ((uint64_t)((want_bits + 7) / 8) <= cap_bytes) {
@@ -321,12 +322,26 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
   } else {
     t.blocks = (uint32_t)(cap_bytes / 8);
     t.k2 = (double)cap_bytes * 8.0 / (double)n < 8.0;
-    const unsigned __int128 bits2 = t.k2 ? (unsigned __int128)n * 12 : want_bits;
-    t.blocks2 = blocks_for_bits(bits2);
-    e = cb_dmalloc(&t.bloom2, (size_t)t.blocks2 * 8);
-    if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom2, 0, (size_t)t.blocks2 * 8, c->stream);
+    t.blocks2 = blocks_for_bits(t.k2 ? (unsigned __int128)n * 12 : want_bits);
   }
-  if (e == cudaSuccess) e = cb_dmalloc(&t.bloom, (size_t)t.blocks * 8);
+  cudaError_t e = cudaSuccess;
+  if (with_bloom && c->d_table && c->slots == t.slots && c->bloom_blocks == t.blocks &&
+      c->bloom2_blocks == t.blocks2) {
+    // rebuilding a set-B structure of the same geometry: clear and refill the buffers in place
+    // instead of growing the memory pool by another table
+    t.table = c->d_table;
+    t.bloom = c->d_bloom;
+    t.bloom2 = c->d_bloom2;
+    c->d_table = nullptr;
+    c->d_bloom = c->d_bloom2 = nullptr;
+    c->slots = 0;
+    c->bloom_blocks = c->bloom2_blocks = 0;
+  } else {
+    e = cb_dmalloc(&t.table, t.slots * sizeof(Slot));
+    if (e == cudaSuccess && t.blocks2) e = cb_dmalloc(&t.bloom2, (size_t)t.blocks2 * 8);
+    if (e == cudaSuccess) e = cb_dmalloc(&t.bloom, (size_t)t.blocks * 8);
+  }
+  if (e == cudaSuccess && t.bloom2) e = cudaMemsetAsync(t.bloom2, 0, (size_t)t.blocks2 * 8, c->stream);
   if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom, 0, (size_t)t.blocks * 8, c->stream);
   if (e == cudaSuccess) {
     launch_table_clear(t.table, t.slots, c->stream);
@@ -490,6 +505,95 @@ static int ensure_pairs(cb_ctx* c, uint64_t cap) {
   return CB_OK;
 }
 
+// d <= 2.  d = 0 is one kernel.  d = 1, 2 run in chunks of seeds: the enumeration kernel fills the
+// global candidate queue, the table kernel drains it.  A chunk whose candidates did not fit is
+// skipped by the table kernel (nothing accumulated) and redone here in smaller pieces.
+static int run_chunks(cb_ctx* c, ProbeParams& p, uint64_t w_first, uint64_t w_count, uint64_t per_chunk,
+                      int depth, int* launches) {
+  std::vector<std::pair<uint64_t, uint64_t>> chunks;
+  for (uint64_t at = 0; at < w_count; at += per_chunk) chunks.emplace_back(w_first + at, std::min(per_chunk, w_count - at));
+  CU(c, cudaMemsetAsync(c->d_counters + CTR_OVERFLOW, 0, sizeof(unsigned long long), c->stream));
+  for (size_t k = 0; k < chunks.size(); k++) {
+    p.w_first = chunks[k].first;
+    p.w_count = chunks[k].second;
+    p.split = 1;
+    if (p.differences == 2) {  // too few seeds to fill the machine: split each seed's outer space
+      const uint64_t want_items = (uint64_t)c->sm_count * 64 * 4;
+      while (p.split < 64 && p.w_count * p.split < want_items) p.split <<= 1;
+    }
+    CU(c, cudaMemsetAsync(c->d_counters + CTR_GQ, 0, sizeof(unsigned long long), c->stream));
+    CU(c, cudaMemsetAsync(c->d_counters + CTR_WORK, 0, sizeof(unsigned long long), c->stream));
+    const char* kerr = nullptr;
+    const int l = launch_probe(p, c->sm_count, c->stream, &kerr);
+    if (l < 0) return fail(c, CB_ERR_LIMIT, "cb_run: %s", kerr ? kerr : "launch failed");
+    launch_table_stage(p, c->sm_count, (uint32_t)k, c->stream);
+    CU(c, cudaGetLastError());
+    *launches += l + 1;
+  }
+  int rc = read_counters(c);
+  if (rc) return rc;
+  const uint64_t over = c->h_counters[CTR_OVERFLOW];
+  if (over == 0) return CB_OK;
+  if (depth >= 6 || per_chunk <= 1)
+    return fail(c, CB_ERR_LIMIT, "cb_run: candidate queue too small even for single seeds");
+  std::vector<uint32_t> ids(std::min<uint64_t>(over, 64));
+  CU(c, cudaMemcpyAsync(ids.data(), c->d_overflow, ids.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (over > 64) {  // more than we recorded: nothing of those chunks was accumulated, but we do not
+    // know which — cannot happen with <= 64 chunks; guard anyway
+    return fail(c, CB_ERR_LIMIT, "cb_run: too many overflowed chunks");
+  }
+  const uint64_t saved_matches = c->h_counters[CTR_MATCHES];
+  (void)saved_matches;
+  for (uint32_t id : ids) {
+    rc = run_chunks(c, p, chunks[id].first, chunks[id].second, std::max<uint64_t>(per_chunk / 8, 1), depth + 1, launches);
+    if (rc) return rc;
+  }
+  return CB_OK;
+}
+
+static int run_hash_path(cb_ctx* c, ProbeParams& p, uint64_t count, int* launches) {
+  CU(c, cudaMemsetAsync(c->d_counters + CTR_WORK, 0, sizeof(unsigned long long), c->stream));
+  if (p.differences == 0) {
+    p.w_first = 0;
+    p.w_count = count;
+    p.split = 1;
+    const char* kerr = nullptr;
+    const int l = launch_probe(p, c->sm_count, c->stream, &kerr);
+    if (l < 0) return fail(c, CB_ERR_LIMIT, "cb_run: %s", kerr ? kerr : "launch failed");
+    CU(c, cudaGetLastError());
+    *launches += l;
+    return CB_OK;
+  }
+  // global candidate queue: 2^26 entries (1 GiB) unless the run is small
+  const uint64_t cap = 1ull << 26;
+  if (!c->d_gq_hv) {
+    CU(c, cb_dmalloc(&c->d_gq_hv, cap * sizeof(uint64_t)));
+    CU(c, cb_dmalloc(&c->d_gq_vs, cap * sizeof(uint2)));
+    CU(c, cb_dmalloc(&c->d_overflow, 64 * sizeof(uint32_t)));
+  }
+  p.gq_hv = c->d_gq_hv;
+  p.gq_vs = c->d_gq_vs;
+  p.gq_cap = cap;
+  p.overflow_chunks = c->d_overflow;
+  // Seeds per chunk.  A small first chunk measures how many candidates a seed produces on this
+  // data (it depends on d, on the filters' false-positive rate and on how much the sets overlap);
+  // the rest runs in chunks sized to fill the queue at most half.  Few, large chunks matter for
+  // d = 2, where one seed is ~36 000 probes and every kernel tail costs.
+  const double L = p.a.n ? (double)c->run_res_bytes / (double)p.a.n : 1.0;
+  const double s1 = p.sigma - 1.0;
+  double probes = 1.0 + s1 * L + (p.indels ? (L + p.sigma * (L + 1.0)) : 0.0);
+  if (p.differences == 2) probes += s1 * s1 * L * (L - 1.0) / 2.0;
+  const uint64_t guess = (uint64_t)std::max(1.0, (double)(cap / 2) / (probes * 0.03));
+  const uint64_t first_n = std::min<uint64_t>(count, std::min<uint64_t>(guess, std::max<uint64_t>(count / 32, 4096)));
+  int rc = run_chunks(c, p, 0, first_n, first_n, 0, launches);
+  if (rc || first_n == count) return rc;
+  const double per_seed = std::max(1.0, (double)c->h_counters[CTR_GQ] / (double)first_n);
+  uint64_t per_chunk = (uint64_t)std::max(1.0, (double)(cap / 2) / (per_seed * 1.5));
+  per_chunk = std::max<uint64_t>(per_chunk, (count - first_n + 63) / 64);
+  return run_chunks(c, p, first_n, count - first_n, per_chunk, 0, launches);
+}
+
 extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count) {
   if (!c || !a) return fail(c, CB_ERR_INVALID, "cb_run: NULL argument");
   if (!c->b) return fail(c, CB_ERR_STATE, "cb_run: set B has not been built (cb_build_b / cb_set_b)");
@@ -536,6 +640,7 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     p.b = cb_view_of(c->b);
     p.a_first = first;
     p.a_count = count;
+    c->run_res_bytes = a->res_bytes;
     p.table = c->d_table;
     p.table_mask = c->slots - 1;
     p.bloom = c->d_bloom;
@@ -566,16 +671,9 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     p.count_bloom = 1;
     p.differences = c->cfg.differences;
     p.indels = c->cfg.indels != 0;
-    // d = 2: split each seed's outer (position, residue) space over several warps when there
-    // are too few seeds to fill the machine
-    p.split = 1;
-    if (c->cfg.differences == 2) {
-      const uint64_t want_items = (uint64_t)c->sm_count * 64 * 4;
-      while (p.split < 64 && count * p.split < want_items) p.split <<= 1;
-    }
-    // Keep the first-level Bloom filter resident in L2 while the probe kernel runs: every probe
-    // reads it, everything else the kernel touches (second-level filter, table, metadata) is
-    // touched once.  Persisting-L2 access window over the filter, streaming for the rest.
+    // Keep the first-level Bloom filter resident in L2 while the probe kernels run: every probe
+    // reads it, everything else they touch (second-level filter, table, metadata) is touched
+    // once.  Persisting-L2 access window over the filter, streaming for the rest.
     bool window = false;
     if (c->d_bloom2 && c->l2_persist_set > 0 && !getenv("CB_NO_L2_WINDOW")) {
       cudaStreamAttrValue av{};
@@ -587,15 +685,13 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
       window = cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
       if (!window) cudaGetLastError();
     }
-    const char* kerr = nullptr;
-    launches = launch_probe(p, c->sm_count, c->stream, &kerr);
+    rc = run_hash_path(c, p, count, &launches);
     if (window) {
       cudaStreamAttrValue av{};
       av.accessPolicyWindow.num_bytes = 0;
       cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
     }
-    if (launches < 0) return fail(c, CB_ERR_LIMIT, "cb_run: %s", kerr ? kerr : "launch failed");
-    CU(c, cudaGetLastError());
+    if (rc) return rc;
   } else {
     rc = cb_run_brute(c, a, first, count, false, &launches);
     if (rc) return rc;
@@ -621,9 +717,9 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
       p.pairs_cap = c->pairs_cap;
       p.no_matrix = 1;
       p.count_bloom = 0;
-      const char* kerr = nullptr;
-      int l2 = launch_probe(p, c->sm_count, c->stream, &kerr);
-      if (l2 < 0) return fail(c, CB_ERR_LIMIT, "cb_run: %s", kerr ? kerr : "launch failed");
+      int l2 = 0;
+      rc = run_hash_path(c, p, count, &l2);
+      if (rc) return rc;
       launches += l2;
     } else {
       int l2 = 0;

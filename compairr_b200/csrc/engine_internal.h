@@ -86,6 +86,10 @@ struct cb_ctx {
   bool matrix_external = false;
   uint64_t rows = 0, cols = 0;
 
+  uint64_t* d_gq_hv = nullptr;      // global candidate queue (enumeration kernel -> table kernel)
+  uint2* d_gq_vs = nullptr;
+  uint32_t* d_overflow = nullptr;
+  uint64_t run_res_bytes = 0;
   cb::PairOut* d_pairs = nullptr;
   uint64_t pairs_cap = 0;
   std::vector<cb_pair> pending;

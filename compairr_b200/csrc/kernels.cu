@@ -160,12 +160,16 @@ __device__ __forceinline__ SeqMeta ld_meta_plain(const SeqRec* p) {
 }
 
 // One thread per set-B sequence.  Identical (sequence, V, J) share ONE slot: the first arrival
-// owns the slot (claims it with a CAS on the index word, publishes the hash, sets the filters),
-// later arrivals verify they really are the same sequence and push themselves onto the slot's
-// occurrence list (atomicExch of the head, SeqRec.next = old head).  So probe chains never walk
-// clusters of duplicates, the exact verify runs once per distinct sequence, and the filters hold
-// distinct keys only.  The reference inserts every sequence into its own slot
-// (overlap.cc:63-128); the set of (seed, hit) matches is the same.
+// owns the slot (one CAS on the index word), later arrivals verify they really are the same
+// sequence and push themselves onto the slot's occurrence list (atomicExch of the head,
+// SeqRec.next = old head).  So probe chains never walk clusters of duplicates, the exact verify
+// runs once per distinct sequence, and the filters hold distinct keys only.  The reference
+// inserts every sequence into its own slot (overlap.cc:63-128); the set of (seed, hit) matches is
+// the same.
+// The index word carries the low 32 bits of the hash above the 32-bit head index, so a thread
+// that meets an occupied slot can tell "possibly my sequence" from the one atomic word it read —
+// no second word to wait for, no fence, no lock.  Slot.hash is written plainly: only the probe
+// kernels (later launches) read it.
 __global__ void __launch_bounds__(256)
 build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __restrict__ hash,
              uint64_t first, uint64_t n, bool ignore_genes, Slot* table, uint64_t mask,
@@ -175,35 +179,33 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
        t += (uint64_t)gridDim.x * blockDim.x) {
     const uint64_t i = first + t;
     const uint64_t h = hash[i];
+    const unsigned long long tagged = (h << 32) | i;  // i < 2^32 - 1 (checked at upload)
     uint64_t slot = table_home(h, mask);
     SeqMeta me;
     bool have_me = false;
     for (;;) {
       unsigned long long* idxp = reinterpret_cast<unsigned long long*>(&table[slot].idx);
-      uint64_t idx = ld_volatile_u64(&table[slot].idx);
-      if (idx == SLOT_EMPTY) {
-        idx = atomicCAS(idxp, SLOT_EMPTY, SLOT_LOCKED);
-        if (idx == SLOT_EMPTY) {  // we own the slot: publish hash, then ourselves as the head
-          *reinterpret_cast<volatile uint64_t*>(&table[slot].hash) = h;
+      unsigned long long cur = ld_volatile_u64(&table[slot].idx);
+      if (cur == SLOT_EMPTY) {
+        cur = atomicCAS(idxp, SLOT_EMPTY, tagged);
+        if (cur == SLOT_EMPTY) {  // we own the slot
+          table[slot].hash = h;
           meta[i].next = SEQ_NIL;  // a set may be built more than once
-          __threadfence();
-          atomicExch(idxp, (unsigned long long)i);
           atomicOr(bloom + bloom_block(h, bloom_blocks), k2 ? bloom1_pattern(h) : bloom_pattern(h));
           if (bloom2) atomicOr(bloom2 + bloom_block(h, bloom2_blocks), bloom_pattern(h));
           break;
         }
       }
-      while (idx == SLOT_LOCKED) idx = ld_volatile_u64(&table[slot].idx);  // owner is publishing
-      if (ld_volatile_u64(&table[slot].hash) == h) {
+      if ((uint32_t)(cur >> 32) == (uint32_t)h) {  // same low hash half: compare the sequences
         if (!have_me) {
           me = ld_meta_plain(meta + i);
           have_me = true;
         }
-        const SeqMeta o = ld_meta_plain(meta + idx);
+        const SeqMeta o = ld_meta_plain(meta + (uint32_t)cur);
         bool same = o.len == me.len && (ignore_genes || (o.v == me.v && o.j == me.j));
         for (uint32_t p = 0; p < me.len && same; p++) same = res[me.off + p] == res[o.off + p];
         if (same) {
-          const unsigned long long old = atomicExch(idxp, (unsigned long long)i);
+          const unsigned long long old = atomicExch(idxp, tagged);
           meta[i].next = (uint32_t)old;
           break;
         }
@@ -286,11 +288,11 @@ __global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ 
   const uint32_t lane = threadIdx.x & 31;
   // warp-uniform trip count: probe_chains() re-converges with warp-wide votes
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
-  for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); i0 < P.a_count;
+  for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); i0 < P.w_count;
        i0 += stride) {
-    const uint64_t i = i0 + lane;
-    const bool in = i < P.a_count;
-    const uint64_t sidx = P.a_first + (in ? i : 0);
+    const bool in = i0 + lane < P.w_count;
+    const uint64_t i = P.w_first + (in ? i0 + lane : 0);  // relative to a_first
+    const uint64_t sidx = P.a_first + i;
     const uint64_t h = P.a.hash[sidx];
     bool walking = in;
     if (P.use_bloom && in) {
@@ -307,9 +309,9 @@ __global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ 
 int launch_variant_kernels(const ProbeParams& p, int sm_count, cudaStream_t st, const char** err);  // variant.cu
 
 int launch_probe(const ProbeParams& p, int sm_count, cudaStream_t st, const char** err) {
-  if (p.a_count == 0) return 0;
+  if (p.w_count == 0) return 0;
   if (p.differences == 0) {
-    const uint64_t blocks = (p.a_count + 255) / 256;
+    const uint64_t blocks = (p.w_count + 255) / 256;
     const uint64_t cap = (uint64_t)sm_count * 8;
     identical_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(p);
     return 1;

@@ -21,7 +21,9 @@ enum Counter : int {
   CTR_DUPS = 4,
   CTR_MAXLEN = 5,
   CTR_PROBES = 6,
-  CTR_COUNT = 8
+  CTR_GQ = 7,       // cursor of the global candidate queue (may exceed capacity: overflow)
+  CTR_OVERFLOW = 8, // chunks whose candidates did not fit the queue (they are redone smaller)
+  CTR_COUNT = 16
 };
 
 struct DeviceSetView {
@@ -35,8 +37,15 @@ struct DeviceSetView {
 struct ProbeParams {
   DeviceSetView a;
   DeviceSetView b;
-  uint64_t a_first;  // first seed of this launch
-  uint64_t a_count;  // seeds in this launch
+  uint64_t a_first;  // first seed of the run: matrix rows / queue entries are relative to it
+  uint64_t a_count;  // seeds in the run
+  uint64_t w_first;  // this launch works on seeds [a_first + w_first, a_first + w_first + w_count)
+  uint64_t w_count;
+  // global candidate queue between the enumeration kernel and the table kernel
+  uint64_t* gq_hv;
+  uint2* gq_vs;      // {variant descriptor, seed number relative to a_first}
+  uint64_t gq_cap;
+  uint32_t* overflow_chunks;  // ids of chunks that overflowed the queue (first 64)
   const Slot* table;
   uint64_t table_mask;
   const unsigned long long* bloom;   // first-level filter (sized to stay L2-resident)
@@ -96,6 +105,8 @@ void launch_count_dups(DeviceSetView s, unsigned long long* counters, cudaStream
 // K3+K4: enumerate variants, Bloom, probe, verify, accumulate.  Returns launches made, <0 on
 // a configuration the kernels cannot take (message in *err).
 int launch_probe(const ProbeParams& p, int sm_count, cudaStream_t st, const char** err);
+// K4 as its own kernel: consumes the global candidate queue (d = 1, 2 paths).
+void launch_table_stage(const ProbeParams& p, int sm_count, uint32_t chunk_id, cudaStream_t st);
 
 // Closed-form variant count of seeds [first, first+count) summed into counters[CTR_PROBES]
 // (bookkeeping for the probes/s metric; not part of the timed hot path).

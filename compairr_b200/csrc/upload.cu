@@ -284,6 +284,12 @@ int set_b_impl(cb_ctx* c, const HostCols& h) {
   int rc = cb_bind_device(c);
   if (rc) return rc;
   c->stats.ms_hash_b = c->stats.ms_build_b = c->stats.ms_dups_b = 0;
+  if (c->b_owned && c->b) {  // replacing our own copy of set B: give its memory back to the pool first
+    cudaStreamSynchronize(c->stream);
+    cb_free_dset(c->b);
+    c->b = nullptr;
+    c->b_owned = false;
+  }
   BuiltTable bt;
   const bool hash_path = c->cfg.differences <= MAXDIFF_HASH;
   if (hash_path) {

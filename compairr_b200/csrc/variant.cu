@@ -82,25 +82,21 @@ __device__ __forceinline__ void ring_push(WarpCtx& c, bool pass, uint64_t hv, ui
   __syncwarp();
 }
 
-// Table stage for n <= 32 queued candidates; called by the whole warp.  Out of line: it is rare
-// (< 1 % of probes reach it) and keeping it out of the enumeration loop keeps that loop lean.
-__device__ __noinline__ uint32_t drain_table(const ProbeParams* __restrict__ P, unsigned char* wb,
-                                             uint32_t head, uint32_t n) {
-  const uint32_t lane = threadIdx.x & 31;
-  const bool act = lane < n;
-  const uint32_t e = (head + lane) & (VK_QCAP - 1);
-  uint64_t hv = 0;
-  uint32_t var = 0, slocal = 0;
-  if (act) {
-    hv = q_hv(wb, 1)[e];
-    var = q_var(wb, 1)[e];
-    slocal = q_seed(wb, 1)[e];
-  }
-  return probe_chains(P, act, hv, var, P->a_first + slocal, slocal, nullptr, 0);
-}
-
+// Hand n <= 32 queued candidates to the table stage: one cursor bump per warp, coalesced stores
+// into the global candidate queue.  The table stage is a separate kernel (table_kernel) — thread
+// per candidate, whole GPU's worth of parallelism behind its dependent loads — so the enumeration
+// kernel contains no call, no verify code and no matrix atomics, and its registers are its own.
+// If the queue is full the entries are dropped and the cursor shows it: the host redoes that
+// chunk of seeds in smaller pieces (the enumeration kernel has no other side effect).
 __device__ __forceinline__ void q2_drain(const ProbeParams& P, WarpCtx& c, uint32_t n) {
-  c.nmatch += drain_table(&P, c.wb, c.q2.head, n);
+  unsigned long long pos = 0;
+  if (c.lane == 0) pos = atomicAdd(P.counters + CTR_GQ, (unsigned long long)n);
+  pos = __shfl_sync(FULL, pos, 0);
+  if (c.lane < n && pos + n <= P.gq_cap) {
+    const uint32_t e = (c.q2.head + c.lane) & (VK_QCAP - 1);
+    P.gq_hv[pos + c.lane] = q_hv(c.wb, 1)[e];
+    P.gq_vs[pos + c.lane] = make_uint2(q_var(c.wb, 1)[e], q_seed(c.wb, 1)[e]);
+  }
   __syncwarp();
   c.q2.head = (c.q2.head + n) & (VK_QCAP - 1);
   c.q2.count -= n;
@@ -384,15 +380,15 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant1_kernel(const __grid_co
 
   for (uint32_t i = threadIdx.x; i < P.zrows * SIGMA; i += VK_THREADS) z[i] = P.ztab[i];
   __syncthreads();
-  const uint64_t n_batches = (P.a_count + VK_WB - 1) / VK_WB;
+  const uint64_t n_batches = (P.w_count + VK_WB - 1) / VK_WB;
 
   for (;;) {
     unsigned long long b = 0;
     if (lane == 0) b = atomicAdd(P.counters + CTR_WORK, 1ull);
     b = __shfl_sync(FULL, b, 0);
     if (b >= n_batches) break;
-    const uint64_t first = b * VK_WB;
-    const uint32_t nb = (uint32_t)((P.a_count - first < VK_WB) ? P.a_count - first : VK_WB);
+    const uint64_t first = P.w_first + b * VK_WB;  // relative to a_first
+    const uint32_t nb = (uint32_t)((P.w_first + P.w_count - first < VK_WB) ? P.w_first + P.w_count - first : VK_WB);
     __syncwarp();  // previous batch fully consumed
     if (lane < nb * 2)
       reinterpret_cast<uint4*>(b_meta)[lane] =
@@ -416,7 +412,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant1_kernel(const __grid_co
     }
   }
   finish(P, c);
-  flush_counters(P, c.nmatch, P.count_bloom ? c.npass : 0);
+  flush_counters(P, 0, P.count_bloom ? c.npass : 0);
 }
 
 // ---- d = 2 -------------------------------------------------------------------------------------------
@@ -437,7 +433,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant2_kernel(const __grid_co
   for (uint32_t i = threadIdx.x; i < P.zrows * SIGMA; i += VK_THREADS) z[i] = P.ztab[i];
   __syncthreads();
 
-  const uint64_t total_items = P.a_count * P.split;
+  const uint64_t total_items = P.w_count * P.split;
   const uint32_t split_mask = P.split - 1;
   const uint32_t split_shift = 31 - __clz(P.split);
   for (;;) {
@@ -445,7 +441,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant2_kernel(const __grid_co
     if (lane == 0) item = atomicAdd(P.counters + CTR_WORK, 1ull);
     item = __shfl_sync(FULL, item, 0);
     if (item >= total_items) break;
-    const uint32_t slocal = (uint32_t)(item >> split_shift);
+    const uint32_t slocal = (uint32_t)(P.w_first + (item >> split_shift));
     const uint32_t part = (uint32_t)item & split_mask;
     const uint64_t sidx = P.a_first + slocal;
     const uint64_t off_len = __ldg(&P.a.meta[sidx].off_len);  // same address in all lanes: one broadcast
@@ -459,7 +455,41 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant2_kernel(const __grid_co
     phase_b<SIGMA, false>(P, c, z, sres, sc, L, h, slocal, part, P.split);
   }
   finish(P, c);
-  flush_counters(P, c.nmatch, P.count_bloom ? c.npass : 0);
+  flush_counters(P, 0, P.count_bloom ? c.npass : 0);
+}
+
+// ---- K4: the table stage ----------------------------------------------------------------------------
+//
+// One thread per queued candidate (hash, variant, seed): probe chain, exact verify against the head
+// of the occurrence list, score + matrix atomics + pair append per occurrence.  A queue that
+// overflowed is not touched at all: the chunk is recorded and redone by the host.
+__global__ void __launch_bounds__(256) table_kernel(const __grid_constant__ ProbeParams P, uint32_t chunk_id) {
+  const unsigned long long filled = P.counters[CTR_GQ];
+  if (filled > P.gq_cap) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+      const unsigned long long k = atomicAdd(P.counters + CTR_OVERFLOW, 1ull);
+      if (k < 64) P.overflow_chunks[k] = chunk_id;
+    }
+    return;
+  }
+  uint32_t nmatch = 0;
+  const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
+  for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); i0 < filled; i0 += stride) {
+    const uint64_t i = i0 + (threadIdx.x & 31);
+    const bool act = i < filled;
+    uint64_t hv = 0;
+    uint2 vs = make_uint2(0, 0);
+    if (act) {
+      hv = P.gq_hv[i];
+      vs = P.gq_vs[i];
+    }
+    nmatch += probe_chains(&P, act, hv, vs.x, P.a_first + vs.y, vs.y, nullptr, 0);
+  }
+  flush_counters(P, nmatch, 0);
+}
+
+void launch_table_stage(const ProbeParams& p, int sm_count, uint32_t chunk_id, cudaStream_t st) {
+  table_kernel<<<sm_count * 8, 256, 0, st>>>(p, chunk_id);
 }
 
 // ---- launch ------------------------------------------------------------------------------------------
@@ -497,7 +527,7 @@ int launch_variant_kernels(const ProbeParams& p, int sm_count, cudaStream_t st, 
   }
   if (p.differences == 1) {
     const size_t smem = vk_layout(p.zrows, p.sigma, p.lmax, p.indels, true).total;
-    const uint64_t blocks = ((p.a_count + VK_WB - 1) / VK_WB + VK_WARPS - 1) / VK_WARPS;
+    const uint64_t blocks = ((p.w_count + VK_WB - 1) / VK_WB + VK_WARPS - 1) / VK_WARPS;
     if (p.sigma == 20)
       return p.indels ? launch_one(variant1_kernel<20, true>, p, smem, blocks, sm_count, st, err)
                       : launch_one(variant1_kernel<20, false>, p, smem, blocks, sm_count, st, err);
@@ -505,7 +535,7 @@ int launch_variant_kernels(const ProbeParams& p, int sm_count, cudaStream_t st, 
                     : launch_one(variant1_kernel<4, false>, p, smem, blocks, sm_count, st, err);
   }
   const size_t smem = vk_layout(p.zrows, p.sigma, p.lmax, false, false).total;
-  const uint64_t ctas = (p.a_count * p.split + VK_WARPS - 1) / VK_WARPS;
+  const uint64_t ctas = (p.w_count * p.split + VK_WARPS - 1) / VK_WARPS;
   return p.sigma == 20 ? launch_one(variant2_kernel<20>, p, smem, ctas, sm_count, st, err)
                        : launch_one(variant2_kernel<4>, p, smem, ctas, sm_count, st, err);
 }
