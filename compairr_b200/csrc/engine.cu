@@ -365,6 +365,7 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
 static int build_table_for(cb_ctx* c, cb_dset* s, bool with_bloom, BuiltTable* out) {
   int rc = cb_table_alloc(c, s->n, with_bloom, out);
   if (rc) return rc;
+  launch_reset_next(s->d_meta, s->n, c->stream);  // the set may have been inserted before
   cb_table_insert(c, *out, s, 0, s->n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {

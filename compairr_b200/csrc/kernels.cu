@@ -189,8 +189,7 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
       if (cur == SLOT_EMPTY) {
         cur = atomicCAS(idxp, SLOT_EMPTY, tagged);
         if (cur == SLOT_EMPTY) {  // we own the slot
-          table[slot].hash = h;
-          meta[i].next = SEQ_NIL;  // a set may be built more than once
+          table[slot].hash = h;  // SeqRec.next is SEQ_NIL already (pack kernel / reset_next_kernel)
           atomicOr(bloom + bloom_block(h, bloom_blocks), k2 ? bloom1_pattern(h) : bloom_pattern(h));
           if (bloom2) atomicOr(bloom2 + bloom_block(h, bloom2_blocks), bloom_pattern(h));
           break;
@@ -213,6 +212,19 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
       slot = (slot + 1) & mask;
     }
   }
+}
+
+// Before a set is inserted a second time its occurrence links are reset — one streaming pass
+// instead of a random store per slot owner inside the build kernel.
+__global__ void __launch_bounds__(256) reset_next_kernel(SeqRec* meta, uint64_t n) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+    meta[i].next = SEQ_NIL;
+}
+
+void launch_reset_next(SeqRec* meta, uint64_t n, cudaStream_t st) {
+  if (n == 0) return;
+  const uint64_t blocks = (n + 255) / 256;
+  reset_next_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(meta, n);
 }
 
 void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, uint64_t first, uint64_t n,

@@ -95,7 +95,9 @@ void launch_hash(const SeqRec* meta, const uint8_t* res, uint64_t n, const uint6
 
 // K2: table + Bloom build, duplicate count
 void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st);
-// Inserts sequences [first, first + n) of the set; writes their SeqRec.next links.
+void launch_reset_next(SeqRec* meta, uint64_t n, cudaStream_t st);
+// Inserts sequences [first, first + n) of the set; writes their SeqRec.next links (which must be
+// SEQ_NIL on entry).
 void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, uint64_t first, uint64_t n,
                   bool ignore_genes, Slot* table, uint64_t mask, unsigned long long* bloom,
                   uint32_t bloom_blocks, bool k2, unsigned long long* bloom2, uint32_t bloom2_blocks,

@@ -270,6 +270,7 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
       }
       table->release();
       *table = fresh;
+      launch_reset_next(s->d_meta, n, ks);
       cb_table_insert(c, *table, s, 0, n);
     }
     UP(cudaGetLastError());
