@@ -24,7 +24,10 @@ with open(out, "w") as f:
     src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(io.StringIO(src)))
     if len(r) > 3:
-        h, data = r[1], r[2:]
+        # several kernels: keep the first kernel's block (blocks are separated by "Kernel Name" rows)
+        ends = [i for i, row in enumerate(r) if row and row[0] == "Kernel Name"]
+        stop = ends[1] if len(ends) > 1 else len(r)
+        h, data = r[1], [row for row in r[2:stop] if len(row) == len(r[1])]
         ix = {x: i for i, x in enumerate(h)}
         tot = sum(int(x[ix["# Samples"]] or 0) for x in data) or 1
         stalls = [x for x in h if x.startswith("stall_") and "Not Issued" not in x]
