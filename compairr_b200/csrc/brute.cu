@@ -23,6 +23,7 @@
 
 #include "device_utils.cuh"
 #include "engine_internal.h"
+#include "hamming_tc.cuh"
 
 using namespace cb;
 
@@ -295,6 +296,35 @@ static int bucket_sort(cb_ctx* c, DeviceSetView v, uint64_t first, uint64_t n, u
 }
 
 // Set B: sort + pack, once.
+// Pack the sequences of a bucket-sorted order (4 residues per word, word-major inside a bucket).
+static int pack_order(cb_ctx* c, DeviceSetView v, const uint32_t* order, uint64_t n,
+                      const std::vector<uint64_t>& keys, const std::vector<uint64_t>& starts,
+                      std::vector<uint64_t>& pack_off, uint32_t** packed) {
+  cudaStream_t st = c->stream;
+  const size_t nb = keys.size();
+  pack_off.assign(nb + 1, 0);
+  for (size_t i = 0; i < nb; i++) {
+    const uint64_t len = keys[i] >> 44;
+    pack_off[i + 1] = pack_off[i] + ((len + 3) / 4) * (starts[i + 1] - starts[i]);
+  }
+  *packed = nullptr;
+  if (n == 0) return CB_OK;
+  uint64_t *d_starts = nullptr, *d_poff = nullptr;
+  BCU(c, cb_dmalloc(packed, std::max<uint64_t>(pack_off[nb], 1) * 4));
+  BCU(c, cb_dmalloc(&d_starts, (nb + 1) * 8));
+  BCU(c, cb_dmalloc(&d_poff, (nb + 1) * 8));
+  BCU(c, cudaMemcpyAsync(d_starts, starts.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
+  BCU(c, cudaMemcpyAsync(d_poff, pack_off.data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
+  const uint64_t blocks = (n + 255) / 256;
+  pack_words_kernel<<<(unsigned)std::min<uint64_t>(blocks, 148 * 16), 256, 0, st>>>(
+      v.meta, v.res, order, d_starts, d_poff, (uint32_t)nb, n, *packed);
+  BCU(c, cudaGetLastError());
+  BCU(c, cudaStreamSynchronize(st));
+  cb_dfree(d_starts);
+  cb_dfree(d_poff);
+  return CB_OK;
+}
+
 static int cb_build_brute_b(cb_ctx* c, cb_dset* b) {
   uint32_t** order = &b->d_order;
   std::vector<uint64_t>* keys = &b->bucket_key;
@@ -305,28 +335,7 @@ static int cb_build_brute_b(cb_ctx* c, cb_dset* b) {
   DeviceSetView v = cb_view_of(b);
   int rc = bucket_sort(c, v, 0, v.n, order, *keys, *starts);
   if (rc) return rc;
-  cudaStream_t st = c->stream;
-  const size_t nb = keys->size();
-  pack_off->assign(nb + 1, 0);
-  for (size_t i = 0; i < nb; i++) {
-    const uint64_t len = (*keys)[i] >> 44;
-    (*pack_off)[i + 1] = (*pack_off)[i] + ((len + 3) / 4) * ((*starts)[i + 1] - (*starts)[i]);
-  }
-  if (v.n == 0) return CB_OK;
-  uint64_t *d_starts = nullptr, *d_poff = nullptr;
-  BCU(c, cb_dmalloc(packed, std::max<uint64_t>((*pack_off)[nb], 1) * 4));
-  BCU(c, cb_dmalloc(&d_starts, (nb + 1) * 8));
-  BCU(c, cb_dmalloc(&d_poff, (nb + 1) * 8));
-  BCU(c, cudaMemcpyAsync(d_starts, starts->data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
-  BCU(c, cudaMemcpyAsync(d_poff, pack_off->data(), (nb + 1) * 8, cudaMemcpyHostToDevice, st));
-  const uint64_t blocks = (v.n + 255) / 256;
-  pack_words_kernel<<<(unsigned)std::min<uint64_t>(blocks, 148 * 16), 256, 0, st>>>(
-      v.meta, v.res, *order, d_starts, d_poff, (uint32_t)nb, v.n, *packed);
-  BCU(c, cudaGetLastError());
-  BCU(c, cudaStreamSynchronize(st));
-  cb_dfree(d_starts);
-  cb_dfree(d_poff);
-  return CB_OK;
+  return pack_order(c, v, *order, v.n, *keys, *starts, *pack_off, packed);
 }
 
 int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bool pairs_only,
@@ -348,8 +357,25 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
   rc = bucket_sort(c, cb_view_of(a), first, count, &a_order, a_keys, a_starts);
   if (rc) return rc;
   *launches += 3;
+  std::vector<uint64_t> a_poff;
+  uint32_t* a_packed = nullptr;
+  const bool use_tc = !(cfg.flags & CB_FLAG_NO_TENSOR);
+  if (use_tc) {  // the tensor-core kernel builds its one-hot tiles from packed words on both sides
+    rc = pack_order(c, cb_view_of(a), a_order, count, a_keys, a_starts, a_poff, &a_packed);
+    if (rc) {
+      cb_dfree(a_order);
+      return rc;
+    }
+    (*launches)++;
+  }
 
-  // merge-join the two sorted bucket directories; group joins by packed width
+  // merge-join the two sorted bucket directories.  Bucket pairs that are a dense contraction worth
+  // the tensor cores (one-hot width fits the shared-memory tiles, enough rows to fill a 128 x 256
+  // tile several times) go to the tcgen05 kernel; the rest to the CUDA-core kernel, grouped by
+  // packed width.
+  const uint32_t sigma = (uint32_t)cfg.alphabet_size;
+  std::vector<TcItem> tc_items;
+  uint32_t tc_kmax = 0;
   std::vector<BruteJoin> joins[4];  // W = 4, 8, 16, generic
   uint32_t max_words[4] = {4, 8, 16, 0};
   const uint64_t sm_target = (uint64_t)c->sm_count * 8;
@@ -369,12 +395,79 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
     J.tiles_b = (J.b_n + J.b_chunk - 1) / J.b_chunk;
     const uint32_t words = (J.len + 3) / 4;
     const int cls = words <= 4 ? 0 : words <= 8 ? 1 : words <= 16 ? 2 : 3;
-    if (cls == 3) max_words[3] = std::max(max_words[3], (words + 3) & ~3u);
-    if (J.len > 0) joins[cls].push_back(J);
+    const uint32_t kpad = (sigma * J.len + 31) & ~31u;
+    const bool dense = use_tc && J.len > 0 && kpad <= TC_KMAX && (int)J.len > cfg.differences &&
+                       (uint64_t)J.a_n * J.b_n >= (uint64_t)TC_M * TC_N * 4 && J.a_n >= 32 && J.b_n >= 64;
+    if (dense) {
+      // one item = one 128-row A tile against a chunk of B; chunk sized so the whole join gives at
+      // least a few items per SM
+      const uint32_t a_tiles = (J.a_n + TC_M - 1) / TC_M;
+      uint32_t b_chunk = 64 * TC_N;
+      while (b_chunk > TC_N && (uint64_t)a_tiles * ((J.b_n + b_chunk - 1) / b_chunk) < sm_target / 2) b_chunk >>= 1;
+      for (uint32_t a0 = 0; a0 < J.a_n; a0 += TC_M)
+        for (uint32_t b0 = 0; b0 < J.b_n; b0 += b_chunk) {
+          TcItem it{};
+          it.a_start = J.a_start + a0;
+          it.a_n = std::min<uint32_t>(TC_M, J.a_n - a0);
+          it.a_pack = a_poff[ia];
+          it.a_pos = a0;
+          it.a_bucket = J.a_n;
+          it.b_start = J.b_start + b0;
+          it.b_n = std::min<uint32_t>(b_chunk, J.b_n - b0);
+          it.b_pack = J.b_pack;
+          it.b_pos = b0;
+          it.b_bucket = J.b_n;
+          it.len = J.len;
+          it.kpad = kpad;
+          tc_items.push_back(it);
+        }
+      tc_kmax = std::max(tc_kmax, kpad);
+    } else {
+      if (cls == 3) max_words[3] = std::max(max_words[3], (words + 3) & ~3u);
+      if (J.len > 0) joins[cls].push_back(J);
+    }
     ia++;
     ib++;
   }
   int ret = CB_OK;
+  if (!tc_items.empty()) {
+    TcItem* d_items = nullptr;
+    BCU(c, cb_dmalloc(&d_items, tc_items.size() * sizeof(TcItem)));
+    BCU(c, cudaMemcpyAsync(d_items, tc_items.data(), tc_items.size() * sizeof(TcItem), cudaMemcpyHostToDevice, st));
+    TcLaunch T{};
+    T.a = cb_view_of(a);
+    T.b = cb_view_of(b);
+    T.a_order = a_order;
+    T.b_order = *b_order;
+    T.a_packed = a_packed;
+    T.b_packed = *b_packed;
+    T.items = d_items;
+    T.n_items = (uint32_t)tc_items.size();
+    T.kmax = tc_kmax;
+    T.sigma = sigma;
+    T.a_first = first;
+    T.matrix = c->d_matrix;
+    T.n_cols = c->cols;
+    T.pairs = c->d_pairs;
+    T.pairs_cap = c->pairs_cap;
+    T.counters = c->d_counters;
+    T.score = cfg.score;
+    T.differences = cfg.differences;
+    T.ignore_counts = cfg.ignore_counts != 0;
+    T.existence = cfg.mode == CB_MODE_EXISTENCE;
+    T.no_matrix = (cfg.no_matrix != 0) || pairs_only;
+    T.want_pairs = cfg.want_pairs != 0;
+    const char* kerr = nullptr;
+    if (launch_hamming_tc(T, c->sm_count, st, &kerr) < 0) {
+      ret = cb_fail(c, CB_ERR_LIMIT, "d>=3 tensor-core kernel: %s", kerr ? kerr : "launch failed");
+    } else {
+      cudaError_t e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) ret = cb_fail(c, CB_ERR_CUDA, "d>=3 tensor-core kernel: %s", cudaGetErrorString(e));
+      (*launches)++;
+    }
+    cb_dfree(d_items);
+  }
   for (int cls = 0; cls < 4 && ret == CB_OK; cls++) {
     std::vector<BruteJoin>& js = joins[cls];
     if (js.empty()) continue;
@@ -447,5 +540,6 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
     cb_dfree(d_joins);
   }
   cb_dfree(a_order);
+  cb_dfree(a_packed);
   return ret;
 }

@@ -144,3 +144,21 @@ def test_upload_of_a_slice_and_long_sequences():
         eng.run_a(NarrowSet.from_seqset(a.slice(250, a.n - 250)))
         assert np.array_equal(eng.matrix(), mo)
         assert _pairs(eng.drain_pairs()) == _pairs(po)
+
+
+@pytest.mark.parametrize("d", [3, 4])
+@pytest.mark.parametrize("nucleotides", [False, True])
+def test_d3_tensor_core_path(d, nucleotides):
+    """Buckets big enough for the tcgen05 one-hot GEMM kernel (-g: length buckets only): same
+    matrix and pairs as the oracle's pairwise definition, and as the CUDA-core kernel."""
+    pool = synth.make_pool(71, 1500)
+    a = synth.make_set(72, 4, 1500, pool=pool, nucleotides=nucleotides)
+    b = synth.make_set(73, 5, 2000, pool=pool, nucleotides=nucleotides)
+    kw = dict(differences=d, ignore_genes=True)
+    m, p, info = overlap(a, b, OverlapOptions(want_pairs=True, nucleotides=nucleotides, **kw))
+    mo, po, io = orc.overlap(a, b, want_pairs=True, threads=4, **kw)
+    assert np.array_equal(m, mo)
+    assert _pairs(p) == _pairs(po)
+    assert info["run"]["matches"] == io["matches"]
+    m2, p2, _ = overlap(a, b, OverlapOptions(want_pairs=True, nucleotides=nucleotides, flags=4, **kw))
+    assert np.array_equal(m2, mo) and _pairs(p2) == _pairs(po)
