@@ -14,6 +14,8 @@
 // DESIGN.md (its epilogue, one TMEM read per pair, bounds it near this kernel's rate for
 // CDR3-length sequences); it is not built yet.
 #include <cuda_runtime.h>
+#include <cstdio>
+#include <cstdlib>
 #include <stdio.h>
 
 #include <algorithm>
@@ -375,6 +377,7 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
   // packed width.
   const uint32_t sigma = (uint32_t)cfg.alphabet_size;
   std::vector<TcItem> tc_items;
+  const uint32_t tc_kp = tc_cols_per_position(sigma);
   uint32_t tc_kmax = 0;
   std::vector<BruteJoin> joins[4];  // W = 4, 8, 16, generic
   uint32_t max_words[4] = {4, 8, 16, 0};
@@ -395,20 +398,20 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
     J.tiles_b = (J.b_n + J.b_chunk - 1) / J.b_chunk;
     const uint32_t words = (J.len + 3) / 4;
     const int cls = words <= 4 ? 0 : words <= 8 ? 1 : words <= 16 ? 2 : 3;
-    const uint32_t kpad = (sigma * J.len + 31) & ~31u;
-    const bool dense = use_tc && J.len > 0 && kpad <= TC_KMAX && (int)J.len > cfg.differences &&
-                       (uint64_t)J.a_n * J.b_n >= (uint64_t)TC_M * TC_N * 4 && J.a_n >= 32 && J.b_n >= 64;
+    const uint32_t kpad = (tc_kp * J.len + 31) & ~31u;
+    const bool dense = use_tc && tc_kp != 0 && J.len > 0 && kpad <= TC_KMAX && (int)J.len > cfg.differences &&
+                       (uint64_t)J.a_n * J.b_n >= (uint64_t)128 * 256 * 4 && J.a_n >= 32 && J.b_n >= 64;
     if (dense) {
       // one item = one 128-row A tile against a chunk of B; chunk sized so the whole join gives at
       // least a few items per SM
-      const uint32_t a_tiles = (J.a_n + TC_M - 1) / TC_M;
-      uint32_t b_chunk = 64 * TC_N;
-      while (b_chunk > TC_N && (uint64_t)a_tiles * ((J.b_n + b_chunk - 1) / b_chunk) < sm_target / 2) b_chunk >>= 1;
-      for (uint32_t a0 = 0; a0 < J.a_n; a0 += TC_M)
+      const uint32_t a_tiles = (J.a_n + TC_MA - 1) / TC_MA;
+      uint32_t b_chunk = 128 * TC_NB;
+      while (b_chunk > TC_NB && (uint64_t)a_tiles * ((J.b_n + b_chunk - 1) / b_chunk) < sm_target / 2) b_chunk >>= 1;
+      for (uint32_t a0 = 0; a0 < J.a_n; a0 += TC_MA)
         for (uint32_t b0 = 0; b0 < J.b_n; b0 += b_chunk) {
           TcItem it{};
           it.a_start = J.a_start + a0;
-          it.a_n = std::min<uint32_t>(TC_M, J.a_n - a0);
+          it.a_n = std::min<uint32_t>(TC_MA, J.a_n - a0);
           it.a_pack = a_poff[ia];
           it.a_pos = a0;
           it.a_bucket = J.a_n;
@@ -431,6 +434,10 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
   }
   int ret = CB_OK;
   if (!tc_items.empty()) {
+    // largest first: the kernel's CTAs pull items from a counter
+    std::stable_sort(tc_items.begin(), tc_items.end(), [](const TcItem& x, const TcItem& y) {
+      return (uint64_t)x.a_n * x.b_n * x.kpad > (uint64_t)y.a_n * y.b_n * y.kpad;
+    });
     TcItem* d_items = nullptr;
     BCU(c, cb_dmalloc(&d_items, tc_items.size() * sizeof(TcItem)));
     BCU(c, cudaMemcpyAsync(d_items, tc_items.data(), tc_items.size() * sizeof(TcItem), cudaMemcpyHostToDevice, st));
@@ -444,7 +451,7 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
     T.items = d_items;
     T.n_items = (uint32_t)tc_items.size();
     T.kmax = tc_kmax;
-    T.sigma = sigma;
+    T.aa = tc_kp == 8;
     T.a_first = first;
     T.matrix = c->d_matrix;
     T.n_cols = c->cols;
@@ -457,12 +464,17 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
     T.existence = cfg.mode == CB_MODE_EXISTENCE;
     T.no_matrix = (cfg.no_matrix != 0) || pairs_only;
     T.want_pairs = cfg.want_pairs != 0;
+    const char* dbg = getenv("CB_TC_DEBUG");
+    cudaEvent_t e0, e1;
+    if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     const char* kerr = nullptr;
     if (launch_hamming_tc(T, c->sm_count, st, &kerr) < 0) {
       ret = cb_fail(c, CB_ERR_LIMIT, "d>=3 tensor-core kernel: %s", kerr ? kerr : "launch failed");
     } else {
       cudaError_t e = cudaGetLastError();
+      if (dbg) cudaEventRecord(e1, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (dbg) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); fprintf(stderr, "[tc] items=%u kernel %.3f ms\n", T.n_items, ms); }
       if (e != cudaSuccess) ret = cb_fail(c, CB_ERR_CUDA, "d>=3 tensor-core kernel: %s", cudaGetErrorString(e));
       (*launches)++;
     }

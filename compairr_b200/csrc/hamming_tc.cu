@@ -23,11 +23,11 @@
 
 namespace cb {
 
-constexpr int TC_THREADS = 256;  // warps 0-3: epilogue (one TMEM lane quarter each); warps 4-7: tile builders
+constexpr int TC_THREADS = 416;  // warps 0-7: epilogue; 8-11: tile builders; 12: MMA issue
 constexpr uint32_t TC_IDESC = (2u << 4)              // D format: S32
                               | (0u << 7) | (0u << 10)  // A, B format: unsigned 8-bit
-                              | ((TC_N >> 3) << 17)     // N
-                              | ((TC_M >> 4) << 24);    // M
+                              | ((TC_NB >> 3) << 17)    // N
+                              | ((TC_ROWS >> 4) << 24); // M
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
@@ -64,150 +64,299 @@ __device__ __forceinline__ void mbar_wait(uint32_t mbar, uint32_t phase) {
       : "memory");
 }
 
-// byte offset of (row, k) inside a one-hot tile of `rows` rows
-__device__ __forceinline__ uint32_t onehot_off(uint32_t row, uint32_t k, uint32_t rows) {
-  return (k >> 4) * (rows * 16) + (row >> 3) * 128 + (row & 7) * 16 + (k & 15);
-}
-
-// Zero a tile and write the one-hot image of n sequences of a bucket into it; executed by
-// `nthreads` threads numbered t0 = 0..nthreads-1 that share named barrier `bar`.  The residues come
-// from the bucket's packed array (4 per word, word-major), so the loads coalesce across rows.
-__device__ __forceinline__ void build_tile(uint8_t* tile, uint32_t rows, uint32_t kpad,
-                                           const uint32_t* __restrict__ packed, uint64_t pack_off,
-                                           uint32_t bucket_n, uint32_t pos0, uint32_t n, uint32_t len,
-                                           uint32_t sigma, uint32_t t0, uint32_t nthreads, int bar) {
-  uint4* p = reinterpret_cast<uint4*>(tile);
-  const uint4 z = make_uint4(0, 0, 0, 0);
-  for (uint32_t i = t0; i < rows * kpad / 16; i += nthreads) p[i] = z;
-  asm volatile("bar.sync %0, %1;" ::"r"(bar), "r"(nthreads) : "memory");
-  const uint32_t words = (len + 3) >> 2;
-  for (uint32_t r = t0; r < n; r += nthreads) {
-    const uint32_t* src = packed + pack_off + pos0 + r;
-    for (uint32_t k = 0; k < words; k++) {
-      const uint32_t w = __ldg(src + (uint64_t)k * bucket_n);
+// Write the image of one sequence (or an all-zero row) into row `row` of a 128-row tile: every
+// 16-byte K chunk of the row is written exactly once with one 128-bit store, so tiles are never
+// zeroed.  Residues come from the bucket's packed array (4 per word, word-major: coalesced across
+// rows); `first` holds packed words 0-3 of the row, requested by the caller ahead of time so their
+// L2 latency is off the critical path; later groups of four are requested one group ahead.
+//
+//   AA (alphabet <= 20)   8 bytes per position, values {0,1,2} (code LUT in shared memory),
+//                         one packed word -> two chunks
+//   NT (alphabet <= 4)    4 bytes per position, one-hot; one packed word -> one chunk
+template <bool AA>
+__device__ __forceinline__ void build_row(uint8_t* tile, uint32_t row, bool valid, const uint32_t* __restrict__ src,
+                                          uint32_t stride, uint32_t len, uint32_t kpad, const uint2* lut,
+                                          const uint32_t (&first)[4]) {
+  const uint32_t words = valid ? (len + 3) >> 2 : 0;
+  const uint32_t nw = AA ? kpad >> 5 : kpad >> 4;  // packed-word slots that cover the padded row
+  uint8_t* const dst = tile + (row >> 3) * 128 + (row & 7) * 16;
+  uint32_t cur[4], nxt[4];
 #pragma unroll
-      for (uint32_t bb = 0; bb < 4; bb++) {
-        const uint32_t pp = k * 4 + bb;
-        if (pp < len) tile[onehot_off(r, pp * sigma + ((w >> (8 * bb)) & 0xff), rows)] = 1;
+  for (int j = 0; j < 4; j++) cur[j] = first[j];
+  for (uint32_t g = 0; g * 4 < nw; g++) {
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+      const uint32_t k = (g + 1) * 4 + j;
+      nxt[j] = k < words ? __ldg(src + (uint64_t)k * stride) : 0u;
+    }
+#pragma unroll
+    for (uint32_t j = 0; j < 4; j++) {
+      const uint32_t k = g * 4 + j;
+      if (k < nw) {  // warp-uniform
+        const uint32_t w = cur[j];
+        if (AA) {
+          uint2 c[4];
+#pragma unroll
+          for (uint32_t bb = 0; bb < 4; bb++) {
+            const uint32_t pp = k * 4 + bb;
+            c[bb] = lut[(valid && pp < len) ? ((w >> (8 * bb)) & 31) : 31];
+          }
+          *reinterpret_cast<uint4*>(dst + (2 * k) * (TC_ROWS * 16)) = make_uint4(c[0].x, c[0].y, c[1].x, c[1].y);
+          if (2 * k + 1 < (kpad >> 4))
+            *reinterpret_cast<uint4*>(dst + (2 * k + 1) * (TC_ROWS * 16)) = make_uint4(c[2].x, c[2].y, c[3].x, c[3].y);
+        } else {
+          uint32_t c[4];
+#pragma unroll
+          for (uint32_t bb = 0; bb < 4; bb++) {
+            const uint32_t pp = k * 4 + bb;
+            c[bb] = (valid && pp < len) ? 1u << (((w >> (8 * bb)) & 3) * 8) : 0u;
+          }
+          *reinterpret_cast<uint4*>(dst + k * (TC_ROWS * 16)) = make_uint4(c[0], c[1], c[2], c[3]);
+        }
       }
     }
+#pragma unroll
+    for (int j = 0; j < 4; j++) cur[j] = nxt[j];
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// packed words 0-3 of sequence `r` of a bucket (zeros past the end of the bucket or the sequence)
+__device__ __forceinline__ void request_row(uint32_t (&w)[4], const uint32_t* __restrict__ src, uint32_t stride,
+                                            bool valid, uint32_t len) {
+  const uint32_t words = (len + 3) >> 2;
+#pragma unroll
+  for (uint32_t j = 0; j < 4; j++) w[j] = (valid && j < words) ? __ldg(src + (uint64_t)j * stride) : 0u;
+}
+
+#define TMEM_LD32(v, taddr)                                                                                     \
+  asm volatile(                                                                                                 \
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "                                                                 \
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "                                 \
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"                 \
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),         \
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),   \
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), \
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])  \
+      : "r"(taddr))
+
+// tcgen05.wait::ld, with the destination registers as operands so no use of them can be scheduled
+// ahead of the wait
+#define TMEM_WAIT32(v)                                                                                          \
+  asm volatile("tcgen05.wait::ld.sync.aligned;"                                                                 \
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), \
+                 "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]),       \
+                 "+r"(v[15]), "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]),     \
+                 "+r"(v[22]), "+r"(v[23]), "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]),     \
+                 "+r"(v[29]), "+r"(v[30]), "+r"(v[31])::"memory")
+
+// largest of 32 accumulator columns, as a depth-4 tree of 3-input maxima (VIMNMX3): the common
+// case is "no column of this row reaches the threshold"
+__device__ __forceinline__ int max3(int a, int b, int c) { return max(a, max(b, c)); }
+__device__ __forceinline__ int max32(const uint32_t (&v)[32]) {
+  int t[11];
+#pragma unroll
+  for (int j = 0; j < 10; j++) t[j] = max3((int)v[3 * j], (int)v[3 * j + 1], (int)v[3 * j + 2]);
+  t[10] = max((int)v[30], (int)v[31]);
+  const int u0 = max3(t[0], t[1], t[2]), u1 = max3(t[3], t[4], t[5]), u2 = max3(t[6], t[7], t[8]);
+  return max3(max3(u0, u1, u2), t[9], t[10]);
+}
+
+__device__ __forceinline__ uint32_t hit_mask(const uint32_t (&v)[32], int thr) {
+  uint32_t hits = 0;
+#pragma unroll
+  for (int j = 0; j < 32; j++) hits |= ((int)v[j] >= thr ? 1u : 0u) << j;
+  return hits;
+}
+
+template <bool AA>
 __global__ void __launch_bounds__(TC_THREADS, 1) hamming_tc_kernel(const __grid_constant__ TcLaunch P) {
   extern __shared__ __align__(1024) uint8_t smem[];
-  const uint32_t tid = threadIdx.x, warp = tid >> 5;
-  const bool epilogue_warp = warp < 4;
-  // carve: A tile | B tile 0 | B tile 1 | barriers | tmem pointer
+  const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const bool epilogue_warp = warp < 8, builder_warp = warp >= 8 && warp < 12, mma_warp = warp == 12;
+  // carve: A tiles 0,1 | B tiles 0,1 | candidate queues | code LUT | barriers | tmem pointer | item slot
+  const uint32_t tile_bytes = TC_ROWS * P.kmax;
   uint8_t* const tile_a = smem;
-  uint8_t* const tile_b0 = tile_a + (size_t)TC_M * P.kmax;
-  uint8_t* const tile_b1 = tile_b0 + (size_t)TC_N * P.kmax;
-  uint64_t* const mbar = reinterpret_cast<uint64_t*>(tile_b1 + (size_t)TC_N * P.kmax);  // two barriers
+  uint8_t* const tile_b = smem + 2 * (size_t)tile_bytes;
+  uint2* const queues = reinterpret_cast<uint2*>(smem + 4 * (size_t)tile_bytes);
+  uint2* const lut = queues + 8 * TC_QCAP;
+  uint64_t* const mbar = reinterpret_cast<uint64_t*>(lut + 32);  // two barriers
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(mbar + 2);
+  uint32_t* const item_slot = tmem_slot + 1;
+  uint2* const q = queues + (warp & 7) * TC_QCAP;
 
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                 "r"(2u * TC_N));
+                 "r"(512u));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
   }
-  if (tid == 0) {
+  if (tid == 32) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar)));
     asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(mbar + 1)));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (tid >= 64 && tid < 96) {
+    // residue code, 8 bytes: low digit r & 3 one-hot with weight 2 in bytes 0-3; high digit r >> 2
+    // as weight 2 in byte 4 + (r >> 2), the fifth value (residues 16-19) as 1,1,1,1.  Equal
+    // residues score 8, different ones 0, 2, 4 or 6; entry 31 is the all-zero row.
+    const uint32_t r = tid - 64, h = r >> 2;
+    lut[r] = r < 20 ? make_uint2(2u << ((r & 3) * 8), h < 4 ? 2u << (h * 8) : 0x01010101u) : make_uint2(0, 0);
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  uint32_t phase[2] = {0, 0};
+  uint32_t phases = 0;  // bit b = parity to wait for on barrier b
   uint32_t nmatch = 0;
 
-  for (uint32_t it = blockIdx.x; it < P.n_items; it += gridDim.x) {
+  for (;;) {
+    if (tid == 0) *item_slot = (uint32_t)atomicAdd(P.counters + CTR_WORK, 1ull);
+    __syncthreads();
+    const uint32_t it = *item_slot;
+    if (it >= P.n_items) break;
     const TcItem I = P.items[it];
     const uint32_t kpad = I.kpad, ksteps = kpad >> 5;
-    const int thr = (int)I.len - P.differences;
-    const uint32_t n_tiles = (I.b_n + TC_N - 1) / TC_N;
+    const int thr = (AA ? 8 : 1) * ((int)I.len - P.differences);
+    const uint32_t n_tiles = (I.b_n + TC_NB - 1) / TC_NB;
+    const uint32_t n_at = (I.a_n + TC_ROWS - 1) / TC_ROWS;  // 1 or 2 accumulator row blocks
+    uint32_t qn = 0;                                         // this warp's queued candidates (uniform)
+    const uint32_t* const a_src = P.a_packed + I.a_pack + I.a_pos;
+    const uint32_t* const b_src = P.b_packed + I.b_pack + I.b_pos;
 
-    // item prologue, all 256 threads: A tile and the first B tile
-    build_tile(tile_a, TC_M, kpad, P.a_packed, I.a_pack, I.a_bucket, I.a_pos, I.a_n, I.len, P.sigma, tid, TC_THREADS, 1);
-    build_tile(tile_b0, TC_N, kpad, P.b_packed, I.b_pack, I.b_bucket, I.b_pos, min((uint32_t)TC_N, I.b_n), I.len,
-               P.sigma, tid, TC_THREADS, 1);
-    const uint32_t aseq = (epilogue_warp && tid < I.a_n) ? __ldg(P.a_order + I.a_start + tid) : 0xffffffffu;
-    __syncthreads();
-
-    // software pipeline over the B tiles: iteration t issues MMA[t], runs epilogue[t-1] on warps
-    // 0-3 and builds B[t+1] on warps 4-7, all three concurrently
-    for (uint32_t t = 0; t <= n_tiles; t++) {
-      if (t < n_tiles && tid == 128) {
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t buf = t & 1;
-        const uint32_t a_addr = smem_u32(tile_a), b_addr = smem_u32(buf ? tile_b1 : tile_b0);
-        const uint32_t lbo_a = TC_M * 16, lbo_b = TC_N * 16;
-        for (uint32_t s = 0; s < ksteps; s++)
-          mma_i8(tmem_base + buf * TC_N, make_desc(a_addr + 2 * s * lbo_a, lbo_a, 128),
-                 make_desc(b_addr + 2 * s * lbo_b, lbo_b, 128), s > 0);
-        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
-                         smem_u32(mbar + buf))
-                     : "memory");
-      }
-      if (t >= 1) {  // MMA[t-1] complete: its accumulator half is readable, its B buffer reusable
-        const uint32_t pb = (t - 1) & 1;
-        mbar_wait(smem_u32(mbar + pb), phase[pb]);
-        phase[pb] ^= 1;
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      }
-      if (epilogue_warp) {
-        if (t >= 1) {
-          const uint32_t pt = t - 1, pb = pt & 1;
-          const uint32_t bn = min((uint32_t)TC_N, I.b_n - pt * TC_N);
-          for (uint32_t c0 = 0; c0 < bn; c0 += 32) {  // warp-uniform trip count
-            uint32_t v[32];
-            const uint32_t taddr = tmem_base + pb * TC_N + ((warp * 32u) << 16) + c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]),
-                  "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]),
-                  "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]),
-                  "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            // threshold test without branches: one bit per column, then a (rare) loop over set bits
-            uint32_t hits = 0;
-#pragma unroll
-            for (int j = 0; j < 32; j++) hits |= ((int)v[j] >= thr ? 1u : 0u) << j;
-            if (bn - c0 < 32) hits &= (1u << (bn - c0)) - 1;
-            if (aseq == 0xffffffffu) hits = 0;
-            while (hits) {
-              const uint32_t j = __ffs(hits) - 1;
-              hits &= hits - 1;
-              const uint32_t hit = __ldg(P.b_order + I.b_start + (uint64_t)pt * TC_N + c0 + j);
-              const SeqMeta am = ld_meta(P.a.meta + aseq);
-              const SeqMeta bm = ld_meta(P.b.meta + hit);
-              nmatch++;
-              if (!P.no_matrix) {
-                const uint64_t mrow = P.existence ? (uint64_t)aseq - P.a_first : am.rep;
-                atomicAdd(P.matrix + mrow * P.n_cols + bm.rep, score_of(P.score, P.ignore_counts, am.count, bm.count));
-              }
-              if (P.want_pairs) {
-                const unsigned long long at = atomicAdd(P.counters + CTR_PAIRS, 1ull);
-                if (at < P.pairs_cap) {
-                  PairOut po;
-                  po.a = aseq + P.a.index_base;
-                  po.b = hit + P.b.index_base;
-                  P.pairs[at] = po;
-                }
+    // K5b: candidates of this warp, one per lane: exact residue compare (the AA code is a filter;
+    // the NT one-hot dot product is already the exact number of equal positions), then score,
+    // matrix atomics and pair append (overlap.cc:300-340)
+    auto drain = [&]() {
+      for (uint32_t b0 = 0; b0 < qn; b0 += 32) {
+        if (b0 + lane < qn) {
+          const uint2 e = q[b0 + lane];
+          bool ok = true;
+          if (AA) {
+            const uint32_t words = (I.len + 3) >> 2;
+            uint32_t mism = 0;
+            for (uint32_t k = 0; k < words; k++)
+              mism += __popc(__vcmpne4(__ldg(a_src + (uint64_t)k * I.a_bucket + e.x),
+                                       __ldg(b_src + (uint64_t)k * I.b_bucket + e.y)) &
+                             0x01010101u);
+            ok = (int)mism <= P.differences;
+          }
+          if (ok) {
+            const uint32_t aseq = __ldg(P.a_order + I.a_start + e.x);
+            const uint32_t bseq = __ldg(P.b_order + I.b_start + e.y);
+            const SeqMeta am = ld_meta(P.a.meta + aseq);
+            const SeqMeta bm = ld_meta(P.b.meta + bseq);
+            nmatch++;
+            if (!P.no_matrix) {
+              const uint64_t mrow = P.existence ? (uint64_t)aseq - P.a_first : am.rep;
+              atomicAdd(P.matrix + mrow * P.n_cols + bm.rep, score_of(P.score, P.ignore_counts, am.count, bm.count));
+            }
+            if (P.want_pairs) {
+              const unsigned long long at = atomicAdd(P.counters + CTR_PAIRS, 1ull);
+              if (at < P.pairs_cap) {
+                PairOut po;
+                po.a = aseq + P.a.index_base;
+                po.b = bseq + P.b.index_base;
+                P.pairs[at] = po;
               }
             }
           }
         }
-      } else if (t + 1 < n_tiles) {
-        const uint32_t nt = t + 1;
-        build_tile((nt & 1) ? tile_b1 : tile_b0, TC_N, kpad, P.b_packed, I.b_pack, I.b_bucket,
-                   I.b_pos + nt * TC_N, min((uint32_t)TC_N, I.b_n - nt * TC_N), I.len, P.sigma, tid - 128, 128, 2);
+      }
+      __syncwarp();
+      qn = 0;
+    };
+    // append this lane's hit columns (bit mask over columns col0..col0+31 of row a_local), one
+    // per lane per round, compacted by ballot
+    auto push = [&](uint32_t hits, uint32_t a_local, uint32_t col0) {
+      for (;;) {
+        const bool has = hits != 0;
+        const uint32_t bal = __ballot_sync(FULL, has);
+        if (!bal) break;
+        if (qn > TC_QCAP - 32) drain();
+        if (has) {
+          const uint32_t j = __ffs(hits) - 1;
+          hits &= hits - 1;
+          q[qn + __popc(bal & ((1u << lane) - 1))] = make_uint2(a_local, col0 + j);
+        }
+        qn += __popc(bal);
+        __syncwarp();
+      }
+    };
+
+    // item prologue: threads 0-255 write one set-A row each, the builder warps row tid - 256 of
+    // the first B tile; the builders then request the first words of their row of tile 1
+    uint32_t pre[4];
+    if (tid < TC_MA) {
+      if (tid < n_at * TC_ROWS) {
+        const bool valid = tid < I.a_n;
+        request_row(pre, a_src + tid, I.a_bucket, valid, I.len);
+        build_row<AA>(tile_a + (size_t)(tid >> 7) * tile_bytes, tid & 127, valid, a_src + tid, I.a_bucket, I.len, kpad,
+                      lut, pre);
+      }
+    } else if (builder_warp) {
+      const uint32_t brow = tid - TC_MA;
+      bool valid = brow < I.b_n;
+      request_row(pre, b_src + brow, I.b_bucket, valid, I.len);
+      build_row<AA>(tile_b, brow, valid, b_src + brow, I.b_bucket, I.len, kpad, lut, pre);
+      valid = TC_NB + brow < I.b_n;
+      request_row(pre, b_src + TC_NB + brow, I.b_bucket, valid, I.len);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+
+    // software pipeline over the B tiles: iteration t issues MMA[t] (warp 12), runs epilogue[t-1]
+    // on warps 0-7 and builds B[t+1] on warps 8-11, all three concurrently
+    for (uint32_t t = 0; t <= n_tiles; t++) {
+      if (mma_warp && t < n_tiles && lane == 0) {
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t buf = t & 1;
+        const uint32_t b_addr = smem_u32(tile_b + (size_t)buf * tile_bytes);
+        constexpr uint32_t lbo = TC_ROWS * 16;
+        for (uint32_t at = 0; at < n_at; at++) {
+          const uint32_t a_addr = smem_u32(tile_a + (size_t)at * tile_bytes);
+          for (uint32_t s = 0; s < ksteps; s++)
+            mma_i8(tmem_base + buf * 256 + at * TC_NB, make_desc(a_addr + 2 * s * lbo, lbo, 128),
+                   make_desc(b_addr + 2 * s * lbo, lbo, 128), s > 0);
+        }
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                         smem_u32(mbar + buf))
+                     : "memory");
+      }
+      if (t >= 1) {  // MMA[t-1] complete: its accumulators are readable, its B buffer reusable
+        const uint32_t pb = (t - 1) & 1;
+        mbar_wait(smem_u32(mbar + pb), (phases >> pb) & 1);
+        phases ^= 1u << pb;
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      }
+      if (epilogue_warp) {
+        if (t >= 1) {
+          // warp w reads lane quarter w & 3 (set-A rows) and column half w >> 2 of each accumulator
+          // block: two chunks of 32 columns.  Rows past a_n and columns past the tile's b_n are
+          // all-zero rows, so their dot products are 0 < thr and need no masking.
+          const uint32_t pt = t - 1, pb = pt & 1, quarter = warp & 3, half = warp >> 2;
+          for (uint32_t at = 0; at < n_at; at++) {
+            const uint32_t col = half * 64;
+            const uint32_t tbase = tmem_base + pb * 256 + at * TC_NB + col + ((quarter * 32u) << 16);
+            const uint32_t a_local = at * TC_ROWS + quarter * 32 + lane;
+            uint32_t va[32], vb[32];
+            TMEM_LD32(va, tbase);
+            TMEM_LD32(vb, tbase + 32);
+            TMEM_WAIT32(va);
+            TMEM_WAIT32(vb);
+            if (__any_sync(FULL, max32(va) >= thr)) push(hit_mask(va, thr), a_local, pt * TC_NB + col);
+            if (__any_sync(FULL, max32(vb) >= thr)) push(hit_mask(vb, thr), a_local, pt * TC_NB + col + 32);
+          }
+          if (t == n_tiles) drain();
+        }
+      } else if (builder_warp && t + 1 < n_tiles) {
+        const uint32_t nt = t + 1, brow = tid - TC_MA;
+        const uint32_t r = nt * TC_NB + brow;
+        uint32_t nxt[4];
+        request_row(nxt, b_src + r + TC_NB, I.b_bucket, r + TC_NB < I.b_n, I.len);
+        build_row<AA>(tile_b + (size_t)(nt & 1) * tile_bytes, brow, r < I.b_n, b_src + r, I.b_bucket, I.len, kpad, lut,
+                      pre);
+#pragma unroll
+        for (int j = 0; j < 4; j++) pre[j] = nxt[j];
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncthreads();
@@ -216,29 +365,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) hamming_tc_kernel(const __grid_
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) nmatch += __shfl_xor_sync(FULL, nmatch, o);
-  if ((tid & 31) == 0 && nmatch) atomicAdd(P.counters + CTR_MATCHES, (unsigned long long)nmatch);
+  if (lane == 0 && nmatch) atomicAdd(P.counters + CTR_MATCHES, (unsigned long long)nmatch);
   __syncthreads();
-  if (warp == 0)
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2u * TC_N));
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u));
 }
 
 size_t tc_smem_bytes(uint32_t kmax) {
-  return (size_t)(TC_M + 2 * TC_N) * kmax + 16 + 16 + 1024;
+  return (size_t)4 * TC_ROWS * kmax + 8 * TC_QCAP * sizeof(uint2) + 32 * sizeof(uint2) + 16 + 16 + 1024;
 }
+
+uint32_t tc_cols_per_position(uint32_t sigma) { return sigma <= 4 ? 4 : sigma <= 20 ? 8 : 0; }
 
 int launch_hamming_tc(const TcLaunch& p, int sm_count, cudaStream_t st, const char** err) {
   const size_t smem = tc_smem_bytes(p.kmax);
   if (smem > 227 * 1024) {
-    *err = "one-hot tiles do not fit shared memory";
+    *err = "tiles do not fit shared memory";
     return -1;
   }
-  if (cudaFuncSetAttribute(hamming_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
-      cudaSuccess) {
+  auto kernel = p.aa ? hamming_tc_kernel<true> : hamming_tc_kernel<false>;
+  if (cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     *err = "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed for the tensor-core kernel";
     return -1;
   }
+  if (cudaMemsetAsync(p.counters + CTR_WORK, 0, sizeof(unsigned long long), st) != cudaSuccess) {
+    *err = "cudaMemsetAsync failed";
+    return -1;
+  }
   const unsigned grid = (unsigned)(p.n_items < (uint32_t)sm_count ? p.n_items : (uint32_t)sm_count);
-  hamming_tc_kernel<<<grid, TC_THREADS, smem, st>>>(p);
+  kernel<<<grid, TC_THREADS, smem, st>>>(p);
   return 1;
 }
 

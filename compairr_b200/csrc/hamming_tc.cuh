@@ -7,9 +7,11 @@
 
 namespace cb {
 
-constexpr int TC_M = 128;  // set-A sequences per tile (accumulator rows = TMEM lanes)
-constexpr int TC_N = 256;  // set-B sequences per tile (accumulator columns)
-constexpr uint32_t TC_KMAX = 352;  // largest one-hot width (bytes): (128 + 2 * 256) rows x 352 B = 220 KB of shared memory
+constexpr uint32_t TC_ROWS = 128;  // rows of every shared-memory tile (MMA M, and MMA N)
+constexpr uint32_t TC_MA = 256;    // set-A sequences per work item: two accumulator row blocks
+constexpr uint32_t TC_NB = 128;    // set-B sequences per tile (accumulator columns per row block)
+constexpr uint32_t TC_KMAX = 416;  // widest row image (bytes): 4 tiles x 128 rows x 416 B = 208 KB of shared memory
+constexpr uint32_t TC_QCAP = 64;   // candidate queue entries per epilogue warp
 
 struct TcItem {       // one set-A tile against a run of set-B tiles of the same bucket
   uint64_t a_start;   // position in the A bucket order
@@ -20,10 +22,10 @@ struct TcItem {       // one set-A tile against a run of set-B tiles of the same
   uint32_t b_pos;
   uint32_t a_bucket;  // sequences in the whole A bucket (stride between packed words)
   uint32_t b_bucket;
-  uint32_t a_n;       // <= TC_M
-  uint32_t b_n;       // any (processed TC_N at a time)
+  uint32_t a_n;       // <= TC_MA
+  uint32_t b_n;       // any (processed TC_NB at a time)
   uint32_t len;       // sequence length of the bucket
-  uint32_t kpad;      // sigma * len rounded up to 32
+  uint32_t kpad;      // columns per position * len, rounded up to 32
 };
 
 struct TcLaunch {
@@ -35,7 +37,7 @@ struct TcLaunch {
   const TcItem* items;
   uint32_t n_items;
   uint32_t kmax;      // largest kpad among the items
-  uint32_t sigma;
+  uint32_t aa;        // 1: 8-byte residue code (filter + exact verify, alphabet <= 20), 0: 4-byte one-hot (exact, alphabet <= 4)
   uint64_t a_first;
   double* matrix;
   uint64_t n_cols;
@@ -47,6 +49,8 @@ struct TcLaunch {
 };
 
 size_t tc_smem_bytes(uint32_t kmax);
+// bytes one sequence position occupies in a tile row (0: alphabet not supported by this kernel)
+uint32_t tc_cols_per_position(uint32_t sigma);
 int launch_hamming_tc(const TcLaunch& p, int sm_count, cudaStream_t st, const char** err);
 
 }  // namespace cb
