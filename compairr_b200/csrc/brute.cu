@@ -57,7 +57,8 @@ bucket_key_kernel(const SeqRec* __restrict__ meta, uint64_t first, uint64_t n, b
   if ((threadIdx.x & 31) == 0 && gm) atomicMax(gene_max, (unsigned long long)gm);
 }
 
-// Pack the sequences of a bucket-sorted order into words, word-major inside each bucket:
+// Pack the sequences of a bucket-sorted order into words (4 residues each, the last word filled up
+// with TC_PACK_PAD), word-major inside each bucket:
 // word k of the s-th sequence of a bucket lives at pack_off[bucket] + k * bucket_n + s.
 __global__ void __launch_bounds__(256)
 pack_words_kernel(const SeqRec* __restrict__ meta, const uint8_t* __restrict__ res,
@@ -81,7 +82,7 @@ pack_words_kernel(const SeqRec* __restrict__ meta, const uint8_t* __restrict__ r
       uint32_t w = 0;
       for (uint32_t b = 0; b < 4; b++) {
         const uint32_t p = k * 4 + b;
-        if (p < m.len) w |= (uint32_t)r[p] << (8 * b);
+        w |= (p < m.len ? (uint32_t)r[p] : TC_PACK_PAD) << (8 * b);
       }
       packed[pack_off[lo] + (uint64_t)k * bn + s] = w;
     }
@@ -148,10 +149,11 @@ __global__ void __launch_bounds__(BK_THREADS) brute_kernel(const __grid_constant
       const uint32_t a = i / Wrt, k = i - a * Wrt;
       const uint32_t seq = P.a_order[J.a_start + a0 + a];
       const SeqMeta m = ld_meta(P.a.meta + seq);
-      uint32_t w = 0;
+      uint32_t w = 0;  // same padding as pack_words_kernel inside the sequence's words, zero words past them
       for (uint32_t bb = 0; bb < 4; bb++) {
         const uint32_t p = k * 4 + bb;
         if (p < m.len) w |= (uint32_t)__ldg(P.a.res + m.off + p) << (8 * bb);
+        else if (k < words) w |= TC_PACK_PAD << (8 * bb);
       }
       sm_words[i] = w;
       if (k == 0) a_idx[a] = seq;
@@ -464,17 +466,12 @@ int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bo
     T.existence = cfg.mode == CB_MODE_EXISTENCE;
     T.no_matrix = (cfg.no_matrix != 0) || pairs_only;
     T.want_pairs = cfg.want_pairs != 0;
-    const char* dbg = getenv("CB_TC_DEBUG");
-    cudaEvent_t e0, e1;
-    if (dbg) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0, st); }
     const char* kerr = nullptr;
     if (launch_hamming_tc(T, c->sm_count, st, &kerr) < 0) {
       ret = cb_fail(c, CB_ERR_LIMIT, "d>=3 tensor-core kernel: %s", kerr ? kerr : "launch failed");
     } else {
       cudaError_t e = cudaGetLastError();
-      if (dbg) cudaEventRecord(e1, st);
       if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (dbg) { float ms = 0; cudaEventElapsedTime(&ms, e0, e1); fprintf(stderr, "[tc] items=%u kernel %.3f ms\n", T.n_items, ms); }
       if (e != cudaSuccess) ret = cb_fail(c, CB_ERR_CUDA, "d>=3 tensor-core kernel: %s", cudaGetErrorString(e));
       (*launches)++;
     }

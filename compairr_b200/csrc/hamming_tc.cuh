@@ -11,7 +11,9 @@ constexpr uint32_t TC_ROWS = 128;  // rows of every shared-memory tile (MMA M, a
 constexpr uint32_t TC_MA = 256;    // set-A sequences per work item: two accumulator row blocks
 constexpr uint32_t TC_NB = 128;    // set-B sequences per tile (accumulator columns per row block)
 constexpr uint32_t TC_KMAX = 416;  // widest row image (bytes): 4 tiles x 128 rows x 416 B = 208 KB of shared memory
+constexpr uint32_t TC_BSTAGES = 4;  // most B tile stages in shared memory (fewer when rows are wide)
 constexpr uint32_t TC_QCAP = 64;   // candidate queue entries per epilogue warp
+constexpr uint32_t TC_PACK_PAD = 20;  // byte that fills the last packed word of a sequence (no residue has this code)
 
 struct TcItem {       // one set-A tile against a run of set-B tiles of the same bucket
   uint64_t a_start;   // position in the A bucket order
@@ -37,6 +39,7 @@ struct TcLaunch {
   const TcItem* items;
   uint32_t n_items;
   uint32_t kmax;      // largest kpad among the items
+  uint32_t b_stages;  // set by launch_hamming_tc
   uint32_t aa;        // 1: 8-byte residue code (filter + exact verify, alphabet <= 20), 0: 4-byte one-hot (exact, alphabet <= 4)
   uint64_t a_first;
   double* matrix;
@@ -48,9 +51,9 @@ struct TcLaunch {
   uint8_t ignore_counts, existence, no_matrix, want_pairs;
 };
 
-size_t tc_smem_bytes(uint32_t kmax);
+size_t tc_smem_bytes(uint32_t kmax, uint32_t b_stages);
 // bytes one sequence position occupies in a tile row (0: alphabet not supported by this kernel)
 uint32_t tc_cols_per_position(uint32_t sigma);
-int launch_hamming_tc(const TcLaunch& p, int sm_count, cudaStream_t st, const char** err);
+int launch_hamming_tc(TcLaunch p, int sm_count, cudaStream_t st, const char** err);
 
 }  // namespace cb
