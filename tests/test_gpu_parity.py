@@ -3,7 +3,7 @@ inputs.  Bit-exact for integer-valued scores, counts and pair lists; 1e-12 relat
 import numpy as np
 import pytest
 
-from compairr_b200 import OverlapOptions, overlap, synth
+from compairr_b200 import OverlapOptions, SeqSet, overlap, synth
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -162,3 +162,36 @@ def test_d3_tensor_core_path(d, nucleotides):
     assert info["run"]["matches"] == io["matches"]
     m2, p2, _ = overlap(a, b, OverlapOptions(want_pairs=True, nucleotides=nucleotides, flags=4, **kw))
     assert np.array_equal(m2, mo) and _pairs(p2) == _pairs(po)
+
+
+def test_d4_every_pair_matches_tensor_core():
+    """Worst case for the tcgen05 epilogue: every accumulator passes the threshold (all sequences
+    are 2-substitution neighbours of one centre, so any two differ in <= 4 positions), which
+    overflows the per-warp candidate queues while a TMEM stage is held; plus rows of residues
+    16-19 (the (1,1,1,1) code) and a second bucket one residue shorter (partial last tiles)."""
+    rng = np.random.default_rng(2024)
+    def neighbours(centre, n):
+        out = set()
+        while len(out) < n:
+            s = centre.copy()
+            p = rng.choice(centre.size, 2, replace=False)
+            s[p] = rng.integers(0, 20, 2)
+            out.add(bytes(s))
+        return [np.frombuffer(x, np.uint8) for x in sorted(out)]
+    def make(n15, n14, n_reps, seed):
+        c15 = np.array([16, 17, 18, 19, 0, 1, 2, 3, 16, 4, 19, 8, 12, 18, 7], np.uint8)
+        seqs = neighbours(c15, n15) + neighbours(c15[:14], n14)
+        r = np.random.default_rng(seed)
+        off = np.zeros(len(seqs) + 1, np.uint64)
+        np.cumsum([s.size for s in seqs], out=off[1:])
+        n = len(seqs)
+        return SeqSet(np.concatenate(seqs), off, np.zeros(n, np.uint32), np.zeros(n, np.uint32),
+                      r.integers(0, n_reps, n).astype(np.uint32), r.integers(1, 9, n).astype(np.uint64), n_reps)
+    a, b = make(600, 333, 3, 1), make(900, 415, 4, 2)
+    kw = dict(differences=4, ignore_genes=True)
+    m, p, info = overlap(a, b, OverlapOptions(want_pairs=True, **kw))
+    mo, po, io = orc.overlap(a, b, want_pairs=True, threads=4, **kw)
+    assert io["matches"] == 600 * 900 + 333 * 415
+    assert np.array_equal(m, mo)
+    assert _pairs(p) == _pairs(po)
+    assert info["run"]["matches"] == io["matches"]
