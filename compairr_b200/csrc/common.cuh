@@ -111,8 +111,18 @@ CB_HD uint64_t vj_hash(uint64_t seed, uint32_t v, uint32_t j) {
   return splitmix64(splitmix64(seed ^ 0x7E11C0DEull) ^ (((uint64_t)v << 32) | j));
 }
 
-// Home slot: upper half of the hash (hashtable.h:36-41).
-CB_HD uint64_t table_home(uint64_t h, uint64_t mask) { return (h >> 32) & mask; }
+// Home slot (hashtable.h:36-41 takes the upper half of the hash): hash bits 61 downwards, the same
+// bits that pick the Bloom block, so keys ordered by those bits touch the table AND the filters in
+// address order — what the partitioned build relies on to keep its working set in L2.
+CB_HD uint64_t table_home(uint64_t h, uint64_t mask) {
+#if defined(__CUDA_ARCH__)
+  const int bits = __popcll(mask);
+#else
+  const int bits = __builtin_popcountll(mask);
+#endif
+  return (h >> (62 - bits)) & mask;
+}
+constexpr int CB_PARTITION_TOP_BIT = 62;  // partition keys are hash bits [62 - p, 62)
 
 // Bloom: one 64-bit block per key; block chosen by multiply-shift range reduction over bits
 // 30..61 (any block count, not only powers of two), pattern = 3 bits in each 32-bit half taken

@@ -20,6 +20,40 @@ __device__ __forceinline__ SeqMeta ld_meta(const SeqRec* p) {
   return unpack_rec(lo.x, lo.y, hi.x, hi.y, hi.z, hi.w);
 }
 
+// Are the `len` residues at res + oa and res + ob equal?  Aligned 64-bit loads and funnel shifts
+// instead of a byte loop with two dependent loads per residue: all loads of a sequence of up to
+// 24 residues are issued at once (one memory round trip).  Reads whole aligned words, i.e. up to 7
+// bytes past a sequence: residue buffers are allocated with 16 bytes of slack (upload.cu).
+__device__ __forceinline__ bool seq_equal(const uint8_t* __restrict__ res, uint64_t oa, uint64_t ob, uint32_t len) {
+  const uint64_t* pa = reinterpret_cast<const uint64_t*>(res + (oa & ~7ull));
+  const uint64_t* pb = reinterpret_cast<const uint64_t*>(res + (ob & ~7ull));
+  const uint32_t sa = (uint32_t)(oa & 7) * 8, sb = (uint32_t)(ob & 7) * 8;
+  const uint32_t na = ((uint32_t)(oa & 7) + len + 7) >> 3, nb = ((uint32_t)(ob & 7) + len + 7) >> 3;
+  auto chunk = [](uint64_t lo, uint64_t hi, uint32_t s) { return s ? (lo >> s) | (hi << (64 - s)) : lo; };
+  auto mask = [](uint32_t rem) { return rem >= 8 ? ~0ull : (1ull << (rem * 8)) - 1; };
+  uint64_t diff = 0;
+  if (len <= 24) {
+    uint64_t wa[4], wb[4];
+#pragma unroll
+    for (uint32_t k = 0; k < 4; k++) {
+      wa[k] = k < na ? __ldg(pa + k) : 0ull;
+      wb[k] = k < nb ? __ldg(pb + k) : 0ull;
+    }
+#pragma unroll
+    for (uint32_t k = 0; k < 3; k++)
+      if (k * 8 < len) diff |= (chunk(wa[k], wa[k + 1], sa) ^ chunk(wb[k], wb[k + 1], sb)) & mask(len - k * 8);
+    return diff == 0;
+  }
+  uint64_t a_lo = __ldg(pa), b_lo = __ldg(pb);
+  for (uint32_t k = 0; k * 8 < len; k++) {
+    const uint64_t a_hi = k + 1 < na ? __ldg(pa + k + 1) : 0ull, b_hi = k + 1 < nb ? __ldg(pb + k + 1) : 0ull;
+    diff |= (chunk(a_lo, a_hi, sa) ^ chunk(b_lo, b_hi, sb)) & mask(len - k * 8);
+    a_lo = a_hi;
+    b_lo = b_hi;
+  }
+  return diff == 0;
+}
+
 // Filter word test.  K2 = true: 1 bit per 32-bit half (the low-bits-per-key geometry of a
 // first-level filter capped to stay L2-resident), else 3 + 3 bits.
 __device__ __forceinline__ bool bloom_word_test(unsigned long long w, uint64_t h, bool k2) {

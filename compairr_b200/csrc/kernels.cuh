@@ -98,10 +98,13 @@ void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st);
 void launch_reset_next(SeqRec* meta, uint64_t n, cudaStream_t st);
 // Inserts sequences [first, first + n) of the set; writes their SeqRec.next links (which must be
 // SEQ_NIL on entry).
-void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, uint64_t first, uint64_t n,
-                  bool ignore_genes, Slot* table, uint64_t mask, unsigned long long* bloom,
-                  uint32_t bloom_blocks, bool k2, unsigned long long* bloom2, uint32_t bloom2_blocks,
-                  cudaStream_t st);
+// part_hash/part_idx (both or neither): the keys sorted by their top hash bits, position t =
+// sequence first + part_idx[t] with hash part_hash[t].
+void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const uint64_t* part_hash,
+                  const uint32_t* part_idx, uint64_t first, uint64_t n, bool ignore_genes, Slot* table,
+                  uint64_t mask, unsigned long long* bloom, uint32_t bloom_blocks, bool k2,
+                  unsigned long long* bloom2, uint32_t bloom2_blocks, cudaStream_t st);
+void launch_iota(uint32_t* p, uint64_t n, cudaStream_t st);
 void launch_count_dups(DeviceSetView s, unsigned long long* counters, cudaStream_t st);
 
 // K3+K4: enumerate variants, Bloom, probe, verify, accumulate.  Returns launches made, <0 on

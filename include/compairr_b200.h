@@ -86,6 +86,7 @@ typedef struct cb_config {
 #define CB_FLAG_NO_SMEM_TILE 1u   /* accumulate straight into the global matrix (A/B testing)    */
 #define CB_FLAG_NO_BLOOM 2u       /* probe the hash table for every variant (A/B testing)        */
 #define CB_FLAG_NO_TENSOR 4u      /* d >= 3: CUDA-core kernel only, no tcgen05 GEMM (A/B testing) */
+#define CB_FLAG_NO_PARTITION 8u   /* table build in input order, no radix sort by home slot (A/B testing) */
 
 /*
  * One sequence set in structure-of-arrays form — what db_read() (src/db.cc:708-901) leaves
