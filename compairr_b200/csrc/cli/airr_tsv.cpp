@@ -1,12 +1,17 @@
 // airr_tsv.cpp — see airr_tsv.h.
 #include "airr_tsv.h"
 
+#include <fcntl.h>
 #include <stdlib.h>
 #include <string.h>
+#include <sys/mman.h>
 #include <sys/stat.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <chrono>
+#include <string_view>
+#include <thread>
 
 static std::chrono::steady_clock::time_point g_t0;
 
@@ -48,26 +53,51 @@ void init_map(bool nt) {
   if (nt) g_map['U'] = g_map['u'] = 3;  // db.cc:53-71
 }
 
-// split a line in place on tabs; returns field count
-size_t split_tabs(char* line, std::vector<char*>& out) {
-  out.clear();
-  char* p = line;
-  out.push_back(p);
-  for (; *p; p++)
-    if (*p == '\t') {
-      *p = 0;
-      out.push_back(p + 1);
+// The whole input in memory: a private mapping for regular files, a buffer for pipes.
+struct FileData {
+  const char* p = nullptr;
+  size_t n = 0;
+  void* map = nullptr;
+  std::string owned;
+  ~FileData() {
+    if (map) munmap(map, n);
+  }
+};
+
+using sv = std::string_view;
+
+// split [b, e) on tabs into at most f.size() fields; returns the number of fields on the line
+// (counting stops once every wanted column has been seen)
+inline int split_tabs(const char* b, const char* e, std::vector<sv>& f) {
+  int nf = 0;
+  const int want = (int)f.size();
+  while (nf < want) {
+    const char* t = (const char*)memchr(b, '\t', (size_t)(e - b));
+    if (!t) {
+      f[nf++] = sv(b, (size_t)(e - b));
+      return nf;
     }
-  return out.size();
+    f[nf++] = sv(b, (size_t)(t - b));
+    b = t + 1;
+  }
+  return nf;
 }
 
-void parse_header(char* line, const Options& o, bool require_sequence_id, Columns& c) {
-  std::vector<char*> f;
-  split_tabs(line, f);
+void parse_header(const std::string& line, const Options& o, bool require_sequence_id, Columns& c) {
+  std::vector<std::string> f;
+  {
+    size_t b = 0;
+    for (;;) {
+      const size_t t = line.find('\t', b);
+      f.emplace_back(line.substr(b, t == std::string::npos ? std::string::npos : t - b));
+      if (t == std::string::npos) break;
+      b = t + 1;
+    }
+  }
   c.keep.assign(o.keep_names.size(), 0);
   for (size_t i = 0; i < f.size(); i++) {
     const int col = (int)i + 1;
-    const char* t = f[i];
+    const char* t = f[i].c_str();
     if (!strcmp(t, "repertoire_id")) c.repertoire_id = col;
     else if (!strcmp(t, "sequence_id")) c.sequence_id = col;
     else if (!strcmp(t, "duplicate_count")) c.duplicate_count = col;
@@ -105,23 +135,264 @@ void parse_header(char* line, const Options& o, bool require_sequence_id, Column
   }
 }
 
+// First-seen-order string interning with a one-entry cache (consecutive lines mostly repeat the
+// repertoire and often the genes).  Views point into the file data or at static strings.
+struct Interner {
+  std::unordered_map<sv, uint32_t> map;
+  std::vector<sv> names;
+  sv last;
+  uint32_t last_no = 0;
+  bool have_last = false;
+  uint32_t get(sv s) {
+    if (have_last && s == last) return last_no;
+    auto it = map.find(s);
+    uint32_t no;
+    if (it != map.end()) {
+      no = it->second;
+    } else {
+      no = (uint32_t)names.size();
+      names.push_back(s);
+      map.emplace(s, no);
+    }
+    last = s;
+    last_no = no;
+    have_last = true;
+    return no;
+  }
+};
+
+enum ErrKind {
+  ERR_NONE = 0, ERR_CHAR_PRINTABLE, ERR_CHAR_OTHER, ERR_EMPTY_SEQ, ERR_NO_SEQID, ERR_BAD_COUNT, ERR_NO_COUNT,
+  ERR_NO_V, ERR_NO_J, ERR_NO_SEQ
+};
+
+// What one reader thread produced from its range of lines: the same columns as SeqDb with
+// thread-local id numbering, merged in file order afterwards.
+struct Part {
+  std::vector<uint8_t> residues;
+  std::vector<uint32_t> len, v, j, rep;
+  std::vector<uint64_t> count;
+  std::vector<char> id_arena, keep_arena;
+  std::vector<uint64_t> id_off, keep_off;
+  Interner reps, vs, js;
+  unsigned longest = 0, shortest = ~0u;
+  uint64_t total_count = 0, ignored_unknown = 0, ignored_empty = 0, lines = 0;
+  ErrKind err = ERR_NONE;
+  uint64_t err_line = 0;  // 1-based inside this part
+  int err_char = 0;
+  std::string err_text;
+};
+
+struct ParseCtx {
+  const Options* o;
+  const Columns* col;
+  bool require_sequence_id, want_ids;
+  sv default_rep;
+  int seqcol, maxcol;
+};
+
+void parse_range(const char* b, const char* e, const ParseCtx& cx, Part& out) {
+  const Options& o = *cx.o;
+  const Columns& col = *cx.col;
+  std::vector<sv> f((size_t)cx.maxcol);
+  const bool want_keep = !o.keep_names.empty();
+  // capacity guesses from the byte count keep reallocation out of the loop
+  const size_t guess = (size_t)(e - b) / 48 + 16;
+  out.len.reserve(guess);
+  out.v.reserve(guess);
+  out.j.reserve(guess);
+  out.rep.reserve(guess);
+  out.count.reserve(guess);
+  out.residues.reserve(guess * 16);
+  auto fail = [&](ErrKind k, int ch = 0, sv text = sv()) {
+    out.err = k;
+    out.err_line = out.lines;
+    out.err_char = ch;
+    out.err_text.assign(text);
+  };
+  while (b < e) {
+    const char* nl = (const char*)memchr(b, '\n', (size_t)(e - b));
+    const char* le = nl ? nl : e;
+    const char* next = nl ? nl + 1 : e;
+    if (le > b && le[-1] == '\r') le--;
+    out.lines++;
+    const int nf = split_tabs(b, le, f);
+    b = next;
+    auto has = [&](int c) { return c >= 1 && c <= nf; };
+    // residues first, exactly in the reference's order of checks (db.cc:400-503)
+    const bool has_seq = has(cx.seqcol);
+    const sv seq = has_seq ? f[cx.seqcol - 1] : sv();
+    const size_t base = out.residues.size();
+    bool ignore = false;
+    for (size_t i = 0; i < seq.size(); i++) {
+      const unsigned char ch = (unsigned char)seq[i];
+      const signed char m = g_map[ch];
+      if (m >= 0) {
+        out.residues.push_back((uint8_t)m);
+      } else if (ch >= 32 && ch <= 126) {
+        if (o.ignore_unknown) {
+          ignore = true;
+          out.ignored_unknown++;
+        } else {
+          return fail(ERR_CHAR_PRINTABLE, ch);
+        }
+      } else {
+        return fail(ERR_CHAR_OTHER, ch);
+      }
+    }
+    const unsigned seqlen = (unsigned)(out.residues.size() - base);
+    if (seqlen == 0) {
+      if (o.ignore_empty) {
+        ignore = true;
+        out.ignored_empty++;
+      } else {
+        return fail(ERR_EMPTY_SEQ);
+      }
+    }
+    if (ignore) {
+      out.residues.resize(base);
+      continue;
+    }
+    if (seqlen > out.longest) out.longest = seqlen;
+    if (seqlen < out.shortest) out.shortest = seqlen;
+    // repertoire id (db.cc:505-520)
+    const uint32_t rno = out.reps.get(has(col.repertoire_id) ? f[col.repertoire_id - 1] : cx.default_rep);
+    // sequence id (db.cc:523-540)
+    const bool has_sid = has(col.sequence_id);
+    const sv sid = has_sid ? f[col.sequence_id - 1] : sv();
+    if (sid.empty() && cx.require_sequence_id) return fail(ERR_NO_SEQID);
+    // duplicate count (db.cc:543-572): strtol over the whole field, value >= 1
+    uint64_t cnt = 1;
+    const sv dc = has(col.duplicate_count) ? f[col.duplicate_count - 1] : sv();
+    if (!dc.empty()) {
+      bool ok = false;
+      if (dc.size() <= 18 && dc[0] >= '0' && dc[0] <= '9') {  // plain digits: the common case
+        uint64_t v = 0;
+        ok = true;
+        for (char ch : dc) {
+          if (ch < '0' || ch > '9') {
+            ok = false;
+            break;
+          }
+          v = v * 10 + (uint64_t)(ch - '0');
+        }
+        if (ok && v >= 1) cnt = v; else ok = false;
+      }
+      if (!ok) {  // anything else goes through strtol itself (signs, blanks, overflow)
+        const std::string z(dc);
+        if (strlen(z.c_str()) == z.size()) {
+          char* end = nullptr;
+          const long v = strtol(z.c_str(), &end, 10);
+          if (end && *end == 0 && v >= 1) {
+            cnt = (uint64_t)v;
+            ok = true;
+          }
+        }
+      }
+      if (!ok) return fail(ERR_BAD_COUNT, 0, dc);
+    } else if (!o.ignore_counts) {
+      return fail(ERR_NO_COUNT);
+    }
+    out.total_count += cnt;
+    // genes (db.cc:577-631)
+    const sv vc = has(col.v_call) ? f[col.v_call - 1] : sv();
+    const sv jc = has(col.j_call) ? f[col.j_call - 1] : sv();
+    if (!o.ignore_genes && vc.empty()) return fail(ERR_NO_V);
+    const uint32_t vno = out.vs.get(vc);
+    if (!o.ignore_genes && jc.empty()) return fail(ERR_NO_J);
+    const uint32_t jno = out.js.get(jc);
+    if (seq.empty()) return fail(ERR_NO_SEQ);
+    out.len.push_back(seqlen);
+    out.v.push_back(vno);
+    out.j.push_back(jno);
+    out.rep.push_back(rno);
+    out.count.push_back(cnt);
+    if (cx.want_ids) {
+      out.id_off.push_back(out.id_arena.size());
+      out.id_arena.insert(out.id_arena.end(), sid.begin(), sid.end());
+      out.id_arena.push_back(0);
+    }
+    if (want_keep) {
+      out.keep_off.push_back(out.keep_arena.size());
+      for (size_t x = 0; x < col.keep.size(); x++) {
+        if (x) out.keep_arena.push_back('\t');
+        if (has(col.keep[x])) {
+          const sv kv = f[col.keep[x] - 1];
+          out.keep_arena.insert(out.keep_arena.end(), kv.begin(), kv.end());
+        }
+      }
+      out.keep_arena.push_back(0);
+    }
+  }
+}
+
+[[noreturn]] void report(const Part& p, uint64_t lineno, const Options& o) {
+  const unsigned long ln = (unsigned long)lineno;
+  switch (p.err) {
+    case ERR_CHAR_PRINTABLE:
+      fprintf(g_log, "\n\nError: Illegal character '%c' in sequence on line %lu. Use -u to ignore.\n", p.err_char, ln);
+      break;
+    case ERR_CHAR_OTHER:
+      fprintf(g_log, "\n\nError: Illegal character (ascii no %d) in sequence on line %lu\n", p.err_char, ln);
+      break;
+    case ERR_EMPTY_SEQ:
+      fprintf(g_log, "\n\nError: Empty sequence in sequence on line %lu. Use -e to ignore.\n", ln);
+      break;
+    case ERR_NO_SEQID:
+      fprintf(g_log, "\n\nError: missing or empty sequence_id value on line %lu\n", ln);
+      break;
+    case ERR_BAD_COUNT:
+      fprintf(g_log, "\n\nError: Illegal duplicate_count on line %lu: %s\n", ln, p.err_text.c_str());
+      break;
+    case ERR_NO_COUNT:
+      fprintf(g_log, "\n\nError: missing or empty duplicate_count on line %lu\n", ln);
+      break;
+    case ERR_NO_V:
+      fprintf(g_log, "\n\nError: missing or empty v_call value on line %lu\n", ln);
+      break;
+    case ERR_NO_J:
+      fprintf(g_log, "\n\nError: missing or empty j_call value on line %lu\n", ln);
+      break;
+    default:
+      fprintf(g_log, "\n\nError: missing or empty %s value on line %lu\n", o.seq_header, ln);
+      break;
+  }
+  exit(1);
+}
+
+// run fn(t) for t in [0, n) on n threads (inline when n == 1)
+template <class F>
+void parallel(unsigned n, F fn) {
+  if (n <= 1) {
+    fn(0u);
+    return;
+  }
+  std::vector<std::thread> pool;
+  for (unsigned t = 0; t < n; t++) pool.emplace_back(fn, t);
+  for (auto& th : pool) th.join();
+}
+
 }  // namespace
 
+// The reference reads with getline/strsep/std::map on one thread (db.cc:708-901), ~0.4 us per
+// line: 40 s for a 10^8-line file, far more than the whole GPU phase.  Here the
+// file is mapped, cut into one range of whole lines per host thread, parsed into thread-local
+// columns with thread-local id numbering, and merged in file order — so sequence order (the -x
+// row order and the index space of pairs) and the first-seen numbering of repertoires and genes
+// are exactly the serial reader's, and the earliest malformed line is the one reported.
 void read_airr_tsv(const char* filename, const Options& o, bool require_sequence_id, bool want_ids,
                    const char* default_repertoire_id, GeneTables& genes, SeqDb& db) {
-  FILE* fp = nullptr;
-  if (!strcmp(filename, "-")) {
-    const int fd = dup(STDIN_FILENO);
-    fp = fd < 0 ? nullptr : fdopen(fd, "rb");
-  } else {
-    fp = fopen(filename, "rb");
-  }
-  if (!fp) {
+  int fd = -1;
+  if (!strcmp(filename, "-"))
+    fd = dup(STDIN_FILENO);
+  else
+    fd = open(filename, O_RDONLY);
+  if (fd < 0) {
     fprintf(g_log, "\nError: Unable to open input data file (%s).\n", filename);
     exit(1);
   }
   struct stat fs;
-  if (fstat(fileno(fp), &fs)) {
+  if (fstat(fd, &fs)) {
     fprintf(g_log, "\nUnable to fstat on input file (%s)\n", filename);
     exit(1);
   }
@@ -129,154 +400,154 @@ void read_airr_tsv(const char* filename, const Options& o, bool require_sequence
   init_map(o.nucleotides);
 
   progress_begin(o, "Reading sequences:");
-  char* line = nullptr;
-  size_t cap = 0;
-  ssize_t len = getline(&line, &cap, fp);
-  if (len < 0) fatal("Unable to read from the input file");
-  uint64_t lineno = 0;
-  bool in_header = true;
-  Columns col;
-  std::vector<char*> f;
-  const char* const empty = "";
-  while (len >= 0) {
-    if (len > 0 && line[len - 1] == '\n') line[--len] = 0;
-    if (len > 0 && line[len - 1] == '\r') line[--len] = 0;
-    lineno++;
-    if (in_header) {
-      if (line[0] != '#' && line[0] != '@') {  // leading comment lines are skipped (db.cc:766-782)
-        parse_header(line, o, require_sequence_id, col);
-        in_header = false;
-      }
-    } else {
-      const int nf = (int)split_tabs(line, f);
-      auto field = [&](int c) -> const char* { return (c >= 1 && c <= nf) ? f[c - 1] : nullptr; };
-      const char* seq = field(o.cdr3 ? (o.nucleotides ? col.cdr3 : col.cdr3_aa)
-                                     : (o.nucleotides ? col.junction : col.junction_aa));
-      // residues first, exactly in the reference's order of checks (db.cc:400-503)
-      const size_t slen = seq ? strlen(seq) : 0;
-      const size_t base = db.residues.size();
-      bool ignore = false;
-      for (size_t i = 0; i < slen; i++) {
-        const unsigned char ch = (unsigned char)seq[i];
-        const signed char m = g_map[ch];
-        if (m >= 0) {
-          db.residues.push_back((uint8_t)m);
-        } else if (ch >= 32 && ch <= 126) {
-          if (o.ignore_unknown) {
-            ignore = true;
-            db.ignored_unknown++;
-          } else {
-            fprintf(g_log, "\n\nError: Illegal character '%c' in sequence on line %lu. Use -u to ignore.\n", ch,
-                    (unsigned long)lineno);
-            exit(1);
-          }
-        } else {
-          fprintf(g_log, "\n\nError: Illegal character (ascii no %d) in sequence on line %lu\n", ch,
-                  (unsigned long)lineno);
-          exit(1);
-        }
-      }
-      const unsigned seqlen = (unsigned)(db.residues.size() - base);
-      if (seqlen == 0) {
-        if (o.ignore_empty) {
-          ignore = true;
-          db.ignored_empty++;
-        } else {
-          fprintf(g_log, "\n\nError: Empty sequence in sequence on line %lu. Use -e to ignore.\n",
-                  (unsigned long)lineno);
-          exit(1);
-        }
-      }
-      if (ignore) {
-        db.residues.resize(base);
-      } else {
-        if (seqlen > db.longest) db.longest = seqlen;
-        if (seqlen < db.shortest) db.shortest = seqlen;
-        // repertoire id (db.cc:505-520)
-        const char* rid = field(col.repertoire_id);
-        if (!rid) rid = default_repertoire_id;
-        auto rit = db.rep_map.find(rid);
-        uint32_t rno;
-        if (rit == db.rep_map.end()) {
-          rno = (uint32_t)db.rep_names.size();
-          db.rep_names.emplace_back(rid);
-          db.rep_map.emplace(rid, rno);
-        } else {
-          rno = rit->second;
-        }
-        // sequence id (db.cc:523-540)
-        const char* sid = field(col.sequence_id);
-        if (!(sid && *sid) && require_sequence_id) {
-          fprintf(g_log, "\n\nError: missing or empty sequence_id value on line %lu\n", (unsigned long)lineno);
-          exit(1);
-        }
-        // duplicate count (db.cc:543-572)
-        const char* dc = field(col.duplicate_count);
-        uint64_t cnt = 1;
-        if (dc && *dc) {
-          char* end = nullptr;
-          const long v = strtol(dc, &end, 10);
-          if (end && *end == 0 && v >= 1) {
-            cnt = (uint64_t)v;
-          } else {
-            fprintf(g_log, "\n\nError: Illegal duplicate_count on line %lu: %s\n", (unsigned long)lineno, dc);
-            exit(1);
-          }
-        } else if (!o.ignore_counts) {
-          fprintf(g_log, "\n\nError: missing or empty duplicate_count on line %lu\n", (unsigned long)lineno);
-          exit(1);
-        }
-        db.total_count += cnt;
-        // genes (db.cc:577-631)
-        const char* vc = field(col.v_call);
-        const char* jc = field(col.j_call);
-        if (!o.ignore_genes && !(vc && *vc)) {
-          fprintf(g_log, "\n\nError: missing or empty v_call value on line %lu\n", (unsigned long)lineno);
-          exit(1);
-        }
-        if (!vc) vc = empty;
-        auto intern = [](std::unordered_map<std::string, uint32_t>& map, std::vector<std::string>& names,
-                         const char* s) {
-          auto it = map.find(s);
-          if (it != map.end()) return it->second;
-          const uint32_t no = (uint32_t)names.size();
-          names.emplace_back(s);
-          map.emplace(s, no);
-          return no;
-        };
-        const uint32_t vno = intern(genes.v_map, genes.v_names, vc);
-        if (!o.ignore_genes && !(jc && *jc)) {
-          fprintf(g_log, "\n\nError: missing or empty j_call value on line %lu\n", (unsigned long)lineno);
-          exit(1);
-        }
-        if (!jc) jc = empty;
-        const uint32_t jno = intern(genes.j_map, genes.j_names, jc);
-        if (!(seq && *seq)) {
-          fprintf(g_log, "\n\nError: missing or empty %s value on line %lu\n", o.seq_header, (unsigned long)lineno);
-          exit(1);
-        }
-        db.offsets.push_back(db.residues.size());
-        db.v.push_back(vno);
-        db.j.push_back(jno);
-        db.rep.push_back(rno);
-        db.count.push_back(cnt);
-        if (want_ids) db.seq_id.emplace_back(sid ? sid : empty);
-        if (!o.keep_names.empty()) {
-          std::string k;
-          for (size_t x = 0; x < col.keep.size(); x++) {
-            if (x) k.push_back('\t');
-            const char* kv = field(col.keep[x]);
-            if (kv) k += kv;
-          }
-          db.keep.push_back(std::move(k));
-        }
-      }
+  auto data = std::make_shared<FileData>();
+  if (S_ISREG(fs.st_mode) && fs.st_size > 0) {
+    void* m = mmap(nullptr, (size_t)fs.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m != MAP_FAILED) {
+      data->map = m;
+      data->p = (const char*)m;
+      data->n = (size_t)fs.st_size;
+      madvise(m, data->n, MADV_WILLNEED);
     }
-    len = getline(&line, &cap, fp);
   }
+  if (!data->map) {  // pipes, empty files, or a mapping that failed
+    char buf[1 << 16];
+    for (;;) {
+      const ssize_t r = read(fd, buf, sizeof buf);
+      if (r < 0) fatal("Unable to read from the input file");
+      if (r == 0) break;
+      data->owned.append(buf, (size_t)r);
+    }
+    data->p = data->owned.data();
+    data->n = data->owned.size();
+  }
+  close(fd);
+  if (data->n == 0) fatal("Unable to read from the input file");
+
+  // leading comment lines are skipped, the first other line is the header (db.cc:766-782)
+  const char* p = data->p;
+  const char* const end = p + data->n;
+  uint64_t lineno = 0;
+  Columns col;
+  bool have_header = false;
+  while (p < end && !have_header) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* le = nl ? nl : end;
+    lineno++;
+    if (*p != '#' && *p != '@') {
+      const char* he = (le > p && le[-1] == '\r') ? le - 1 : le;
+      std::string header(p, (size_t)(he - p));
+      header.resize(strlen(header.c_str()));
+      parse_header(header, o, require_sequence_id, col);
+      have_header = true;
+    }
+    p = nl ? nl + 1 : end;
+  }
+
+  ParseCtx cx;
+  cx.o = &o;
+  cx.col = &col;
+  cx.require_sequence_id = require_sequence_id;
+  cx.want_ids = want_ids;
+  cx.default_rep = sv(default_repertoire_id);
+  cx.seqcol = o.cdr3 ? (o.nucleotides ? col.cdr3 : col.cdr3_aa) : (o.nucleotides ? col.junction : col.junction_aa);
+  cx.maxcol = std::max({col.repertoire_id, col.sequence_id, col.duplicate_count, col.v_call, col.j_call, cx.seqcol, 1});
+  for (int k : col.keep) cx.maxcol = std::max(cx.maxcol, k);
+
+  // one range of whole lines per thread
+  const size_t body = (size_t)(end - p);
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 1;
+  unsigned n_thr = o.threads > 1 ? (unsigned)o.threads : std::min(hw, 32u);
+  size_t min_bytes = 1 << 20;  // per thread; COMPAIRR_B200_READ_MIN_BYTES lets tests split small files
+  if (const char* e = getenv("COMPAIRR_B200_READ_MIN_BYTES")) min_bytes = std::max<size_t>(1, strtoull(e, nullptr, 10));
+  n_thr = (unsigned)std::max<size_t>(1, std::min<size_t>(n_thr, body / min_bytes));
+  std::vector<const char*> cut(n_thr + 1, end);
+  cut[0] = p;
+  for (unsigned t = 1; t < n_thr; t++) {
+    const char* c = p + body / n_thr * t;
+    if (c < cut[t - 1]) c = cut[t - 1];
+    const char* nl = (const char*)memchr(c, '\n', (size_t)(end - c));
+    cut[t] = nl ? nl + 1 : end;
+  }
+  std::vector<Part> parts(n_thr);
+  parallel(n_thr, [&](unsigned t) { parse_range(cut[t], cut[t + 1], cx, parts[t]); });
+  for (unsigned t = 0; t < n_thr; t++) {  // the earliest malformed line, numbered from the top of the file
+    if (parts[t].err != ERR_NONE) report(parts[t], lineno + parts[t].err_line, o);
+    lineno += parts[t].lines;
+  }
+
+  // merge: global ids in file order of first appearance, then every thread copies its columns
+  // into place
+  auto intern = [](std::unordered_map<std::string, uint32_t>& map, std::vector<std::string>& names, sv s) {
+    std::string key(s);
+    auto it = map.find(key);
+    if (it != map.end()) return it->second;
+    const uint32_t no = (uint32_t)names.size();
+    names.push_back(key);
+    map.emplace(std::move(key), no);
+    return no;
+  };
+  std::vector<std::vector<uint32_t>> rmap(n_thr), vmap(n_thr), jmap(n_thr);
+  std::vector<uint64_t> seq0(n_thr + 1, db.n()), res0(n_thr + 1, db.residues.size());
+  std::vector<uint64_t> id0(n_thr + 1, db.id_arena.size()), keep0(n_thr + 1, db.keep_arena.size());
+  for (unsigned t = 0; t < n_thr; t++) {
+    Part& pt = parts[t];
+    for (sv s : pt.reps.names) rmap[t].push_back(intern(db.rep_map, db.rep_names, s));
+    for (sv s : pt.vs.names) vmap[t].push_back(intern(genes.v_map, genes.v_names, s));
+    for (sv s : pt.js.names) jmap[t].push_back(intern(genes.j_map, genes.j_names, s));
+    seq0[t + 1] = seq0[t] + pt.len.size();
+    res0[t + 1] = res0[t] + pt.residues.size();
+    id0[t + 1] = id0[t] + pt.id_arena.size();
+    keep0[t + 1] = keep0[t] + pt.keep_arena.size();
+    if (!pt.len.empty()) {
+      db.longest = std::max(db.longest, pt.longest);
+      db.shortest = std::min(db.shortest, pt.shortest);
+    }
+    db.total_count += pt.total_count;
+    db.ignored_unknown += pt.ignored_unknown;
+    db.ignored_empty += pt.ignored_empty;
+  }
+  const uint64_t n_total = seq0[n_thr];
+  db.residues.resize(res0[n_thr]);
+  db.offsets.resize(n_total + 1);
+  db.v.resize(n_total);
+  db.j.resize(n_total);
+  db.rep.resize(n_total);
+  db.count.resize(n_total);
+  if (want_ids) {
+    db.id_arena.resize(id0[n_thr]);
+    db.id_off.resize(n_total);
+  }
+  if (!o.keep_names.empty()) {
+    db.keep_arena.resize(keep0[n_thr]);
+    db.keep_off.resize(n_total);
+  }
+  parallel(n_thr, [&](unsigned t) {
+    Part& pt = parts[t];
+    const uint64_t s0 = seq0[t], cnt = pt.len.size();
+    if (!pt.residues.empty()) memcpy(db.residues.data() + res0[t], pt.residues.data(), pt.residues.size());
+    uint64_t off = res0[t];
+    for (uint64_t i = 0; i < cnt; i++) {
+      off += pt.len[i];
+      db.offsets[s0 + i + 1] = off;
+      db.v[s0 + i] = vmap[t][pt.v[i]];
+      db.j[s0 + i] = jmap[t][pt.j[i]];
+      db.rep[s0 + i] = rmap[t][pt.rep[i]];
+      db.count[s0 + i] = pt.count[i];
+    }
+    if (want_ids && cnt) {
+      memcpy(db.id_arena.data() + id0[t], pt.id_arena.data(), pt.id_arena.size());
+      for (uint64_t i = 0; i < cnt; i++) db.id_off[s0 + i] = id0[t] + pt.id_off[i];
+    }
+    if (!o.keep_names.empty() && cnt) {
+      memcpy(db.keep_arena.data() + keep0[t], pt.keep_arena.data(), pt.keep_arena.size());
+      for (uint64_t i = 0; i < cnt; i++) db.keep_off[s0 + i] = keep0[t] + pt.keep_off[i];
+    }
+    Part().residues.swap(pt.residues);  // give the memory back early
+  });
+  parts.clear();
   progress_end(o, "Reading sequences:");
-  free(line);
-  fclose(fp);
 
   if (db.ignored_unknown) fprintf(g_log, "%lu sequences with unknown symbols ignored.\n", (unsigned long)db.ignored_unknown);
   if (db.ignored_empty) fprintf(g_log, "%lu empty sequences ignored.\n", (unsigned long)db.ignored_empty);

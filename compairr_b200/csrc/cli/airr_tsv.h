@@ -5,6 +5,7 @@
 #pragma once
 #include <stdint.h>
 
+#include <memory>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -21,8 +22,13 @@ struct SeqDb {
   std::vector<uint64_t> offsets{0};
   std::vector<uint32_t> v, j, rep;
   std::vector<uint64_t> count;
-  std::vector<std::string> seq_id;  // only filled when needed (pairs / existence)
-  std::vector<std::string> keep;    // -k columns, tab-joined
+  // sequence ids (only filled when needed: pairs / existence) and -k columns (tab-joined):
+  // NUL-terminated strings in one arena each
+  std::vector<char> id_arena, keep_arena;
+  std::vector<uint64_t> id_off, keep_off;
+  bool has_ids() const { return !id_off.empty(); }
+  const char* seq_id(uint64_t i) const { return id_arena.data() + id_off[i]; }
+  const char* keep(uint64_t i) const { return keep_arena.data() + keep_off[i]; }
   std::vector<std::string> rep_names;
   std::unordered_map<std::string, uint32_t> rep_map;
   unsigned longest = 0, shortest = ~0u;

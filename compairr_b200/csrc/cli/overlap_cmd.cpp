@@ -107,7 +107,7 @@ struct PairWriter {
     const char* alpha = o.nucleotides ? "acgt" : "ACDEFGHIKLMNPQRSTVWY";  // db.cc:73-74
     buf += d.rep_names[d.rep[i]];
     buf += '\t';
-    if (!d.seq_id.empty()) buf += d.seq_id[i];
+    if (d.has_ids()) buf += d.seq_id(i);
     buf += '\t';
     buf += std::to_string(d.count[i]);
     buf += '\t';
@@ -118,7 +118,7 @@ struct PairWriter {
     for (uint64_t p = d.offsets[i]; p < d.offsets[i + 1]; p++) buf += alpha[d.residues[p]];
     if (!o.keep_names.empty()) {
       buf += '\t';
-      buf += d.keep[i];
+      buf += d.keep(i);
     }
   }
   void write(const cb_pair* p, size_t n) {
@@ -334,7 +334,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
     const uint64_t nrows = o.existence ? N1 : R1;
     auto row_index = [&](uint64_t i) -> uint64_t { return o.existence ? i : s1.order[i]; };
     auto row_name = [&](uint64_t i) -> const char* {
-      return o.existence ? d1.seq_id[i].c_str() : d1.rep_names[s1.order[i]].c_str();
+      return o.existence ? d1.seq_id(i) : d1.rep_names[s1.order[i]].c_str();
     };
     if (o.alternative) {
       fprintf(outfile, o.existence ? "#sequence_id_1\trepertoire_id_2\tmatches\n" : "#repertoire_id_1\trepertoire_id_2\tmatches\n");

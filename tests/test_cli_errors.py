@@ -23,6 +23,35 @@ def test_error_cases_match_reference(case, tmp_path):
     assert r.stderr == case["stderr"]
 
 
+@pytest.mark.parametrize("case", ERR, ids=[c["name"] for c in ERR])
+def test_error_cases_match_reference_with_parallel_reader(case, tmp_path):
+    """The same malformed inputs read by 4 threads over ranges of ~100 bytes: the reported line is
+    still the earliest bad line, numbered from the top of the file."""
+    files = [os.path.join(GOLDEN_DIR, f) for f in case["files"]]
+    env = dict(os.environ, COMPAIRR_B200_READ_MIN_BYTES="100")
+    r = subprocess.run([CLI] + case["args"] + files + ["-t", "4", "-o", str(tmp_path / "o.tsv"), "-l", os.devnull],
+                       capture_output=True, text=True, timeout=60, env=env)
+    assert r.returncode == case["rc"] == 1
+    assert r.stderr == case["stderr"]
+
+
+def test_parallel_reader_reports_earliest_bad_line(tmp_path):
+    """Two malformed lines far apart in a file read by 8 threads: the first one wins, with its
+    absolute line number; comment lines before the header count."""
+    lines = ["# comment", "@ another", "repertoire_id\tsequence_id\tduplicate_count\tv_call\tj_call\tjunction_aa"]
+    for i in range(4000):
+        lines.append(f"R{i % 7}\ts{i}\t{i % 9 + 1}\tV{i % 5}\tJ{i % 3}\tCASS{'ADEF'[i % 4]}YEQYF")
+    lines[3 + 2500] = "R1\tsX\t0\tV1\tJ1\tCASSF"       # illegal duplicate_count on line 2504
+    lines[3 + 3900] = "R1\tsY\t3\tV1\tJ1\tCAS1F"       # illegal character later on
+    f = tmp_path / "bad.tsv"
+    f.write_text("\n".join(lines) + "\n")
+    env = dict(os.environ, COMPAIRR_B200_READ_MIN_BYTES="1000")
+    r = subprocess.run([CLI, "-m", str(f), "-t", "8", "-o", str(tmp_path / "o.tsv")], capture_output=True, text=True,
+                       timeout=60, env=env)
+    assert r.returncode == 1
+    assert r.stderr.endswith("\n\nError: Illegal duplicate_count on line 2504: 0\n")
+
+
 @pytest.mark.parametrize("args,msg", [
     ([], "Please specify a command (--help, --version, --matrix, --existence, --cluster, or --deduplicate)"),
     (["-m", "-x", "a", "b"], "Please specify just one command (--help, --version, --matrix, --existence, --cluster, or --deduplicate)"),

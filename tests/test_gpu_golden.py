@@ -30,6 +30,29 @@ def test_cli_reproduces_reference_files(case, tmp_path):
         assert sorted(lines[1:]) == case["pairs_sorted"]
 
 
+SPLIT = CASES[::3]
+
+
+@pytest.mark.parametrize("case", SPLIT, ids=[c["name"] for c in SPLIT])
+def test_cli_parallel_reader_reproduces_reference_files(case, tmp_path):
+    """Same golden cases with the input cut into ranges of a few hundred bytes parsed by 5 reader
+    threads: sequence order, id numbering and therefore every output byte must not change."""
+    files = [os.path.join(GOLDEN_DIR, f) for f in case["files"]]
+    out, pairs = tmp_path / "out.tsv", tmp_path / "pairs.tsv"
+    cmd = [CLI] + case["args"] + files + ["-t", "5", "-o", str(out), "-l", str(tmp_path / "log.txt")]
+    if case["pairs"]:
+        cmd += ["-p", str(pairs)]
+    env = dict(os.environ, COMPAIRR_B200_READ_MIN_BYTES="200")
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=env)
+    assert r.returncode == 0, r.stderr + open(tmp_path / "log.txt").read()
+    o = parse_args(case["args"])
+    assert_matrix_text(out.read_text(), case["output"], exact=is_integer_score(o))
+    if case["pairs"]:
+        lines = pairs.read_text().splitlines()
+        assert lines[0] == case["pairs_header"]
+        assert sorted(lines[1:]) == case["pairs_sorted"]
+
+
 @pytest.mark.parametrize("case", CASES, ids=[c["name"] for c in CASES])
 def test_cabi_reproduces_reference_files(case):
     o = parse_args(case["args"])
