@@ -123,7 +123,7 @@ void parse_header(const std::string& line, const Options& o, bool require_sequen
     }
     if (!seqcol) fprintf(g_log, " %s", o.seq_header);
     fprintf(g_log, "\n");
-    exit(1);
+    cli_exit(1);
   }
   bool any = false;
   for (int k : c.keep) any |= k < 1;
@@ -357,7 +357,7 @@ void parse_range(const char* b, const char* e, const ParseCtx& cx, Part& out) {
       fprintf(g_log, "\n\nError: missing or empty %s value on line %lu\n", o.seq_header, ln);
       break;
   }
-  exit(1);
+  cli_exit(1);
 }
 
 // run fn(t) for t in [0, n) on n threads (inline when n == 1)
@@ -389,12 +389,12 @@ void read_airr_tsv(const char* filename, const Options& o, bool require_sequence
     fd = open(filename, O_RDONLY);
   if (fd < 0) {
     fprintf(g_log, "\nError: Unable to open input data file (%s).\n", filename);
-    exit(1);
+    cli_exit(1);
   }
   struct stat fs;
   if (fstat(fd, &fs)) {
     fprintf(g_log, "\nUnable to fstat on input file (%s)\n", filename);
-    exit(1);
+    cli_exit(1);
   }
   if (!S_ISREG(fs.st_mode)) fprintf(g_log, "Waiting for data from standard input...\n");
   init_map(o.nucleotides);

@@ -42,5 +42,9 @@ int main(int argc, char** argv) {
   if (pairsfile) fclose(pairsfile);
   fclose(outfile);
   if (g_log != stderr) fclose(g_log);
-  return 0;
+  // Everything the user asked for is on disk.  Leave without running the CUDA runtime's exit
+  // handlers: tearing down the primary context and its memory pools takes seconds (measured: 4 s
+  // of a 5.4 s command) and frees nothing the operating system does not free anyway.
+  fflush(nullptr);
+  _exit(0);
 }

@@ -1,6 +1,8 @@
 // options.cpp — see options.h.  Written against the behaviour of src/compairr.cc:292-706.
 #include "options.h"
 
+#include <unistd.h>
+
 #include <getopt.h>
 #include <stdlib.h>
 #include <string.h>
@@ -15,9 +17,14 @@ static const char* const kScoreDescr[SCORE_END] = {
     "Sum of maximum of counts",  "Sum of mean of counts",   "Morisita-Horn index",
     "Jaccard index"};
 
-void fatal(const char* msg) {
+void cli_exit(int code) {
+  fflush(nullptr);
+  _exit(code);
+}
+
+[[noreturn]] void fatal(const char* msg) {
   fprintf(stderr, "\nError: %s\n", msg);
-  exit(1);
+  cli_exit(1);
 }
 
 void show_header() {
@@ -99,7 +106,7 @@ static int64_t parse_long(const char* s, const char* what) {
   const int64_t v = strtol(s, &end, 10);
   if (*end) {
     fprintf(stderr, "\nInvalid numeric argument for option %s\n", what);
-    exit(1);
+    cli_exit(1);
   }
   return v;
 }
@@ -153,7 +160,7 @@ void parse_args(int argc, char** argv, Options& o) {
             break;
           }
         fprintf(stderr, "Error: Option -%c or --%s specified more than once.\n", c, lname);
-        exit(1);
+        cli_exit(1);
       }
       used[c - 'a'] = true;
     }
@@ -186,7 +193,7 @@ void parse_args(int argc, char** argv, Options& o) {
       default:
         show_header();
         show_usage();
-        exit(1);
+        cli_exit(1);
     }
   }
 
@@ -228,7 +235,7 @@ void parse_args(int argc, char** argv, Options& o) {
   }
   if (o.threads < 1 || o.threads > 256) {
     fprintf(stderr, "\nError: Illegal number of threads specified with -t or --threads, must be in the range 1 to %u.\n", 256u);
-    exit(1);
+    cli_exit(1);
   }
   if (o.differences < 0) fatal("Differences specified with -d or -differences cannot be negative.");
   if (o.indels && o.differences != 1) fatal("Indels are only allowed when d=1");

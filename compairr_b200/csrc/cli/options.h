@@ -35,6 +35,9 @@ enum { SCORE_PRODUCT, SCORE_RATIO, SCORE_MIN, SCORE_MAX, SCORE_MEAN, SCORE_MH, S
 
 extern FILE* g_log;  // stderr or the -l file
 
+[[noreturn]] // flush the C streams and leave at once: no exit handlers (a CUDA context may be coming up on
+// another thread, and the CUDA runtime's own teardown takes seconds)
+[[noreturn]] void cli_exit(int code);
 [[noreturn]] void fatal(const char* msg);  // "\nError: <msg>\n" on stderr, exit 1 (util.cc:84-88)
 void parse_args(int argc, char** argv, Options& o);
 void show_header();

@@ -7,6 +7,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -150,12 +151,43 @@ struct PairWriter {
 void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
   GeneTables genes;
   SeqDb d1, d2s;
+  // COMPAIRR_B200_TRACE=1: wall-clock marks on stderr (where the time outside the logged phases goes)
+  const bool trace = getenv("COMPAIRR_B200_TRACE") != nullptr;
+  const auto t_start = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (trace)
+      fprintf(stderr, "[trace] %8.3f s  %s\n",
+              std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(), what);
+  };
 
+  // the CUDA contexts come up (0.6 - 1.4 s) on another thread while the host parses its input: a
+  // throw-away engine context per device leaves the device's primary context initialised
+  std::thread warm;
+  if (!getenv("COMPAIRR_B200_NO_WARM"))
+    warm = std::thread([&] {
+      const int nd = cb_device_count();
+      for (int g = 0; g < o.gpus && o.device + g < nd; g++) {
+        cb_config w{};
+        w.abi_version = CB_ABI_VERSION;
+        w.device = o.device + g;
+        w.alphabet_size = o.alphabet_size;
+        w.n_reps_a = 1;
+        w.no_matrix = 1;
+        cb_ctx* c = nullptr;
+        if (cb_create(&w, &c) == 0) cb_destroy(c);
+      }
+    });
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } warm_guard{warm};
   fprintf(g_log, "Immune receptor repertoire set 1\n\n");
   read_airr_tsv(o.input1, o, o.existence, o.existence || o.pairs, "1", genes, d1);
   fprintf(g_log, "\n");
+  mark("set 1 read");
   const RepStats s1 = rep_stats(d1);
   log_rep_table(d1, s1);
+  mark("set 1 repertoire table");
   if (o.existence && d1.rep_names.size() > 1)
     fatal("Multiple repertoires are not allowed in the first file specified on the command line with the -x or --existence command.");
 
@@ -176,6 +208,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
   } else if (d2.rep_names.empty()) {
     fatal("Repertoire set is missing repertoire_id.");
   }
+  mark("set 2 read + table");
   fprintf(g_log, "Unique V genes:    %lu\n", (unsigned long)genes.v_names.size());
   fprintf(g_log, "Unique J genes:    %lu\n", (unsigned long)genes.j_names.size());
 
@@ -197,11 +230,14 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
   cfg.n_reps_a = (uint32_t)std::max<uint64_t>(R1, 1);
   cfg.seed = 1;
 
+  if (warm.joinable()) warm.join();
+  mark("warm-up joined");
   std::vector<cb_ctx*> ctx(ngpu, nullptr);
   for (int g = 0; g < ngpu; g++) {
     cfg.device = o.device + g;
     if (cb_create(&cfg, &ctx[g])) engine_fatal(nullptr);
   }
+  mark("contexts created");
   const cb_set whole_b = as_cb_set(d2, 0, d2.n());
   std::vector<cb_dset*> dev_b(ngpu, nullptr);
 
@@ -219,6 +255,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
       if (rc[g]) engine_fatal(ctx[g]);
   }
   progress_end(o, "Hashing sequences:");
+  mark("set B uploaded + built");
   if (o.differences <= 2) {
     if (two_sets) {  // duplicates in set 1 are only checked with two distinct sets (overlap.cc:846-852)
       const cb_set whole_a = as_cb_set(d1, 0, N1);
@@ -232,6 +269,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
     if (dup2) fprintf(g_log, "Warning: %lu duplicates detected in repertoire set 2\n", (unsigned long)dup2);
   }
 
+  mark("duplicate checks");
   // ---- analysis --------------------------------------------------------------------------------
   std::vector<double> matrix;
   const uint64_t rows = o.existence ? N1 : R1;
@@ -296,7 +334,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
   for (int g = 0; g < ngpu; g++)
     if (!errors[g].empty()) {
       fprintf(stderr, "\nError: %s\n", errors[g].c_str());
-      exit(1);
+      cli_exit(1);
     }
   if (!o.existence && !o.no_matrix) {  // sum of the per-GPU partial matrices
     std::vector<double> part(rows * R2);
@@ -309,10 +347,12 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
   if (o.pairs && ngpu > 1)
     for (int g = 0; g < ngpu; g++) pw.write(pair_out[g].data(), pair_out[g].size());
   progress_end(o, "Analysing:        ");
+  mark("analysis done");
   for (int g = 0; g < ngpu; g++) {
     cb_free_set(ctx[g], dev_b[g]);
     cb_destroy(ctx[g]);
   }
+  mark("contexts destroyed");
 
   // ---- results (overlap.cc:540-577, 944-1039) ---------------------------------------------------
   auto value = [&](uint64_t s, unsigned t) -> double {
@@ -355,4 +395,5 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
     progress_end(o, "Writing results:  ");
   }
   fprintf(g_log, "\n");
+  mark("results written");
 }
