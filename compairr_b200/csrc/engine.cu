@@ -374,6 +374,7 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
   uint64_t* part_hash = nullptr;
   uint32_t *iota = nullptr, *part_idx = nullptr;
   void* temp = nullptr;
+  c->insert_launches = n ? 1 : 0;
   if (!(c->cfg.flags & CB_FLAG_NO_PARTITION) && table_bytes >= (256ull << 20) && n >= (1ull << 22) &&
       n * 64 >= t.slots && n < 0xffffffffull) {
     int tbits = 0;
@@ -391,6 +392,7 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
       e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, s->d_hash + first, part_hash, iota, part_idx, n,
                                           CB_PARTITION_TOP_BIT - pbits, CB_PARTITION_TOP_BIT, c->stream);
     }
+    if (e == cudaSuccess) c->insert_launches += 1 + 2 + pbits / 8;  // iota, histogram, scan, one sweep per digit
     if (e != cudaSuccess) {  // no memory for the sort buffers: the direct path still works
       (void)cudaGetLastError();
       cb_dfree(part_hash);
@@ -486,7 +488,7 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
   if (rc) return rc;
   if (c->d_table) {
     cudaEventElapsedTime(&c->stats.ms_build_b, c->ev[0], c->ev[6]);
-    c->stats.kernel_launches = b->n ? 3 : 1;
+    c->stats.kernel_launches = b->n ? 3 + c->insert_launches : 1;  // clear, reset links, [sort,] insert, duplicates
   }
   return CB_OK;
 }

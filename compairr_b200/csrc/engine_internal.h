@@ -53,6 +53,7 @@ struct BuiltTable {
 };
 
 struct cb_ctx {
+  int insert_launches = 0;  // kernels launched by the most recent cb_table_insert (ours + CUB radix sort passes)
   cb_config cfg{};
   int device = 0;
   int sm_count = 148;

@@ -19,6 +19,8 @@
 // into shared memory with coalesced loads, so the per-seed dependent global loads are paid once per
 // batch.  variant2_kernel (d = 2): seeds are heavy (~36 000 probes), warps take (seed, part) items
 // from a global dispenser.
+#include <algorithm>
+
 #include "device_utils.cuh"
 #include "kernels.cuh"
 
@@ -27,7 +29,7 @@ namespace cb {
 constexpr int VK_THREADS = 256;
 constexpr int VK_WARPS = VK_THREADS / 32;
 constexpr int VK_QCAP = 64;  // ring entries per queue per warp
-constexpr int VK_U = 2;      // probes per lane per step
+constexpr int VK_U = 4;      // probes per lane per step: 4 independent filter loads in flight per lane (2: -8 %, 8: register-bound, 2x slower)
 constexpr int VK_WB = 8;     // seeds per warp batch (d = 1)
 
 // Per-warp shared-memory block, addressed from ONE base pointer to keep the register footprint of
@@ -510,13 +512,29 @@ static int launch_one(K kern, const ProbeParams& p, size_t smem, uint64_t work_c
     *err = "variant kernel does not fit on an SM";
     return -1;
   }
+  // The rate of random 8-byte loads an SM sustains has a cliff in the shared-memory carve-out
+  // (tools/bench_l2_random.cu on B200: 268-290 G loads/s chip-wide up to a 100 KB carve-out,
+  // 139-158 G loads/s from 132 KB on, whatever the occupancy) — the L1 side that tracks the
+  // misses in flight shrinks with it.  The Bloom stage is nothing but such loads, so: no more
+  // resident CTAs than fit 100 KB of shared memory (1 KB per CTA is the system's), and ask for
+  // exactly that carve-out instead of the driver's "room for the most CTAs" default.
+  constexpr size_t kCarveCliff = 100 * 1024;
+  const int fit = (int)(kCarveCliff / (smem + 1024));
+  if (fit >= 2 || (fit == 1 && per_sm == 1)) {
+    per_sm = std::min(per_sm, fit);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)(kCarveCliff * 100 / (228 * 1024)));
+  }
   uint64_t grid = (uint64_t)sm_count * per_sm;  // persistent: whole waves of resident CTAs
   if (work_ctas < grid) grid = work_ctas;
   kern<<<(unsigned)grid, VK_THREADS, smem, st>>>(p);
   return 1;
 }
 
-int launch_variant_kernels(const ProbeParams& p, int sm_count, cudaStream_t st, const char** err) {
+int launch_variant_kernels(const ProbeParams& p_in, int sm_count, cudaStream_t st, const char** err) {
+  // only the Zobrist rows the longest seed can touch are staged in shared memory (positions
+  // 0..lmax, +1 for the shifted rows of the indel scans): the table itself may be longer
+  ProbeParams p = p_in;
+  p.zrows = std::min(p_in.zrows, p_in.lmax + 2);
   if (p.lmax + 1 > VAR_MAX_POS) {
     *err = "sequence longer than 510 residues on the d<=2 path";
     return -1;
