@@ -9,6 +9,6 @@ Layout (only what the path needs):
   synth.py         seeded synthetic repertoires
 """
 from .seqset import SeqSet, NarrowSet, encode_sequences, AA_ALPHABET, NT_ALPHABET  # noqa: F401
-from .engine import Engine, OverlapOptions, overlap, SCORES  # noqa: F401
+from .engine import Engine, OverlapOptions, overlap, dedup, cluster, SCORES  # noqa: F401
 
-__all__ = ["SeqSet", "Engine", "OverlapOptions", "overlap", "SCORES", "encode_sequences"]
+__all__ = ["SeqSet", "Engine", "OverlapOptions", "overlap", "dedup", "cluster", "SCORES", "encode_sequences"]

@@ -75,6 +75,8 @@ SYMBOLS = [
     ("cb_build_b", C.c_int, [P, P]),
     ("cb_dups_b", C.c_uint64, [P]),
     ("cb_count_dups", C.c_int, [P, P, C.POINTER(C.c_uint64)]),
+    ("cb_dedup", C.c_int, [P, P, P, P, C.POINTER(C.c_uint64)]),
+    ("cb_cluster", C.c_int, [P, P, P, P, P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("cb_run", C.c_int, [P, P, C.c_uint64, C.c_uint64]),
     ("cb_set_b", C.c_int, [P, C.POINTER(cb_set)]),
     ("cb_set_b_cols", C.c_int, [P, C.POINTER(cb_set_cols)]),

@@ -1,10 +1,11 @@
-// main.cpp — compairr_b200: a CompAIRR-compatible command line for the -m / -x commands on top of
+// main.cpp — compairr_b200: a CompAIRR-compatible command line (-m / -x / -c / -z) on top of
 // the GPU engine (main(), src/compairr.cc:743-798).
 #include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
 #include "options.h"
+#include "cluster_cmd.h"
 #include "overlap_cmd.h"
 
 static FILE* open_output(const char* name) {  // "-" = stdout (util.cc:157-170)
@@ -37,7 +38,12 @@ int main(int argc, char** argv) {
   show_time("Start time:        ");
   show_args(o);
   fprintf(g_log, "\n");
-  overlap_command(o, outfile, pairsfile);
+  if (o.matrix || o.existence)
+    overlap_command(o, outfile, pairsfile);
+  else if (o.deduplicate)
+    dedup_command(o, outfile);
+  else
+    cluster_command(o, outfile);
   show_time("End time:          ");
   if (pairsfile) fclose(pairsfile);
   fclose(outfile);

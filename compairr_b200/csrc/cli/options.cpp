@@ -39,8 +39,8 @@ void show_usage() {
       " -v, --version               display version information",
       " -m, --matrix                compute overlap matrix between two sets",
       " -x, --existence             check existence of sequences in repertoires",
-      " -c, --cluster               cluster sequences in one repertoire (not in this build)",
-      " -z, --deduplicate           deduplicate sequences in repertoires (not in this build)", "",
+      " -c, --cluster               cluster sequences in one repertoire",
+      " -z, --deduplicate           deduplicate sequences in repertoires", "",
       "General options:",
       " -d, --differences INTEGER   number of differences accepted (0*)",
       " -i, --indels                allow insertions or deletions when d=1",
@@ -74,13 +74,15 @@ void show_time(const char* prompt) {
 
 void show_args(const Options& o) {
   if (o.matrix) fprintf(g_log, "Command:           Overlap (-m)\n");
+  if (o.cluster) fprintf(g_log, "Command:           Cluster (-c)\n");
   if (o.existence) fprintf(g_log, "Command:           Existence (-x)\n");
+  if (o.deduplicate) fprintf(g_log, "Command:           Deduplicate (--deduplicate)\n");
   if (o.matrix) {
     fprintf(g_log, "Repertoire set 1:  %s\n", o.input1);
     fprintf(g_log, "Repertoire set 2:  %s\n", o.input2 ? o.input2 : "(same as set 1)");
   } else {
     fprintf(g_log, "Repertoire:        %s\n", o.input1);
-    fprintf(g_log, "Repertoire set:    %s\n", o.input2);
+    if (o.existence) fprintf(g_log, "Repertoire set:    %s\n", o.input2);
   }
   auto yn = [](bool b) { return b ? "Yes" : "No"; };
   fprintf(g_log, "Nucleotides (n):   %s\n", yn(o.nucleotides));
@@ -94,10 +96,12 @@ void show_args(const Options& o) {
   fprintf(g_log, "Threads (t):       %ld\n", (long)o.threads);
   fprintf(g_log, "GPUs:              %d (first device %d)\n", o.gpus, o.device);
   fprintf(g_log, "Output file (o):   %s\n", o.no_matrix ? "(none)" : o.output);
-  fprintf(g_log, "Output format (a): %s\n", o.alternative ? "Column" : "Matrix");
-  fprintf(g_log, "Score (s):         %s\n", kScoreDescr[o.score]);
-  fprintf(g_log, "Pairs file (p):    %s\n", o.pairs ? o.pairs : "(none)");
-  fprintf(g_log, "Keep columns:      %s\n", o.keep_columns ? o.keep_columns : "");
+  if (o.matrix || o.existence) {
+    fprintf(g_log, "Output format (a): %s\n", o.alternative ? "Column" : "Matrix");
+    fprintf(g_log, "Score (s):         %s\n", kScoreDescr[o.score]);
+    fprintf(g_log, "Pairs file (p):    %s\n", o.pairs ? o.pairs : "(none)");
+    fprintf(g_log, "Keep columns:      %s\n", o.keep_columns ? o.keep_columns : "");
+  }
   fprintf(g_log, "Log file (l):      %s\n", o.log ? o.log : "(stderr)");
 }
 
@@ -265,6 +269,4 @@ void parse_args(int argc, char** argv, Options& o) {
   if (o.device < 0) fatal("Option --device cannot be negative.");
   o.alphabet_size = o.nucleotides ? 4 : 20;
   o.seq_header = o.cdr3 ? (o.nucleotides ? "cdr3" : "cdr3_aa") : (o.nucleotides ? "junction" : "junction_aa");
-  if (o.cluster || o.deduplicate)
-    fatal("The --cluster and --deduplicate commands are not part of this build (overlap and existence only).");
 }

@@ -110,6 +110,7 @@ __device__ __forceinline__ uint32_t verify_and_record(const ProbeParams* __restr
         PairOut po;
         po.a = seed_idx + P->a.index_base;
         po.b = node + P->b.index_base;
+        if (P->pair_variant) po.b |= (uint64_t)var << 32;
         P->pairs[at] = po;
       }
     }

@@ -520,6 +520,44 @@ extern "C" int cb_count_dups(cb_ctx* c, cb_dset* s, uint64_t* out) {
   return CB_OK;
 }
 
+extern "C" int cb_dedup(cb_ctx* c, cb_dset* s, uint32_t* leader_out, uint64_t* count_out, uint64_t* merged_out) {
+  if (!c || !s || !leader_out || !count_out) return fail(c, CB_ERR_INVALID, "cb_dedup: NULL argument");
+  int rc = bind(c);
+  if (rc) return rc;
+  if (merged_out) *merged_out = 0;
+  if (s->n == 0) return CB_OK;
+  if (s->n >= 0xffffffffull) return fail(c, CB_ERR_LIMIT, "more than 2^32-1 sequences in one set");
+  const bool live = s == c->b && c->d_table;  // its occurrence lists are already built
+  BuiltTable bt;
+  if (!live) {
+    rc = build_table_for(c, s, false, &bt);
+    if (rc) return rc;
+  }
+  uint32_t* d_lead = nullptr;
+  unsigned long long* d_sum = nullptr;
+  cudaError_t e = cb_dmalloc(&d_lead, s->n * sizeof(uint32_t));
+  if (e == cudaSuccess) e = cb_dmalloc(&d_sum, s->n * sizeof(unsigned long long));
+  if (e == cudaSuccess) e = cudaMemsetAsync(d_sum, 0, s->n * sizeof(unsigned long long), c->stream);
+  if (e == cudaSuccess) {
+    rc = zero_counter(c, CTR_DUPS);
+    if (!rc) {
+      launch_dedup(cb_view_of(s), c->cfg.ignore_counts != 0, d_lead, d_sum, c->d_counters, c->stream);
+      e = cudaGetLastError();
+      if (e == cudaSuccess) e = cudaMemcpyAsync(leader_out, d_lead, s->n * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(count_out, d_sum, s->n * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream);
+      if (e == cudaSuccess) rc = read_counters(c);  // synchronises the stream
+    }
+  }
+  cb_dfree(d_lead);
+  cb_dfree(d_sum);
+  bt.release();
+  if (e != cudaSuccess)
+    return fail(c, e == cudaErrorMemoryAllocation ? CB_ERR_NOMEM : CB_ERR_CUDA, "cb_dedup: %s", cudaGetErrorString(e));
+  if (rc) return rc;
+  if (merged_out) *merged_out = c->h_counters[CTR_DUPS];
+  return CB_OK;
+}
+
 // ---- set A -------------------------------------------------------------------------------------
 
 static int ensure_matrix(cb_ctx* c, uint64_t rows, uint64_t cols, bool reset) {
@@ -715,6 +753,7 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     p.existence = existence;
     p.no_matrix = c->cfg.no_matrix != 0;
     p.want_pairs = c->cfg.want_pairs != 0;
+    p.pair_variant = c->network_mode;
     p.use_bloom = !(c->cfg.flags & CB_FLAG_NO_BLOOM);
     p.count_bloom = 1;
     p.differences = c->cfg.differences;

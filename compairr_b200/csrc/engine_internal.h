@@ -94,6 +94,7 @@ struct cb_ctx {
   cb::PairOut* d_pairs = nullptr;
   uint64_t pairs_cap = 0;
   std::vector<cb_pair> pending;
+  bool network_mode = false;  // cb_cluster: pairs carry their variant descriptor (cluster.cu)
 
   cb_stats stats{};
 };

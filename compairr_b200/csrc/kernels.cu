@@ -291,6 +291,61 @@ void launch_count_dups(DeviceSetView s, unsigned long long* counters, cudaStream
   dups_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(s, counters);
 }
 
+// Deduplication (src/dedup.cc:62-137 process(), :27-59 report()): sequences with equal
+// (repertoire, V, J unless -g, residues) form a group; the group is reported once, at its FIRST
+// member in file order, with the summed count.  On the occurrence lists built by build_kernel every
+// unordered pair of group members is seen exactly once — by whichever of the two sits higher up
+// the list — so two atomicMin per pair leave lead[x] = smallest index of x's group.  The serial
+// reference links each duplicate to the latest earlier one instead (next_seq[]), same groups.
+__global__ void __launch_bounds__(256) dedup_lead_kernel(DeviceSetView s, uint32_t* lead) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < s.n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint4 hi = __ldg(reinterpret_cast<const uint4*>(s.meta + i) + 1);  // v, j, rep, next
+    const uint32_t rep = hi.z;
+    uint32_t node = hi.w, mine = (uint32_t)i;
+    while (node != SEQ_NIL) {
+      const uint4 o = __ldg(reinterpret_cast<const uint4*>(s.meta + node) + 1);
+      if (o.z == rep) {
+        atomicMin(lead + node, (uint32_t)i);
+        mine = min(mine, node);
+      }
+      node = o.w;
+    }
+    if (mine != (uint32_t)i) atomicMin(lead + i, mine);
+  }
+}
+
+// counts[lead[i]] += count of i (1 with -f, dedup.cc:34,39); counters[CTR_DUPS] += members merged away
+__global__ void __launch_bounds__(256)
+dedup_sum_kernel(DeviceSetView s, const uint32_t* __restrict__ lead, bool ignore_counts,
+                 unsigned long long* sums, unsigned long long* counters) {
+  uint32_t merged = 0;
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < s.n;
+       i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint32_t l = lead[i];
+    const unsigned long long c = ignore_counts ? 1ull : (unsigned long long)s.meta[i].count;
+    if (l == (uint32_t)i) {
+      atomicAdd(sums + i, c);  // members may be adding to the same cell
+    } else {
+      atomicAdd(sums + l, c);
+      merged++;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) merged += __shfl_xor_sync(FULL, merged, o);
+  if ((threadIdx.x & 31) == 0 && merged) atomicAdd(counters + CTR_DUPS, (unsigned long long)merged);
+}
+
+void launch_dedup(DeviceSetView s, bool ignore_counts, uint32_t* lead, unsigned long long* sums,
+                  unsigned long long* counters, cudaStream_t st) {
+  if (s.n == 0) return;
+  const uint64_t blocks = (s.n + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < 148 * 16 ? blocks : 148 * 16);
+  iota_kernel<<<grid, 256, 0, st>>>(lead, s.n);
+  dedup_lead_kernel<<<grid, 256, 0, st>>>(s, lead);
+  dedup_sum_kernel<<<grid, 256, 0, st>>>(s, lead, ignore_counts, sums, counters);
+}
+
 // Bookkeeping: closed-form number of variants for a range of seeds (SURVEY section 8d "unit of work").
 __global__ void __launch_bounds__(256)
 count_probes_kernel(DeviceSetView a, uint64_t first, uint64_t count, uint32_t sigma, int d,

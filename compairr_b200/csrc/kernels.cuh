@@ -66,7 +66,8 @@ struct ProbeParams {
   uint32_t split;  // d=2: work items per seed
   int32_t score;
   uint8_t ignore_counts, ignore_genes, existence, no_matrix;
-  uint8_t want_pairs, use_bloom, count_bloom, matrix_only_pairs_off;
+  uint8_t want_pairs, use_bloom, count_bloom;
+  uint8_t pair_variant;  // network mode (-c): pair.b carries the 31-bit variant descriptor in its high half
   int32_t differences;
   uint8_t indels;
   uint8_t bloom_k2;    // first-level geometry: 1+1 bits instead of 3+3
@@ -106,6 +107,10 @@ void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const 
                   unsigned long long* bloom2, uint32_t bloom2_blocks, cudaStream_t st);
 void launch_iota(uint32_t* p, uint64_t n, cudaStream_t st);
 void launch_count_dups(DeviceSetView s, unsigned long long* counters, cudaStream_t st);
+// -z: lead[i] = first member (file order) of i's (repertoire, V, J, sequence) group, sums[lead] =
+// the group's count (sums must be zero on entry), counters[CTR_DUPS] += members merged away
+void launch_dedup(DeviceSetView s, bool ignore_counts, uint32_t* lead, unsigned long long* sums,
+                  unsigned long long* counters, cudaStream_t st);
 
 // K3+K4: enumerate variants, Bloom, probe, verify, accumulate.  Returns launches made, <0 on
 // a configuration the kernels cannot take (message in *err).

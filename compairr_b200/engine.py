@@ -190,6 +190,26 @@ class Engine:
         self._check(cabi.lib.cb_count_dups(self._ctx, d.handle, C.byref(out)))
         return int(out.value)
 
+    def dedup(self, d: DeviceSet):
+        """`compairr -z` on a resident set (src/dedup.cc): (leader index per sequence, group count at
+        each leader, members merged away)."""
+        lead = np.zeros(d.n, dtype=np.uint32)
+        cnt = np.zeros(d.n, dtype=np.uint64)
+        merged = C.c_uint64()
+        self._check(cabi.lib.cb_dedup(self._ctx, d.handle, _ptr(lead), _ptr(cnt), C.byref(merged)))
+        return lead, cnt, int(merged.value)
+
+    def cluster(self, d: DeviceSet):
+        """`compairr -c` on a resident set (src/cluster.cc): per output row (sequence index, 1-based
+        cluster number, cluster size), plus {"clusters", "edges"}."""
+        order = np.zeros(d.n, dtype=np.uint32)
+        no = np.zeros(d.n, dtype=np.uint32)
+        size = np.zeros(d.n, dtype=np.uint32)
+        ncl, ned = C.c_uint64(), C.c_uint64()
+        self._check(cabi.lib.cb_cluster(self._ctx, d.handle, _ptr(order), _ptr(no), _ptr(size),
+                                        C.byref(ncl), C.byref(ned)))
+        return order, no, size, {"clusters": int(ncl.value), "edges": int(ned.value)}
+
     def run(self, d: DeviceSet, first: int = 0, count: Optional[int] = None):
         self._check(cabi.lib.cb_run(self._ctx, d.handle, first, d.n - first if count is None else count))
 
@@ -264,3 +284,21 @@ def overlap(a: SeqSet, b: Optional[SeqSet], opts: OverlapOptions):
             da.free()
         db.free()
         return m, p, info
+
+
+def dedup(a: SeqSet, opts: OverlapOptions):
+    """One-call `compairr -z`: (leader, count, merged) as Engine.dedup."""
+    with Engine(opts, n_reps_a=max(a.n_reps, 1)) as eng:
+        da = eng.upload(a)
+        out = eng.dedup(da)
+        da.free()
+        return out
+
+
+def cluster(a: SeqSet, opts: OverlapOptions):
+    """One-call `compairr -c`: (order, cluster_no, cluster_size, info) as Engine.cluster."""
+    with Engine(opts, n_reps_a=max(a.n_reps, 1)) as eng:
+        da = eng.upload(a)
+        out = eng.cluster(da)
+        da.free()
+        return out

@@ -89,3 +89,36 @@ def format_pairs(pairs: np.ndarray, a: SeqSet, b: SeqSet, distance=False):
             line += f"\t{d}"
         rows.append(line)
     return header, rows
+
+
+def _alpha(s: SeqSet):
+    return "acgt" if s.nucleotides else AA_ALPHABET
+
+
+def _seq_text(s: SeqSet, i: int) -> str:
+    al = _alpha(s)
+    return "".join(al[c] for c in s.residues[int(s.offsets[i]):int(s.offsets[i + 1])])
+
+
+def format_clusters(order, cluster_no, cluster_size, s: SeqSet) -> str:
+    """The `-c` output file (src/cluster.cc:417-446)."""
+    rn, vn, jn = s.names()
+    col = "junction" if s.nucleotides else "junction_aa"
+    out = [f"#cluster_no\tcluster_size\trepertoire_id\tsequence_id\tduplicate_count\tv_call\tj_call\t{col}"]
+    for i, no, size in zip(np.asarray(order).tolist(), np.asarray(cluster_no).tolist(), np.asarray(cluster_size).tolist()):
+        sid = s.seq_ids[i] if s.seq_ids is not None else ""
+        out.append(f"{no}\t{size}\t{rn[s.rep[i]]}\t{sid}\t{s.count[i]}\t{vn[s.v_gene[i]]}\t{jn[s.j_gene[i]]}\t{_seq_text(s, i)}")
+    return "\n".join(out) + "\n"
+
+
+def format_dedup(leader, count, s: SeqSet, ignore_genes=False) -> str:
+    """The `-z` output file (src/dedup.cc:27-59, 169-173, 185-190): one row per group, at its
+    first member, in file order."""
+    rn, vn, jn = s.names()
+    col = "junction" if s.nucleotides else "junction_aa"
+    out = ["repertoire_id\tduplicate_count" + ("" if ignore_genes else "\tv_call\tj_call") + f"\t{col}"]
+    leader = np.asarray(leader)
+    for i in np.nonzero(leader == np.arange(leader.size))[0].tolist():
+        genes = "" if ignore_genes else f"\t{vn[s.v_gene[i]]}\t{jn[s.j_gene[i]]}"
+        out.append(f"{rn[s.rep[i]]}\t{int(count[i])}{genes}\t{_seq_text(s, i)}")
+    return "\n".join(out) + "\n"

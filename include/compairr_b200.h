@@ -213,6 +213,24 @@ int cb_build_b(cb_ctx *ctx, cb_dset *b);
 uint64_t cb_dups_b(const cb_ctx *ctx);
 /* Replaces check_duplicates() (overlap.cc:579-605) for an arbitrary resident set (dup1). */
 int cb_count_dups(cb_ctx *ctx, cb_dset *set, uint64_t *out);
+/* Replaces the process() loop of dedup() (src/dedup.cc:62-137,176-183) for a resident set:
+   sequences with equal (repertoire, V, J unless ignore_genes, residues) form a group.
+   leader_out[i] (n entries) = index of the first member of i's group in set order (== i for
+   the member the reference reports, dedup.cc:27-59); count_out[i] (n entries) = summed
+   duplicate_count of the group at its leader (1 per member with ignore_counts), 0 elsewhere;
+   *merged_out (may be NULL) = members merged away = the reference's "Duplicates merged". */
+int cb_dedup(cb_ctx *ctx, cb_dset *set, uint32_t *leader_out, uint64_t *count_out, uint64_t *merged_out);
+/* Replaces the network and clustering phases of cluster() (src/cluster.cc:57-69,71-274 and
+   :277-300,356-411) for a resident set (index_base 0): single-linkage clusters of the graph
+   that links two sequences when they match under the context's -d/-i/-g options (the same
+   kernels as cb_run, as a self-comparison without self hits).  Builds the set's table first if
+   it is not the context's current set B.  Outputs, n entries each, one per OUTPUT ROW in the
+   reference's row order (clusters by decreasing size, equal sizes in order of their first
+   sequence; inside a cluster the reference's breadth-first order): order_out = sequence index,
+   cluster_no_out = 1-based cluster number, cluster_size_out = size of that cluster.
+   *n_clusters_out / *n_edges_out (either may be NULL) = clusters / directed edges found. */
+int cb_cluster(cb_ctx *ctx, cb_dset *set, uint32_t *order_out, uint32_t *cluster_no_out,
+               uint32_t *cluster_size_out, uint64_t *n_clusters_out, uint64_t *n_edges_out);
 
 /* ---- set A: enumerate, probe, verify, accumulate ------------------------------------------- */
 

@@ -4,6 +4,7 @@ __graft_entry__.smoke() and bench.py's CPU-baseline legs, never from compairr_b2
   overlap(a, b, ...)        the plain-C restatement (overlap_oracle.c) through ctypes
   brute_force(a, b, ...)    a pure-numpy/Python statement of the DEFINITION,
                             hash-free, for small cases
+  dedup(s, ...), cluster(s, ...)   restatements of src/dedup.cc and src/cluster.cc (`-z`, `-c`)
   run_reference(args)       the unmodified reference binary oracle/_ref/compairr (built from
                             /root/reference/src by oracle/Makefile) on TSV files
 """
@@ -125,6 +126,25 @@ def enumerate_variants(codes, sigma, differences, indels):
     return recs, [tuple(int(x) for x in row[1:1 + row[0]]) for row in seqs]
 
 
+def _variant_bytes(codes, sigma, differences, indels):
+    """the variants of one sequence, in enumeration order, as bytes objects"""
+    codes = np.ascontiguousarray(codes, dtype=np.uint8)
+    L = lib()
+    n = L.orc_enumerate(_p(codes), codes.size, sigma, differences, int(indels), None, None, 0, 0)
+    stride = codes.size + 2
+    seqs = np.zeros((n, stride), dtype=np.uint8)
+    L.orc_enumerate(_p(codes), codes.size, sigma, differences, int(indels), None, _p(seqs), stride, n)
+    out = [b""] * n
+    for ln in np.unique(seqs[:, 0]).tolist():
+        idx = np.nonzero(seqs[:, 0] == ln)[0]
+        if ln == 0:
+            continue
+        rows = np.ascontiguousarray(seqs[idx, 1:1 + ln]).view(f"V{ln}").ravel().tolist()
+        for k, r in zip(idx.tolist(), rows):
+            out[k] = r
+    return out
+
+
 # ---- hash-free statement of the definition (SURVEY.md section 4), small inputs only ----------
 
 def _within(x, y, d, indels):
@@ -170,6 +190,88 @@ def brute_force(a, b=None, differences=0, indels=False, ignore_genes=False, igno
                 m[i if existence else a.rep[i], b.rep[k]] += _score(score, ignore_counts, int(a.count[i]), int(b.count[k]))
                 pairs.append((i, k))
     return m, np.array(pairs, dtype=np.uint64).reshape(-1, 2)
+
+
+# ---- `-z` and `-c`: restatements of src/dedup.cc and src/cluster.cc, small inputs only ----------
+# Pinned by tests/test_oracle_golden.py against tests/golden/golden_cz.json (outputs of the
+# unmodified reference binary, byte for byte).  The reference's open-addressing table becomes a
+# dict keyed by what its probe loop compares; a dict value lists indices in insertion (= index)
+# order, which is the order a linear-probing chain filled in index order is walked in.
+
+def _seq(s, i):
+    return bytes(s.residues[int(s.offsets[i]):int(s.offsets[i + 1])])
+
+
+def dedup(s, ignore_genes=False, ignore_counts=False):
+    """dedup(), src/dedup.cc:139-215.  process() (:62-137) links every sequence to the latest
+    earlier one with the same repertoire, V, J (unless -g) and residues; report() (:27-59) prints
+    each chain once, at its first member, with the summed count (1 per member with -f).
+    -> (leader index per sequence, summed count at each leader else 0, duplicates merged)"""
+    last = {}
+    lead = np.arange(s.n, dtype=np.uint32)
+    cnt = np.zeros(s.n, dtype=np.uint64)
+    merged = 0
+    for i in range(s.n):
+        key = (int(s.rep[i]), _seq(s, i)) if ignore_genes else \
+              (int(s.rep[i]), int(s.v_gene[i]), int(s.j_gene[i]), _seq(s, i))
+        if key in last:                      # dedup.cc:128-132: next_seq[last] = seed, returns true
+            lead[i] = lead[last[key]]
+            merged += 1
+        last[key] = i
+        cnt[lead[i]] += np.uint64(1 if ignore_counts else int(s.count[i]))   # report(), :34-43
+    return lead, cnt, merged
+
+
+def cluster(s, differences=0, indels=False, ignore_genes=False):
+    """cluster(), src/cluster.cc:302-475.
+    network (:71-274): the hits of seed x are, for each variant of x in generate_variants order
+    (variants.cc:402-428), the table entries equal to that variant with equal V and J (unless -g)
+    and index != x (:105); for d > 2, all other sequences within Hamming distance d in index order
+    (process_trad, :147-196).  clustering (:277-300, 356-407): breadth-first from every still
+    unclustered seed in index order, a cluster's members chained in the order they are reached;
+    clusters sorted by decreasing size (:41-55, 411; glibc qsort = stable merge sort).
+    -> (order, cluster_no (1-based), cluster_size) per output row, n_clusters, n_edges"""
+    n = s.n
+    seqs = [_seq(s, i) for i in range(n)]
+    vj = [(0, 0) if ignore_genes else (int(s.v_gene[i]), int(s.j_gene[i])) for i in range(n)]
+    network = []
+    if differences <= 2:
+        table = {}
+        for i in range(n):
+            table.setdefault((seqs[i], vj[i]), []).append(i)
+        cache = {}
+        for x in range(n):
+            if seqs[x] not in cache:
+                cache[seqs[x]] = _variant_bytes(np.frombuffer(seqs[x], np.uint8), s.sigma, differences, indels)
+            hits = []
+            for v in cache[seqs[x]]:
+                hits.extend(h for h in table.get((v, vj[x]), ()) if h != x)
+            network.append(hits)
+    else:
+        arr = [np.frombuffer(q, np.uint8) for q in seqs]
+        for x in range(n):
+            network.append([h for h in range(n) if h != x and vj[h] == vj[x] and len(seqs[h]) == len(seqs[x])
+                            and int(np.count_nonzero(arr[h] != arr[x])) <= differences])
+    cid = [-1] * n
+    clusters = []
+    for seed in range(n):
+        if cid[seed] >= 0:
+            continue
+        members = [seed]
+        cid[seed] = len(clusters)
+        k = 0
+        while k < len(members):
+            for h in network[members[k]]:
+                if cid[h] < 0:
+                    cid[h] = len(clusters)
+                    members.append(h)
+            k += 1
+        clusters.append(members)
+    clusters.sort(key=lambda m: -len(m))     # list.sort is stable
+    order = np.array([i for m in clusters for i in m], dtype=np.uint32)
+    no = np.array([k + 1 for k, m in enumerate(clusters) for _ in m], dtype=np.uint32)
+    size = np.array([len(m) for m in clusters for _ in m], dtype=np.uint32)
+    return order, no, size, len(clusters), sum(len(h) for h in network)
 
 
 # ---- the unmodified reference binary ---------------------------------------------------------

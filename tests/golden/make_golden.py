@@ -94,5 +94,38 @@ def main():
     print(len(cases), "cases written")
 
 
+def main_cz():
+    """tests/golden/golden_cz.json: `-c` (cluster) and `-z` (deduplicate) outputs of the reference
+    binary.  Both commands take ONE file and print rows in an order the algorithm defines
+    (src/cluster.cc:356-446, src/dedup.cc:185-190), so the whole output is compared byte for byte."""
+    assert orc.have_reference(), "build oracle/_ref/compairr first (make -C oracle ref)"
+    synth.small_dense_set(106, 2, 150, alphabet="ACDEFGHIK", min_len=3, max_len=6).write_tsv(os.path.join(HERE, "syn_c.tsv"), id_prefix="c")
+    synth.small_dense_set(107, 3, 120, alphabet="ACGT", min_len=4, max_len=7, nucleotides=True).write_tsv(os.path.join(HERE, "syn_nc.tsv"), id_prefix="n")
+    cases = []
+
+    def add(name, args, file):
+        out = os.path.join("/tmp", "golden_out.tsv")
+        log = os.path.join("/tmp", "golden_log.txt")
+        r = orc.run_reference(list(args) + [os.path.join(HERE, file), "-o", out, "-l", log])
+        assert r.returncode == 0, (name, r.stderr)
+        keep = [ln for ln in open(log).read().splitlines() if ln.startswith(("Clusters:", "Duplicates merged:"))]
+        cases.append({"name": name, "args": list(args), "file": file, "output": open(out).read(), "log": keep})
+
+    for f, nt in (("syn_a.tsv", []), ("syn_b.tsv", []), ("syn_c.tsv", []), ("ref_setb.tsv", []), ("syn_nc.tsv", ["-n"])):
+        tag = f.split(".")[0]
+        for d, extra in [("0", []), ("1", []), ("1", ["-i"]), ("2", []), ("3", [])]:
+            for g in ([], ["-g"]):
+                add(f"c_{tag}_d{d}{'_i' if extra else ''}{'_g' if g else ''}", ["-c", "-d", d] + extra + g + nt, f)
+        for opt in ([], ["-g"], ["-f"], ["-g", "-f"]):
+            add(f"z_{tag}{''.join('_' + o[1] for o in opt)}", ["-z"] + opt + nt, f)
+    add("c_syn_c_d1_t3", ["-c", "-d", "1", "-t", "3"], "syn_c.tsv")
+    with open(os.path.join(HERE, "golden_cz.json"), "w") as f:
+        json.dump({"reference": "CompAIRR 1.13.0 (oracle/_ref/compairr)", "cases": cases}, f, indent=1)
+    print(len(cases), "cluster / dedup cases written")
+
+
 if __name__ == "__main__":
-    main()
+    if sys.argv[1:] == ["cz"]:
+        main_cz()
+    else:
+        main()

@@ -120,3 +120,44 @@ def test_live_differential_vs_reference(tmp_path, seed, args):
     a2, b2 = read_airr_pair(str(fa), str(fb))
     m, _, _ = orc.overlap(a2, b2, **hot_opts(o))
     assert_matrix_text(report.format_matrix(m, a2, b2, o["score"]), out.read_text(), exact=is_integer_score(o))
+
+
+# ---- `-c` / `-z`: the restatements of src/cluster.cc and src/dedup.cc against the reference's files ----
+
+def _cz_cases():
+    import json
+    with open(os.path.join(GOLDEN_DIR, "golden_cz.json")) as f:
+        return json.load(f)["cases"]
+
+
+CZ = _cz_cases()
+
+
+def _cz_opts(args):
+    o = dict(differences=0, indels=False, ignore_genes=False, ignore_counts=False, nucleotides=False)
+    it = iter(args)
+    for a in it:
+        if a == "-d":
+            o["differences"] = int(next(it))
+        elif a == "-t":
+            next(it)
+        else:
+            o[{"-i": "indels", "-g": "ignore_genes", "-f": "ignore_counts", "-n": "nucleotides"}.get(a, "_")] = True
+    o.pop("_", None)
+    return o
+
+
+@pytest.mark.parametrize("case", CZ, ids=[c["name"] for c in CZ])
+def test_cluster_and_dedup_oracle_match_reference_files(case):
+    from compairr_b200 import report
+    from compairr_b200.seqset import read_airr_pair
+    o = _cz_opts(case["args"])
+    s, _ = read_airr_pair(os.path.join(GOLDEN_DIR, case["file"]), None, o["nucleotides"])
+    if case["args"][0] == "-c":
+        order, no, size, ncl, _ = orc.cluster(s, o["differences"], o["indels"], o["ignore_genes"])
+        assert report.format_clusters(order, no, size, s) == case["output"]
+        assert case["log"] == [f"Clusters:          {ncl}"]
+    else:
+        lead, cnt, merged = orc.dedup(s, o["ignore_genes"], o["ignore_counts"])
+        assert report.format_dedup(lead, cnt, s, o["ignore_genes"]) == case["output"]
+        assert case["log"] == [f"Duplicates merged: {merged}"]
