@@ -4,12 +4,17 @@
 
 #include <string.h>
 
+#include <stdlib.h>
+
 #include <algorithm>
+#include <chrono>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "airr_tsv.h"
 #include "compairr_b200.h"
+#include "row_writer.h"
 
 namespace {
 
@@ -26,9 +31,37 @@ struct OneSet {
   fatal(msg.c_str());
 }
 
-// db_read(d, filename, false, "1") + upload (both commands read one set, sequence ids optional)
+// COMPAIRR_B200_TRACE=1: wall-clock marks on stderr (as in overlap_cmd.cpp)
+const auto g_t0 = std::chrono::steady_clock::now();
+void mark(const char* what) {
+  static const bool trace = getenv("COMPAIRR_B200_TRACE") != nullptr;
+  if (trace)
+    fprintf(stderr, "[trace] %8.3f s  %s\n",
+            std::chrono::duration<double>(std::chrono::steady_clock::now() - g_t0).count(), what);
+}
+
+// db_read(d, filename, false, "1") + upload (both commands read one set, sequence ids optional).
+// The CUDA context comes up on another thread while the host parses (a throw-away engine
+// context leaves the device's primary context initialised).
 void load(const Options& o, OneSet& s, bool want_ids) {
+  std::thread warm([&] {
+    cb_config w{};
+    w.abi_version = CB_ABI_VERSION;
+    w.device = o.device;
+    w.alphabet_size = o.alphabet_size;
+    w.n_reps_a = 1;
+    w.no_matrix = 1;
+    cb_ctx* c = nullptr;
+    if (cb_create(&w, &c) == 0) cb_destroy(c);
+  });
+  struct Joiner {
+    std::thread& t;
+    ~Joiner() { if (t.joinable()) t.join(); }
+  } guard{warm};
   read_airr_tsv(o.input1, o, false, want_ids, "1", s.genes, s.db);
+  mark("set read");
+  warm.join();
+  mark("warm-up joined");
   cb_config cfg{};
   cfg.abi_version = CB_ABI_VERSION;
   cfg.device = o.device;
@@ -52,23 +85,22 @@ void load(const Options& o, OneSet& s, bool want_ids) {
   h.count = s.db.count.data();
   h.n_reps = (uint32_t)s.db.rep_names.size();
   if (cb_upload(s.ctx, &h, &s.dev)) engine_fatal(s.ctx);
+  mark("set uploaded + hashed");
 }
 
+// The engine is not torn down: main() leaves with _exit() once the files are on disk, and
+// destroying a context with multi-GB pools takes longer (0.2 - 0.6 s measured) than anything the
+// operating system does to reclaim it.
 void unload(OneSet& s) {
-  cb_free_set(s.ctx, s.dev);
-  cb_destroy(s.ctx);
+  if (getenv("COMPAIRR_B200_TEARDOWN")) {
+    cb_free_set(s.ctx, s.dev);
+    cb_destroy(s.ctx);
+  }
 }
 
 void append_sequence(std::string& buf, const Options& o, const SeqDb& d, uint64_t i) {
   const char* alpha = o.nucleotides ? "acgt" : "ACDEFGHIKLMNPQRSTVWY";  // db.cc:73-74
   for (uint64_t p = d.offsets[i]; p < d.offsets[i + 1]; p++) buf += alpha[d.residues[p]];
-}
-
-void flush_if_big(std::string& buf, FILE* f, bool force = false) {
-  if (buf.size() > (1u << 20) || (force && !buf.empty())) {
-    fwrite(buf.data(), 1, buf.size(), f);
-    buf.clear();
-  }
 }
 
 void log_gene_counts(const GeneTables& g) {
@@ -97,6 +129,7 @@ void cluster_command(const Options& o, FILE* outfile) {
   progress_begin(o, "Building network: ");
   if (cb_cluster(s.ctx, s.dev, order.data(), no.data(), size.data(), &clusters, nullptr)) engine_fatal(s.ctx);
   progress_end(o, "Building network: ");
+  mark("clusters computed");
   progress_begin(o, "Clustering:       ");  // done inside cb_cluster, as is the size sort
   progress_end(o, "Clustering:       ");
   progress_begin(o, "Sorting clusters: ");
@@ -106,29 +139,29 @@ void cluster_command(const Options& o, FILE* outfile) {
   progress_begin(o, "Writing clusters: ");
   fprintf(outfile, "#cluster_no\tcluster_size\trepertoire_id\tsequence_id\tduplicate_count\tv_call\tj_call\t%s\n",
           o.seq_header);
-  std::string buf;
-  for (uint64_t k = 0; k < n; k++) {
-    const uint64_t a = order[k];
-    buf += std::to_string(no[k]);
-    buf += '\t';
-    buf += std::to_string(size[k]);
-    buf += '\t';
-    buf += d.rep_names[d.rep[a]];
-    buf += '\t';
-    if (d.has_ids()) buf += d.seq_id(a);
-    buf += '\t';
-    buf += std::to_string(d.count[a]);
-    buf += '\t';
-    buf += s.genes.v_names[d.v[a]];
-    buf += '\t';
-    buf += s.genes.j_names[d.j[a]];
-    buf += '\t';
-    append_sequence(buf, o, d, a);
-    buf += '\n';
-    flush_if_big(buf, outfile);
-  }
-  flush_if_big(buf, outfile, true);
+  write_rows_parallel(outfile, n, (int)o.threads, [&](uint64_t k0, uint64_t k1, std::string& buf) {
+    for (uint64_t k = k0; k < k1; k++) {
+      const uint64_t a = order[k];
+      append_u64(buf, no[k]);
+      buf += '\t';
+      append_u64(buf, size[k]);
+      buf += '\t';
+      buf += d.rep_names[d.rep[a]];
+      buf += '\t';
+      if (d.has_ids()) buf += d.seq_id(a);
+      buf += '\t';
+      append_u64(buf, d.count[a]);
+      buf += '\t';
+      buf += s.genes.v_names[d.v[a]];
+      buf += '\t';
+      buf += s.genes.j_names[d.j[a]];
+      buf += '\t';
+      append_sequence(buf, o, d, a);
+      buf += '\n';
+    }
+  });
   progress_end(o, "Writing clusters: ");
+  mark("clusters written");
   fprintf(g_log, "\n");
   fprintf(g_log, "Clusters:          %u\n", (unsigned)clusters);
 }
@@ -150,28 +183,29 @@ void dedup_command(const Options& o, FILE* outfile) {
   progress_begin(o, "Deduplicating:    ");
   if (cb_dedup(s.ctx, s.dev, leader.data(), count.data(), &merged)) engine_fatal(s.ctx);
   progress_end(o, "Deduplicating:    ");
+  mark("groups computed");
   unload(s);
   fprintf(g_log, "Duplicates merged: %lu\n", (unsigned long)merged);
 
   progress_begin(o, "Writing output:   ");
-  std::string buf;
-  for (uint64_t i = 0; i < n; i++) {
-    if (leader[i] != i) continue;
-    buf += d.rep_names[d.rep[i]];
-    buf += '\t';
-    buf += std::to_string(count[i]);
-    if (!o.ignore_genes) {
+  write_rows_parallel(outfile, n, (int)o.threads, [&](uint64_t i0, uint64_t i1, std::string& buf) {
+    for (uint64_t i = i0; i < i1; i++) {
+      if (leader[i] != i) continue;  // a group is reported once, at its first member
+      buf += d.rep_names[d.rep[i]];
       buf += '\t';
-      buf += s.genes.v_names[d.v[i]];
+      append_u64(buf, count[i]);
+      if (!o.ignore_genes) {
+        buf += '\t';
+        buf += s.genes.v_names[d.v[i]];
+        buf += '\t';
+        buf += s.genes.j_names[d.j[i]];
+      }
       buf += '\t';
-      buf += s.genes.j_names[d.j[i]];
+      append_sequence(buf, o, d, i);
+      buf += '\n';
     }
-    buf += '\t';
-    append_sequence(buf, o, d, i);
-    buf += '\n';
-    flush_if_big(buf, outfile);
-  }
-  flush_if_big(buf, outfile, true);
+  });
   progress_end(o, "Writing output:   ");
+  mark("output written");
   fprintf(g_log, "\n");
 }

@@ -14,6 +14,7 @@
 
 #include "airr_tsv.h"
 #include "compairr_b200.h"
+#include "row_writer.h"
 
 namespace {
 
@@ -94,7 +95,6 @@ struct PairWriter {
   const SeqDb &d1, &d2;
   const GeneTables& g;
   FILE* f;
-  std::string buf;
 
   void header() {
     fprintf(f, "#repertoire_id_1\tsequence_id_1\tduplicate_count_1\tv_call_1\tj_call_1\t%s_1", o.seq_header);
@@ -104,13 +104,13 @@ struct PairWriter {
     if (o.distance) fprintf(f, "\tdistance");
     fprintf(f, "\n");
   }
-  void side(const SeqDb& d, uint64_t i) {
+  void side(std::string& buf, const SeqDb& d, uint64_t i) const {
     const char* alpha = o.nucleotides ? "acgt" : "ACDEFGHIKLMNPQRSTVWY";  // db.cc:73-74
     buf += d.rep_names[d.rep[i]];
     buf += '\t';
     if (d.has_ids()) buf += d.seq_id(i);
     buf += '\t';
-    buf += std::to_string(d.count[i]);
+    append_u64(buf, d.count[i]);
     buf += '\t';
     buf += g.v_names[d.v[i]];
     buf += '\t';
@@ -122,27 +122,24 @@ struct PairWriter {
       buf += d.keep(i);
     }
   }
-  void write(const cb_pair* p, size_t n) {
-    for (size_t k = 0; k < n; k++) {
-      const uint64_t a = p[k].a, b = p[k].b;
-      side(d1, a);
-      buf += '\t';
-      side(d2, b);
-      if (o.distance) {  // Hamming if equal length, else 1 (one indel), overlap.cc:492-502
-        const int64_t l1 = (int64_t)(d1.offsets[a + 1] - d1.offsets[a]), l2 = (int64_t)(d2.offsets[b + 1] - d2.offsets[b]);
-        int64_t dist = 1;
-        if (l1 == l2) dist = hamming(d1.residues.data() + d1.offsets[a], d2.residues.data() + d2.offsets[b], l1);
+  // rows formatted on o.threads host threads, written in the order of p[] (row_writer.h)
+  void write(const cb_pair* p, size_t n) const {
+    write_rows_parallel(f, n, (int)o.threads, [&](uint64_t k0, uint64_t k1, std::string& buf) {
+      for (uint64_t k = k0; k < k1; k++) {
+        const uint64_t a = p[k].a, b = p[k].b;
+        side(buf, d1, a);
         buf += '\t';
-        buf += std::to_string(dist);
+        side(buf, d2, b);
+        if (o.distance) {  // Hamming if equal length, else 1 (one indel), overlap.cc:492-502
+          const int64_t l1 = (int64_t)(d1.offsets[a + 1] - d1.offsets[a]), l2 = (int64_t)(d2.offsets[b + 1] - d2.offsets[b]);
+          int64_t dist = 1;
+          if (l1 == l2) dist = hamming(d1.residues.data() + d1.offsets[a], d2.residues.data() + d2.offsets[b], l1);
+          buf += '\t';
+          append_u64(buf, (uint64_t)dist);
+        }
+        buf += '\n';
       }
-      buf += '\n';
-      if (buf.size() > (1u << 20)) flush();
-    }
-    flush();
-  }
-  void flush() {
-    if (!buf.empty()) fwrite(buf.data(), 1, buf.size(), f);
-    buf.clear();
+    }, 1u << 13);
   }
 };
 
@@ -256,13 +253,16 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
   }
   progress_end(o, "Hashing sequences:");
   mark("set B uploaded + built");
+  cb_dset* whole_a_dev = nullptr;  // set 1 on GPU 0, kept for the analysis when GPU 0 takes all of it
   if (o.differences <= 2) {
     if (two_sets) {  // duplicates in set 1 are only checked with two distinct sets (overlap.cc:846-852)
       const cb_set whole_a = as_cb_set(d1, 0, N1);
-      cb_dset* da = nullptr;
       uint64_t dup1 = 0;
-      if (cb_upload(ctx[0], &whole_a, &da) || cb_count_dups(ctx[0], da, &dup1)) engine_fatal(ctx[0]);
-      cb_free_set(ctx[0], da);
+      if (cb_upload(ctx[0], &whole_a, &whole_a_dev) || cb_count_dups(ctx[0], whole_a_dev, &dup1)) engine_fatal(ctx[0]);
+      if (ngpu > 1) {
+        cb_free_set(ctx[0], whole_a_dev);
+        whole_a_dev = nullptr;
+      }
       if (dup1) fprintf(g_log, "Warning: %lu duplicates detected in repertoire set 1\n", (unsigned long)dup1);
     }
     const uint64_t dup2 = cb_dups_b(ctx[0]);
@@ -274,7 +274,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
   std::vector<double> matrix;
   const uint64_t rows = o.existence ? N1 : R1;
   if (!o.no_matrix) matrix.assign(rows * R2, 0.0);
-  PairWriter pw{o, d1, d2, genes, pairsfile, {}};
+  PairWriter pw{o, d1, d2, genes, pairsfile};
   if (o.pairs) pw.header();
 
   progress_begin(o, "Analysing:        ");
@@ -301,8 +301,11 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
         const bool self_dev = !two_sets;  // set A is the resident set B
         cb_dset* da = nullptr;
         if (bound[g + 1] == bound[g]) return;
+        const bool reuse = whole_a_dev != nullptr;  // one GPU: the dup check left set 1 resident
         if (self_dev) {
           da = dev_b[g];
+        } else if (reuse) {
+          da = whole_a_dev;
         } else {
           const cb_set shard = as_cb_set(d1, bound[g], bound[g + 1] - bound[g]);
           if (cb_upload(c, &shard, &da)) { errors[g] = cb_last_error(c); return; }
@@ -327,7 +330,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
             }
           }
         }
-        if (!self_dev) cb_free_set(c, da);
+        if (!self_dev && !reuse) cb_free_set(c, da);
       });
     for (auto& t : th) t.join();
   }
@@ -348,11 +351,17 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
     for (int g = 0; g < ngpu; g++) pw.write(pair_out[g].data(), pair_out[g].size());
   progress_end(o, "Analysing:        ");
   mark("analysis done");
-  for (int g = 0; g < ngpu; g++) {
-    cb_free_set(ctx[g], dev_b[g]);
-    cb_destroy(ctx[g]);
+  // The engines are not torn down: main() leaves with _exit() once the files are on disk, and
+  // destroying contexts with multi-GB pools took 0.5 s (measured) for nothing the operating system
+  // does not reclaim anyway.
+  if (getenv("COMPAIRR_B200_TEARDOWN")) {
+    for (int g = 0; g < ngpu; g++) {
+      if (g == 0 && whole_a_dev) cb_free_set(ctx[0], whole_a_dev);
+      cb_free_set(ctx[g], dev_b[g]);
+      cb_destroy(ctx[g]);
+    }
+    mark("contexts destroyed");
   }
-  mark("contexts destroyed");
 
   // ---- results (overlap.cc:540-577, 944-1039) ---------------------------------------------------
   auto value = [&](uint64_t s, unsigned t) -> double {
