@@ -101,9 +101,26 @@ CB_HD uint64_t splitmix64(uint64_t x) {
 // Zobrist value of residue r at position p.  A pure function of (seed, p, r) so the table can be
 // extended to longer sequences without invalidating hashes already computed (the reference draws
 // from glibc random(), zobrist.cc:52-63; results do not depend on the values).
+//
+// The values are STRUCTURED by the parity of the position (32 random bits x each):
+//     even p:  [ x : 0 ]      odd p:  [ x : x ]       (high half : low half)
+// so that, h being the XOR of the values of a sequence (and of a 64-bit V/J term),
+//     O(h) = low half               changes only when an ODD  position changes,
+//     E(h) = high half ^ low half   changes only when an EVEN position changes,
+// while the high half itself (home slot, partition order) depends on every position.  All the
+// single-residue variants of a seed at odd positions therefore share E, those at even positions
+// share O — which is what lets ONE filter word answer for all of them (parity filters below).
+// Two different sequences still collide with probability 2^-32 at worst (they differ in E or in
+// O); every hash match is verified on the residues anyway.
 CB_HD uint64_t zobrist_gen(uint64_t seed, uint32_t p, uint32_t r) {
-  return splitmix64(splitmix64(seed ^ 0x5A0B1157ull) + ((uint64_t)p << 8) + r);
+  const uint64_t x = splitmix64(splitmix64(seed ^ 0x5A0B1157ull) + ((uint64_t)p << 8) + r) >> 32;
+  return (p & 1u) ? ((x << 32) | x) : (x << 32);
 }
+CB_HD uint32_t field_odd(uint64_t h) { return (uint32_t)h; }
+CB_HD uint32_t field_even(uint64_t h) { return (uint32_t)(h >> 32) ^ (uint32_t)h; }
+// 32 bits of the hash that depend on every position, for the "possibly the same sequence" tag of
+// a table slot (the low half alone is blind to even positions, the high half repeats the home slot).
+CB_HD uint32_t slot_tag(uint64_t h) { return (uint32_t)(h >> 32) * 0x9E3779B1u ^ (uint32_t)h; }
 
 // Contribution of the (V gene, J gene) pair: zobrist_v_base[v] ^ zobrist_d_base[j] in the
 // reference (zobrist.cc:83-84).  Computed, not tabulated, so no table sized by #V + #J.
@@ -124,10 +141,27 @@ CB_HD uint64_t table_home(uint64_t h, uint64_t mask) {
 }
 constexpr int CB_PARTITION_TOP_BIT = 62;  // partition keys are hash bits [62 - p, 62)
 
-// Bloom: one 64-bit block per key; block chosen by multiply-shift range reduction over bits
-// 30..61 (any block count, not only powers of two), pattern = 3 bits in each 32-bit half taken
-// from the low 30 hash bits.  Normal polarity (1 = present); the reference's is inverted
-// (bloompat.h:50-58), which is an implementation detail.
+// Parity filters (replace bloom_s, bloompat.h:26-58): TWO blocked Bloom filters of `nblocks`
+// 64-bit words each, laid out back to back; every set-B key is in both.
+//     filter E (words [0, nblocks)):        word picked by E(h), 3 + 3 bits picked by O(h)
+//     filter O (words [nblocks, 2 nblocks)): word picked by O(h), 3 + 3 bits picked by E(h)
+// A variant may be looked up in either (no false negatives in both).  The enumeration kernels use
+// filter E for a variant whose free residue sits at an odd position and filter O for an even one:
+// the 19 (or 20) variants at that position — and those at every other position of the same
+// parity — then read the SAME word, so a warp's 32 lookups coalesce into one or two sectors that
+// stay in L1 instead of 32 random L2 sectors.  Word choice by multiply-shift (any word count);
+// normal polarity (1 = present; the reference's is inverted, an implementation detail).
+CB_HD uint32_t mulhi32(uint32_t x, uint32_t n) {
+#if defined(__CUDA_ARCH__)
+  return __umulhi(x, n);
+#else
+  return (uint32_t)(((uint64_t)x * n) >> 32);
+#endif
+}
+// word index of h in the filter serving a free position of the given parity
+CB_HD uint64_t pfilter_word(uint64_t h, uint32_t nblocks, bool odd_free) {
+  return odd_free ? (uint64_t)mulhi32(field_even(h), nblocks) : (uint64_t)nblocks + mulhi32(field_odd(h), nblocks);
+}
 CB_HD uint32_t bloom_block(uint64_t h, uint32_t nblocks) {
   uint32_t x = (uint32_t)(h >> 30);
 #if defined(__CUDA_ARCH__)
@@ -152,6 +186,10 @@ CB_HD uint64_t bloom1_pattern(uint64_t h) {
 }
 CB_HD uint64_t bloom_pattern(uint64_t h) {
   return (uint64_t)bloom_pat_lo(h) | ((uint64_t)bloom_pat_hi(h) << 32);
+}
+// bit pattern of h in the same filter: from the field the word index does not use
+CB_HD uint64_t pfilter_pattern(uint64_t h, bool odd_free) {
+  return bloom_pattern(odd_free ? field_odd(h) : field_even(h));
 }
 
 // ---- score summand (overlap.cc:144-166) ---------------------------------------------------------

@@ -54,17 +54,17 @@ __device__ __forceinline__ bool seq_equal(const uint8_t* __restrict__ res, uint6
   return diff == 0;
 }
 
-// Filter word test.  K2 = true: 1 bit per 32-bit half (the low-bits-per-key geometry of a
-// first-level filter capped to stay L2-resident), else 3 + 3 bits.
-__device__ __forceinline__ bool bloom_word_test(unsigned long long w, uint64_t h, bool k2) {
-  const uint32_t plo = k2 ? bloom1_pat_lo(h) : bloom_pat_lo(h);
-  const uint32_t phi = k2 ? bloom1_pat_hi(h) : bloom_pat_hi(h);
+// Parity-filter lookup of hash h (common.cuh): word from the filter that serves a free position of
+// the given parity, 3 + 3 bits from the field that word index does not use.
+__device__ __forceinline__ bool pfilter_word_test(unsigned long long w, uint64_t h, bool odd_free) {
+  const uint32_t f = odd_free ? field_odd(h) : field_even(h);
+  const uint32_t plo = bloom_pat_lo(f), phi = bloom_pat_hi(f);
   return (((uint32_t)w & plo) == plo) & (((uint32_t)(w >> 32) & phi) == phi);
 }
 
-__device__ __forceinline__ bool bloom_test(const unsigned long long* __restrict__ bloom,
-                                           uint32_t nblocks, uint64_t h, bool k2) {
-  return bloom_word_test(__ldg(bloom + bloom_block(h, nblocks)), h, k2);
+__device__ __forceinline__ bool pfilter_test(const unsigned long long* __restrict__ bloom,
+                                             uint32_t nblocks, uint64_t h, bool odd_free) {
+  return pfilter_word_test(__ldg(bloom + pfilter_word(h, nblocks, odd_free)), h, odd_free);
 }
 
 // Variant descriptor in 31 bits: kind(3) | res1(5) | res2(5) | pos1(9) | pos2(9).  Positions up to

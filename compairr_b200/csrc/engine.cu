@@ -226,7 +226,6 @@ extern "C" void cb_destroy(cb_ctx* c) {
   if (c->h_counters) cudaFreeHost(c->h_counters);
   cb_dfree(c->d_table);
   cb_dfree(c->d_bloom);
-  cb_dfree(c->d_bloom2);
   if (!c->matrix_external) cb_dfree(c->d_matrix);
   cb_dfree(c->d_pairs);
   cb_dfree(c->d_gq_hv);
@@ -306,45 +305,32 @@ static uint32_t blocks_for_bits(unsigned __int128 bits) {
   return (uint32_t)nb;
 }
 
-// Table + Bloom filter(s) sized for n keys.  Filter policy (measured on B200): a Bloom
-// filter probed at random is L2-resident up to ~48 MiB; beyond that every probe is a 64-byte DRAM
-// access.  So the filter the enumeration loop tests is capped (default 40 MiB); when the cap
-// leaves fewer than 8 bits per key it switches to a 1+1-bit geometry and a second, full-size
-// filter in HBM is tested only by the first level's survivors.
+// Table + the two parity filters (common.cuh) sized for n keys: bloom_bits_per_key bits per key in
+// EACH filter.  Their size no longer has to fit L2: a warp's lookups fall into one or two words per
+// step, not 32 random ones, so the filters are read a few dozen sectors per seed.  (Until the
+// parity filters a single filter was capped to stay L2-resident and backed by a second level in
+// HBM; cfg.bloom_l2_cap_kib is accepted and ignored.)
 int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
   BuiltTable t;
   t.slots = 8;
   while (t.slots * c->cfg.table_load_pct < n * 100) t.slots <<= 1;
   const unsigned __int128 want_bits = (unsigned __int128)n * c->cfg.bloom_bits_per_key_x16 / 16;
-  const uint64_t cap_bytes = (uint64_t)c->cfg.bloom_l2_cap_kib << 10;
-  if (!with_bloom) {
-    t.blocks = 16;  // the build kernel always sets a filter; give it a scratch one
-  } else if ((uint64_t)((want_bits + 7) / 8) <= cap_bytes) {
-    t.blocks = blocks_for_bits(want_bits);
-  } else {
-    t.blocks = (uint32_t)(cap_bytes / 8);
-    t.k2 = (double)cap_bytes * 8.0 / (double)n < 8.0;
-    t.blocks2 = blocks_for_bits(t.k2 ? (unsigned __int128)n * 12 : want_bits);
-  }
+  t.blocks = with_bloom ? blocks_for_bits(want_bits) : 16;  // the build kernel always sets the filters; scratch ones if unused
   cudaError_t e = cudaSuccess;
-  if (with_bloom && c->d_table && c->slots == t.slots && c->bloom_blocks == t.blocks &&
-      c->bloom2_blocks == t.blocks2) {
+  if (with_bloom && c->d_table && c->slots == t.slots && c->bloom_blocks == t.blocks) {
     // rebuilding a set-B structure of the same geometry: clear and refill the buffers in place
     // instead of growing the memory pool by another table
     t.table = c->d_table;
     t.bloom = c->d_bloom;
-    t.bloom2 = c->d_bloom2;
     c->d_table = nullptr;
-    c->d_bloom = c->d_bloom2 = nullptr;
+    c->d_bloom = nullptr;
     c->slots = 0;
-    c->bloom_blocks = c->bloom2_blocks = 0;
+    c->bloom_blocks = 0;
   } else {
     e = cb_dmalloc(&t.table, t.slots * sizeof(Slot));
-    if (e == cudaSuccess && t.blocks2) e = cb_dmalloc(&t.bloom2, (size_t)t.blocks2 * 8);
-    if (e == cudaSuccess) e = cb_dmalloc(&t.bloom, (size_t)t.blocks * 8);
+    if (e == cudaSuccess) e = cb_dmalloc(&t.bloom, (size_t)t.blocks * 16);
   }
-  if (e == cudaSuccess && t.bloom2) e = cudaMemsetAsync(t.bloom2, 0, (size_t)t.blocks2 * 8, c->stream);
-  if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom, 0, (size_t)t.blocks * 8, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom, 0, (size_t)t.blocks * 16, c->stream);
   if (e == cudaSuccess) {
     launch_table_clear(t.table, t.slots, c->stream);
     e = cudaGetLastError();
@@ -402,7 +388,7 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
     }
   }
   launch_build(s->d_meta, s->d_res, s->d_hash, part_hash, part_idx, first, n, c->cfg.ignore_genes != 0, t.table,
-               t.slots - 1, t.bloom, t.blocks, t.k2, t.bloom2, t.blocks2, c->stream);
+               t.slots - 1, t.bloom, t.blocks, c->stream);
   cb_dfree(part_hash);
   cb_dfree(iota);
   cb_dfree(part_idx);
@@ -429,27 +415,11 @@ int cb_adopt_table(cb_ctx* c, cb_dset* b, BuiltTable& t, bool owned) {
   c->b_owned = owned;
   cb_dfree(c->d_table);
   cb_dfree(c->d_bloom);
-  cb_dfree(c->d_bloom2);
   c->d_table = t.table;
   c->slots = t.slots;
   c->d_bloom = t.bloom;
   c->bloom_blocks = t.blocks;
-  c->bloom_k2 = t.k2;
-  c->d_bloom2 = t.bloom2;
-  c->bloom2_blocks = t.blocks2;
   t = BuiltTable();
-  // Persisting-L2 carve-out only while a two-level filter is live: it is taken away from normal
-  // accesses, which hurts the single-filter (L2-resident) case.
-  if (c->l2_persist_max > 0) {
-    const size_t want = c->d_bloom2 ? std::min<size_t>(c->l2_persist_max, (size_t)c->bloom_blocks * 8) : 0;
-    if (want != c->l2_persist_set) {
-      if (want == 0) cudaCtxResetPersistingL2Cache();
-      if (cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, want) == cudaSuccess)
-        c->l2_persist_set = want;
-      else
-        cudaGetLastError();
-    }
-  }
   c->dups_b = 0;
   c->stats.ms_dups_b = 0;
   if (!c->d_table) return CB_OK;
@@ -464,8 +434,8 @@ int cb_adopt_table(cb_ctx* c, cb_dset* b, BuiltTable& t, bool owned) {
   c->dups_b = c->h_counters[CTR_DUPS];
   cudaEventElapsedTime(&c->stats.ms_dups_b, c->ev[1], c->ev[2]);
   c->stats.table_slots = c->slots;
-  c->stats.bloom_bytes = (uint64_t)c->bloom_blocks * 8;
-  c->stats.bloom2_bytes = (uint64_t)c->bloom2_blocks * 8;
+  c->stats.bloom_bytes = (uint64_t)c->bloom_blocks * 8;   // filter E
+  c->stats.bloom2_bytes = (uint64_t)c->bloom_blocks * 8;  // filter O
   return CB_OK;
 }
 
@@ -731,9 +701,6 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     p.table_mask = c->slots - 1;
     p.bloom = c->d_bloom;
     p.bloom_blocks = c->bloom_blocks;
-    p.bloom_k2 = c->bloom_k2;
-    p.bloom2 = c->d_bloom2;
-    p.bloom2_blocks = c->bloom2_blocks;
     p.ztab = c->d_ztab;
     p.zrows = a->longest + 2;
     p.sigma = (uint32_t)c->cfg.alphabet_size;
@@ -758,26 +725,7 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     p.count_bloom = 1;
     p.differences = c->cfg.differences;
     p.indels = c->cfg.indels != 0;
-    // Keep the first-level Bloom filter resident in L2 while the probe kernels run: every probe
-    // reads it, everything else they touch (second-level filter, table, metadata) is touched
-    // once.  Persisting-L2 access window over the filter, streaming for the rest.
-    bool window = false;
-    if (c->d_bloom2 && c->l2_persist_set > 0 && !getenv("CB_NO_L2_WINDOW")) {
-      cudaStreamAttrValue av{};
-      av.accessPolicyWindow.base_ptr = c->d_bloom;
-      av.accessPolicyWindow.num_bytes = std::min<size_t>((size_t)c->bloom_blocks * 8, c->l2_window_max);
-      av.accessPolicyWindow.hitRatio = 1.0f;
-      av.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
-      av.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-      window = cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av) == cudaSuccess;
-      if (!window) cudaGetLastError();
-    }
     rc = run_hash_path(c, p, count, &launches);
-    if (window) {
-      cudaStreamAttrValue av{};
-      av.accessPolicyWindow.num_bytes = 0;
-      cudaStreamSetAttribute(c->stream, cudaStreamAttributeAccessPolicyWindow, &av);
-    }
     if (rc) return rc;
   } else {
     rc = cb_run_brute(c, a, first, count, false, &launches);

@@ -39,15 +39,11 @@ cudaError_t cb_dfree(void* p);
 struct BuiltTable {
   cb::Slot* table = nullptr;
   uint64_t slots = 0;
-  unsigned long long* bloom = nullptr;
-  uint32_t blocks = 0;
-  bool k2 = false;
-  unsigned long long* bloom2 = nullptr;
-  uint32_t blocks2 = 0;
+  unsigned long long* bloom = nullptr;  // parity filters E | O back to back, 2 * blocks words
+  uint32_t blocks = 0;                  // 64-bit words per filter
   void release() {
     cb_dfree(table);
     cb_dfree(bloom);
-    cb_dfree(bloom2);
     *this = BuiltTable();
   }
 };
@@ -76,11 +72,8 @@ struct cb_ctx {
   bool b_owned = false;
   cb::Slot* d_table = nullptr;
   uint64_t slots = 0;
-  unsigned long long* d_bloom = nullptr;   // first level (L2-resident)
+  unsigned long long* d_bloom = nullptr;   // parity filters E | O (2 * bloom_blocks words)
   uint32_t bloom_blocks = 0;
-  bool bloom_k2 = false;
-  unsigned long long* d_bloom2 = nullptr;  // second level (HBM), large sets only
-  uint32_t bloom2_blocks = 0;
   uint64_t dups_b = 0;
 
   double* d_matrix = nullptr;

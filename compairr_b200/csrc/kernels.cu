@@ -174,8 +174,7 @@ __global__ void __launch_bounds__(256)
 build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __restrict__ hash,
              const uint64_t* __restrict__ part_hash, const uint32_t* __restrict__ part_idx,
              uint64_t first, uint64_t n, bool ignore_genes, Slot* table, uint64_t mask,
-             unsigned long long* bloom, uint32_t bloom_blocks, bool k2, unsigned long long* bloom2,
-             uint32_t bloom2_blocks) {
+             unsigned long long* bloom, uint32_t bloom_blocks) {
   // part_hash/part_idx: the same keys sorted by their top hash bits (position t holds sequence
   // first + part_idx[t]); the grid then sweeps the table and the filters in address order.
   // Both loops have warp-uniform trip counts and the probe loop is voted: lanes that finish early
@@ -189,7 +188,8 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
     bool walking = t < n;
     const uint64_t i = walking ? first + (part_idx ? part_idx[t] : t) : 0;
     const uint64_t h = walking ? (part_hash ? part_hash[t] : hash[i]) : 0;
-    const unsigned long long tagged = (h << 32) | i;  // i < 2^32 - 1 (checked at upload)
+    const uint32_t tag = slot_tag(h);
+    const unsigned long long tagged = ((unsigned long long)tag << 32) | i;  // i < 2^32 - 1 (checked at upload)
     uint64_t slot = table_home(h, mask);
     SeqMeta me;
     bool have_me = false;
@@ -201,12 +201,12 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
           cur = atomicCAS(idxp, SLOT_EMPTY, tagged);
           if (cur == SLOT_EMPTY) {  // we own the slot
             table[slot].hash = h;  // SeqRec.next is SEQ_NIL already (pack kernel / reset_next_kernel)
-            atomicOr(bloom + bloom_block(h, bloom_blocks), k2 ? bloom1_pattern(h) : bloom_pattern(h));
-            if (bloom2) atomicOr(bloom2 + bloom_block(h, bloom2_blocks), bloom_pattern(h));
+            atomicOr(bloom + pfilter_word(h, bloom_blocks, true), pfilter_pattern(h, true));    // filter E
+            atomicOr(bloom + pfilter_word(h, bloom_blocks, false), pfilter_pattern(h, false));  // filter O
             walking = false;
           }
         }
-        if (walking && (uint32_t)(cur >> 32) == (uint32_t)h) {  // same low hash half: compare the sequences
+        if (walking && (uint32_t)(cur >> 32) == tag) {  // same hash tag: compare the sequences
           if (!have_me) {
             me = ld_meta_plain(meta + i);
             have_me = true;
@@ -240,13 +240,11 @@ void launch_reset_next(SeqRec* meta, uint64_t n, cudaStream_t st) {
 
 void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const uint64_t* part_hash,
                   const uint32_t* part_idx, uint64_t first, uint64_t n, bool ignore_genes, Slot* table,
-                  uint64_t mask, unsigned long long* bloom, uint32_t bloom_blocks, bool k2,
-                  unsigned long long* bloom2, uint32_t bloom2_blocks, cudaStream_t st) {
+                  uint64_t mask, unsigned long long* bloom, uint32_t bloom_blocks, cudaStream_t st) {
   if (n == 0) return;
   const uint64_t blocks = (n + 255) / 256;
   build_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
-      meta, res, hash, part_hash, part_idx, first, n, ignore_genes, table, mask, bloom, bloom_blocks, k2, bloom2,
-      bloom2_blocks);
+      meta, res, hash, part_hash, part_idx, first, n, ignore_genes, table, mask, bloom, bloom_blocks);
 }
 
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t* p, uint64_t n) {
@@ -386,8 +384,7 @@ __global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ 
     const uint64_t h = P.a.hash[sidx];
     bool walking = in;
     if (P.use_bloom && in) {
-      walking = bloom_test(P.bloom, P.bloom_blocks, h, P.bloom_k2);
-      if (walking && P.bloom2 != nullptr) walking = bloom_test(P.bloom2, P.bloom2_blocks, h, false);
+      walking = pfilter_test(P.bloom, P.bloom_blocks, h, true);
     }
     npass += walking;
     nmatch += probe_chains(&P, walking, h, pack_var(VK_IDENTICAL, 0, 0, 0, 0), sidx, (uint32_t)i,

@@ -48,10 +48,8 @@ struct ProbeParams {
   uint32_t* overflow_chunks;  // ids of chunks that overflowed the queue (first 64)
   const Slot* table;
   uint64_t table_mask;
-  const unsigned long long* bloom;   // first-level filter (sized to stay L2-resident)
-  uint32_t bloom_blocks;
-  uint32_t bloom2_blocks;
-  const unsigned long long* bloom2;  // second-level filter in HBM, or nullptr
+  const unsigned long long* bloom;   // parity filters E | O back to back (common.cuh)
+  uint32_t bloom_blocks;             // 64-bit words per filter
   const uint64_t* ztab;  // global copy of the Zobrist table, zrows x sigma
   uint32_t zrows;        // rows staged in shared memory by the variant kernel (>= longest A + 1)
   uint32_t sigma;
@@ -70,7 +68,6 @@ struct ProbeParams {
   uint8_t pair_variant;  // network mode (-c): pair.b carries the 31-bit variant descriptor in its high half
   int32_t differences;
   uint8_t indels;
-  uint8_t bloom_k2;    // first-level geometry: 1+1 bits instead of 3+3
 };
 
 // pack one uploaded chunk of columns into SeqMeta records, track the longest sequence
@@ -103,8 +100,7 @@ void launch_reset_next(SeqRec* meta, uint64_t n, cudaStream_t st);
 // sequence first + part_idx[t] with hash part_hash[t].
 void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const uint64_t* part_hash,
                   const uint32_t* part_idx, uint64_t first, uint64_t n, bool ignore_genes, Slot* table,
-                  uint64_t mask, unsigned long long* bloom, uint32_t bloom_blocks, bool k2,
-                  unsigned long long* bloom2, uint32_t bloom2_blocks, cudaStream_t st);
+                  uint64_t mask, unsigned long long* bloom, uint32_t bloom_blocks, cudaStream_t st);
 void launch_iota(uint32_t* p, uint64_t n, cudaStream_t st);
 void launch_count_dups(DeviceSetView s, unsigned long long* counters, cudaStream_t st);
 // -z: lead[i] = first member (file order) of i's (repertoire, V, J, sequence) group, sums[lead] =

@@ -7,13 +7,14 @@
 //
 //   enumerate  every lane decodes VK_U candidates per step from the seed's index spaces and XORs
 //              their hashes together from shared-memory Zobrist values
-//   filter 1   VK_U independent 8-byte loads of the L2-resident Bloom filter per lane
-//   Q1         survivors are compacted (ballot + prefix popcount) into a per-warp ring; when 32
-//              wait, their second-level filter words (HBM) are REQUESTED and the previous batch's
-//              words, requested one stage earlier, are tested — the HBM latency is never waited on
-//   Q2         survivors of filter 2 (or of filter 1 when there is only one level) are compacted
-//              again; 32 at a time they walk their probe chains, and verification + atomics run
-//              re-converged (device_utils.cuh: probe_chains)
+//   filter     VK_U independent 8-byte loads per lane from the PARITY FILTERS (common.cuh): the
+//              filter is chosen by the parity of the candidate's free position, which makes the
+//              word address the same for all candidates at positions of that parity — the 32
+//              loads of a warp step fall into one or two sectors and are served by L1 after the
+//              first touch, instead of 32 random L2 sectors
+//   queue      survivors are compacted (ballot + prefix popcount) into a per-warp ring in shared
+//              memory; 32 at a time they are appended, coalesced, to the global candidate queue
+//              that the table kernel (K4, own launch) drains
 //
 // variant1_kernel (d = 1): warps stage batches of 8 consecutive seeds (metadata, hashes, residues)
 // into shared memory with coalesced loads, so the per-seed dependent global loads are paid once per
@@ -28,59 +29,41 @@ namespace cb {
 
 constexpr int VK_THREADS = 256;
 constexpr int VK_WARPS = VK_THREADS / 32;
-constexpr int VK_QCAP = 64;  // ring entries per queue per warp
-constexpr int VK_U = 4;      // probes per lane per step: 4 independent filter loads in flight per lane (2: -8 %, 8: register-bound, 2x slower)
+constexpr int VK_QCAP = 64;  // ring entries per warp
+constexpr int VK_U = 4;      // probes per lane per step: 4 independent filter loads in flight per lane
 constexpr int VK_WB = 8;     // seeds per warp batch (d = 1)
 
 // Per-warp shared-memory block, addressed from ONE base pointer to keep the register footprint of
-// the enumeration loop small (separate pointers per array pushed the kernels over their 80-register
-// budget and the queue counters into local memory):
-//   [0, 1024)     queue 1: hv[64] u64 | var[64] u32 | seed[64] u32
-//   [1024, 2048)  queue 2: same
-//   [2048, ...)   seed scratch: zo[lpad] (+ pre[lpad], sm[lpad], sp[lpad] with indels), u64 each
+// the enumeration loop small:
+//   [0, 1024)     survivor ring: hv[64] u64 | var[64] u32 | seed[64] u32
+//   [1024, ...)   seed scratch: zo[lpad] (+ pre[lpad], sm[lpad], sp[lpad] with indels), u64 each
 constexpr uint32_t VK_Q_BYTES = VK_QCAP * 16;
-
-struct Ring {  // queue state; the arrays live at wb + which * VK_Q_BYTES
-  uint32_t head, count;
-};
-
-struct Pend {  // one batch of first-level survivors whose second-level words are in flight
-  uint64_t hv;
-  unsigned long long w;
-  uint32_t var, seed;
-  bool valid;
-};
 
 struct WarpCtx {
   unsigned char* wb;  // per-warp block
-  Ring q1, q2;
-  Pend pd;
+  uint32_t head, count;  // ring state
   uint32_t lane;
   uint32_t nmatch, npass;
 };
 
-__device__ __forceinline__ uint64_t* q_hv(unsigned char* wb, int which) {
-  return reinterpret_cast<uint64_t*>(wb + which * VK_Q_BYTES);
-}
-__device__ __forceinline__ uint32_t* q_var(unsigned char* wb, int which) {
-  return reinterpret_cast<uint32_t*>(wb + which * VK_Q_BYTES + VK_QCAP * 8);
-}
-__device__ __forceinline__ uint32_t* q_seed(unsigned char* wb, int which) {
-  return reinterpret_cast<uint32_t*>(wb + which * VK_Q_BYTES + VK_QCAP * 12);
-}
+__device__ __forceinline__ uint64_t* q_hv(unsigned char* wb) { return reinterpret_cast<uint64_t*>(wb); }
+__device__ __forceinline__ uint32_t* q_var(unsigned char* wb) { return reinterpret_cast<uint32_t*>(wb + VK_QCAP * 8); }
+__device__ __forceinline__ uint32_t* q_seed(unsigned char* wb) { return reinterpret_cast<uint32_t*>(wb + VK_QCAP * 12); }
 
-template <int WHICH>
-__device__ __forceinline__ void ring_push(WarpCtx& c, bool pass, uint64_t hv, uint32_t var, uint32_t seed) {
-  Ring& q = WHICH ? c.q2 : c.q1;
+// mkvar() builds the 31-bit variant descriptor; it runs for survivors only (a fraction of a percent
+// of the candidates), so the enumeration loop itself never packs one.  c.npass is warp-uniform.
+template <typename MkVar>
+__device__ __forceinline__ void ring_push(WarpCtx& c, bool pass, uint64_t hv, MkVar mkvar, uint32_t seed) {
   const unsigned m = __ballot_sync(FULL, pass);
   if (m == 0) return;
   if (pass) {
-    const uint32_t e = (q.head + q.count + __popc(m & ((1u << c.lane) - 1))) & (VK_QCAP - 1);
-    q_hv(c.wb, WHICH)[e] = hv;
-    q_var(c.wb, WHICH)[e] = var;
-    q_seed(c.wb, WHICH)[e] = seed;
+    const uint32_t e = (c.head + c.count + __popc(m & ((1u << c.lane) - 1))) & (VK_QCAP - 1);
+    q_hv(c.wb)[e] = hv;
+    q_var(c.wb)[e] = mkvar();
+    q_seed(c.wb)[e] = seed;
   }
-  q.count += __popc(m);
+  c.count += __popc(m);
+  c.npass += __popc(m);
   __syncwarp();
 }
 
@@ -90,61 +73,54 @@ __device__ __forceinline__ void ring_push(WarpCtx& c, bool pass, uint64_t hv, ui
 // kernel contains no call, no verify code and no matrix atomics, and its registers are its own.
 // If the queue is full the entries are dropped and the cursor shows it: the host redoes that
 // chunk of seeds in smaller pieces (the enumeration kernel has no other side effect).
-__device__ __forceinline__ void q2_drain(const ProbeParams& P, WarpCtx& c, uint32_t n) {
+__device__ __forceinline__ void ring_drain(const ProbeParams& P, WarpCtx& c, uint32_t n) {
   unsigned long long pos = 0;
   if (c.lane == 0) pos = atomicAdd(P.counters + CTR_GQ, (unsigned long long)n);
   pos = __shfl_sync(FULL, pos, 0);
   if (c.lane < n && pos + n <= P.gq_cap) {
-    const uint32_t e = (c.q2.head + c.lane) & (VK_QCAP - 1);
-    P.gq_hv[pos + c.lane] = q_hv(c.wb, 1)[e];
-    P.gq_vs[pos + c.lane] = make_uint2(q_var(c.wb, 1)[e], q_seed(c.wb, 1)[e]);
+    const uint32_t e = (c.head + c.lane) & (VK_QCAP - 1);
+    P.gq_hv[pos + c.lane] = q_hv(c.wb)[e];
+    P.gq_vs[pos + c.lane] = make_uint2(q_var(c.wb)[e], q_seed(c.wb)[e]);
   }
   __syncwarp();
-  c.q2.head = (c.q2.head + n) & (VK_QCAP - 1);
-  c.q2.count -= n;
+  c.head = (c.head + n) & (VK_QCAP - 1);
+  c.count -= n;
 }
-
-// Second-level stage: test the words requested one stage ago, then pop n entries of Q1 and
-// request theirs.
-__device__ __forceinline__ void f2_stage(const ProbeParams& P, WarpCtx& c, uint32_t n) {
-  const bool pass2 = c.pd.valid && bloom_word_test(c.pd.w, c.pd.hv, false);
-  ring_push<1>(c, pass2, c.pd.hv, c.pd.var, c.pd.seed);
-  c.pd.valid = c.lane < n;
-  if (c.pd.valid) {
-    const uint32_t e = (c.q1.head + c.lane) & (VK_QCAP - 1);
-    c.pd.hv = q_hv(c.wb, 0)[e];
-    c.pd.var = q_var(c.wb, 0)[e];
-    c.pd.seed = q_seed(c.wb, 0)[e];
-    c.pd.w = __ldg(P.bloom2 + bloom_block(c.pd.hv, P.bloom2_blocks));
-  }
-  __syncwarp();
-  c.q1.head = (c.q1.head + n) & (VK_QCAP - 1);
-  c.q1.count -= n;
-  if (c.q2.count >= 32) q2_drain(P, c, 32);
-}
-
-__device__ __forceinline__ bool is_two_level(const ProbeParams& P) { return P.bloom2 != nullptr && P.use_bloom; }
 
 // One lane-step's verdicts into the pipeline.
+template <typename MkVar>
 __device__ __forceinline__ void submit(const ProbeParams& P, WarpCtx& c, bool pass, uint64_t hv,
-                                       uint32_t var, uint32_t seed) {
-  c.npass += pass;
-  if (is_two_level(P)) {
-    ring_push<0>(c, pass, hv, var, seed);
-    if (c.q1.count >= 32) f2_stage(P, c, 32);
-  } else {
-    ring_push<1>(c, pass, hv, var, seed);
-    if (c.q2.count >= 32) q2_drain(P, c, 32);
-  }
+                                       MkVar mkvar, uint32_t seed) {
+  ring_push(c, pass, hv, mkvar, seed);
+  if (c.count >= 32) ring_drain(P, c, 32);
+}
+
+// 3 + 3 bit test of filter word w for pattern field f (common.cuh bloom_pat_lo/hi), written as
+// shifts of the word instead of a mask built from six variable shifts: no branches, 14 instructions.
+__device__ __forceinline__ bool pattern_hit(unsigned long long w, uint32_t f) {
+  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+  const uint32_t a = (lo >> (f & 31)) & (lo >> ((f >> 5) & 31)) & (lo >> ((f >> 10) & 31));
+  const uint32_t b = (hi >> ((f >> 15) & 31)) & (hi >> ((f >> 20) & 31)) & (hi >> ((f >> 25) & 31));
+  return (a & b & 1u) != 0u;
 }
 
 __device__ __forceinline__ void finish(const ProbeParams& P, WarpCtx& c) {
   __syncwarp();
-  if (is_two_level(P)) {
-    f2_stage(P, c, c.q1.count);  // tests the batch in flight, requests the tail of Q1
-    f2_stage(P, c, 0);           // tests the tail
-  }
-  while (c.q2.count) q2_drain(P, c, c.q2.count < 32 ? c.q2.count : 32);
+  while (c.count) ring_drain(P, c, c.count < 32 ? c.count : 32);
+}
+
+// VK_U filter lookups per lane: all loads first (VK_U words in flight per lane), then the tests.
+// odd[u] = parity of candidate u's free position (which filter, common.cuh).
+__device__ __forceinline__ void filter_step(const ProbeParams& P, const uint64_t (&hv)[VK_U],
+                                            const bool (&odd)[VK_U], bool (&pass)[VK_U]) {
+  if (!P.use_bloom) return;
+  unsigned long long w[VK_U];
+#pragma unroll
+  for (int u = 0; u < VK_U; u++)  // unconditional: an inactive candidate's hash is a valid address too
+    w[u] = __ldg(P.bloom + pfilter_word(hv[u], P.bloom_blocks, odd[u]));
+#pragma unroll
+  for (int u = 0; u < VK_U; u++)
+    pass[u] = pass[u] & pattern_hit(w[u], odd[u] ? field_odd(hv[u]) : field_even(hv[u]));
 }
 
 // Per-warp scratch for one seed, addressed from the per-warp block.
@@ -157,6 +133,20 @@ struct SeedScratch {
   __device__ __forceinline__ uint64_t* pre() const { return zo + lpad; }
   __device__ __forceinline__ uint64_t* sm() const { return zo + 2 * lpad; }
   __device__ __forceinline__ uint64_t* sp() const { return zo + 3 * lpad; }
+  // d = 1 kernel only, after the scans (finalize_seed): everything a candidate needs, per "slot"
+  // pp = position for substitutions (pp < L), L + position for insertions (pp in [L, 2L]):
+  //   base2[pp]  hash of the variant minus the Zobrist value of its free residue
+  //   word2[pp]  the parity-filter word that every residue at this slot is looked up in
+  //   cmp2[pp]   the residue that must NOT be put there (substitution: the seed's own; insertion:
+  //              the residue before it, variants.cc:341-353; 255 = none)
+  // and for deletions (t < L) / the identical candidate (t = L, or 0 without indels):
+  //   dh[t], wd[t]  variant hash and its filter word
+  static constexpr uint32_t kScan = INDELS ? 4 : 1, kSlots = INDELS ? 2 : 1;
+  __device__ __forceinline__ uint64_t* base2() const { return zo + kScan * lpad; }
+  __device__ __forceinline__ uint64_t* word2() const { return zo + (kScan + kSlots) * lpad; }
+  __device__ __forceinline__ uint64_t* dh() const { return zo + (kScan + 2 * kSlots) * lpad; }
+  __device__ __forceinline__ uint64_t* wd() const { return zo + (kScan + 2 * kSlots + 1) * lpad; }
+  __device__ __forceinline__ uint8_t* cmp2() const { return reinterpret_cast<uint8_t*>(zo + (kScan + 2 * kSlots + 2) * lpad); }
 };
 
 // Fill zo[] (and the three scans) for the seed whose residues are at sres[0..L).  Returns VJ.
@@ -224,12 +214,13 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
   for (uint32_t base = 0; base < T; base += 32 * VK_U) {
     uint64_t hv[VK_U];
     uint32_t var[VK_U];
-    bool pass[VK_U];
+    bool pass[VK_U], odd[VK_U];
 #pragma unroll
     for (int u = 0; u < VK_U; u++) {
       const uint32_t idx = base + u * 32 + c.lane;
       pass[u] = idx < T;
       hv[u] = h;
+      odd[u] = true;
       var[u] = pack_var(VK_IDENTICAL, 0, 0, 0, 0);
       if (pass[u] && idx >= 1) {
         uint32_t t = idx - 1;
@@ -237,33 +228,120 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
           const uint32_t pos = t / S1, rp = t - pos * S1;
           const uint32_t r = sub_residue(rp, sres[pos]);
           hv[u] = h ^ s.zo[pos] ^ z[pos * SIGMA + r];
+          odd[u] = pos & 1;
           var[u] = pack_var(VK_SUBSTITUTION, pos, r, 0, 0);
         } else if (INDELS) {
           t -= nsub;
           if (t < L) {  // deletion of residue t: only at the start of a run, only if L > 1
             pass[u] = (L > 1) && (t == 0 || sres[t] != sres[t - 1]);
             hv[u] = vjh ^ s.pre()[t] ^ s.sm()[t + 1];
+            odd[u] = t & 1;  // no free residue: either filter, alternate for balance
             var[u] = pack_var(VK_DELETION, t, 0, 0, 0);
           } else {  // insertion of residue r before seed position pos
             t -= L;
             const uint32_t pos = t / SIGMA, r = t - pos * SIGMA;
             pass[u] = (pos == 0) || (r != sres[pos - 1]);
             hv[u] = vjh ^ s.pre()[pos] ^ z[pos * SIGMA + r] ^ s.sp()[pos];
+            odd[u] = pos & 1;  // the inserted residue sits at position pos of the variant
             var[u] = pack_var(VK_INSERTION, pos, r, 0, 0);
           }
         }
       }
     }
-    if (P.use_bloom) {
-      unsigned long long w[VK_U];
+    filter_step(P, hv, odd, pass);
 #pragma unroll
-      for (int u = 0; u < VK_U; u++)  // all loads first: VK_U sectors in flight per lane
-        w[u] = pass[u] ? __ldg(P.bloom + bloom_block(hv[u], P.bloom_blocks)) : 0ull;
+    for (int u = 0; u < VK_U; u++) {
+      const uint32_t v = var[u];
+      submit(P, c, pass[u], hv[u], [v] { return v; }, slocal);
+    }
+  }
+}
+
+// d = 1: per-slot bases, filter words and forbidden residues of one seed (see SeedScratch).  The
+// filter words are fetched HERE, once per slot — one or two coalesced loads per lane per seed —
+// because a slot's word does not depend on the residue placed there (parity filters, common.cuh):
+// the enumeration loop below then runs on shared memory alone.
+template <int SIGMA, bool INDELS>
+__device__ __forceinline__ void finalize_seed(const ProbeParams& P, const uint8_t* sres, uint32_t L, uint64_t h,
+                                              uint64_t vjh, uint32_t lane, const SeedScratch<SIGMA, INDELS>& s) {
+  const uint32_t nslots = INDELS ? 2 * L + 1 : L;
+  const bool filt = P.use_bloom;
+  for (uint32_t pp = lane; pp < nslots; pp += 32) {
+    uint64_t b;
+    uint32_t pos, cmp;
+    if (pp < L) {
+      pos = pp;
+      b = h ^ s.zo[pp];
+      cmp = sres[pp];
+    } else {
+      pos = pp - L;
+      b = vjh ^ s.pre()[pos] ^ s.sp()[pos];
+      cmp = pos == 0 ? 255u : sres[pos - 1];
+    }
+    // the free residue sits at position pos: it cannot change the field that picks the word
+    const unsigned long long w = filt ? __ldg(P.bloom + pfilter_word(b, P.bloom_blocks, pos & 1)) : ~0ull;
+    s.base2()[pp] = b;
+    s.word2()[pp] = w;
+    s.cmp2()[pp] = (uint8_t)cmp;
+  }
+  const uint32_t nd = INDELS ? L + 1 : 1;  // deletions, then the identical candidate
+  for (uint32_t t = lane; t < nd; t += 32) {
+    const uint64_t hv = (INDELS && t < L) ? (vjh ^ s.pre()[t] ^ s.sm()[t + 1]) : h;
+    s.dh()[t] = hv;
+    s.wd()[t] = filt ? __ldg(P.bloom + pfilter_word(hv, P.bloom_blocks, true)) : ~0ull;
+  }
+  __syncwarp();
+}
+
+// d = 1 enumeration.  Substitutions and insertions share one index space of SIGMA candidates per
+// slot (a substitution's own residue is one masked candidate in 20 — cheaper than a second decode):
+// q -> slot pp = q / SIGMA, residue r = q % SIGMA; hash = base2[pp] ^ Z(pos, r).  Then one step
+// for the deletions (one per run of equal residues, only if L > 1) and the identical candidate.
+template <int SIGMA, bool INDELS>
+__device__ __forceinline__ void phase_d1(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
+                                         const uint8_t* sres, const SeedScratch<SIGMA, INDELS>& s,
+                                         uint32_t L, uint32_t slocal) {
+  const uint32_t nslots = INDELS ? 2 * L + 1 : L;
+  const uint32_t Q = nslots * SIGMA;
+  for (uint32_t base = 0; base < Q; base += 32 * VK_U) {
+    uint64_t hv[VK_U];
+    uint32_t code[VK_U];
+    bool pass[VK_U];
 #pragma unroll
-      for (int u = 0; u < VK_U; u++) pass[u] = pass[u] && bloom_word_test(w[u], hv[u], P.bloom_k2);
+    for (int u = 0; u < VK_U; u++) {
+      const uint32_t q = base + u * 32 + c.lane;
+      const bool in = q < Q;
+      const uint32_t qq = in ? q : 0u;
+      const uint32_t pp = qq / SIGMA, r = qq - pp * SIGMA;
+      const uint32_t pos = pp - (pp >= L ? L : 0u);
+      const uint64_t b = s.base2()[pp];
+      const unsigned long long w = s.word2()[pp];
+      const uint32_t cmp = s.cmp2()[pp];
+      hv[u] = b ^ z[pos * SIGMA + r];
+      code[u] = qq;
+      pass[u] = in & (r != cmp) & pattern_hit(w, (pos & 1) ? field_odd(hv[u]) : field_even(hv[u]));
     }
 #pragma unroll
-    for (int u = 0; u < VK_U; u++) submit(P, c, pass[u], hv[u], var[u], slocal);
+    for (int u = 0; u < VK_U; u++) {
+      const uint32_t qq = code[u];
+      submit(P, c, pass[u], hv[u], [qq, L] {
+        const uint32_t pp = qq / SIGMA, r = qq - pp * SIGMA;
+        return pp < L ? pack_var(VK_SUBSTITUTION, pp, r, 0, 0) : pack_var(VK_INSERTION, pp - L, r, 0, 0);
+      }, slocal);
+    }
+  }
+  const uint32_t nd = INDELS ? L + 1 : 1;
+  for (uint32_t t0 = 0; t0 < nd; t0 += 32) {
+    const uint32_t t = t0 + c.lane;
+    const bool in = t < nd;
+    const uint32_t tt = in ? t : 0u;
+    const bool is_del = INDELS && tt < L;
+    const bool valid = in && (!is_del || (L > 1 && (tt == 0 || sres[tt] != sres[tt - 1])));
+    const uint64_t hv = s.dh()[tt];
+    const bool pass = valid & pattern_hit(s.wd()[tt], field_odd(hv));
+    submit(P, c, pass, hv, [is_del, tt] {
+      return is_del ? pack_var(VK_DELETION, tt, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0);
+    }, slocal);
   }
 }
 
@@ -284,31 +362,29 @@ __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const 
     for (uint32_t tb = 0; tb < ninner; tb += 32 * VK_U) {
       uint64_t hv[VK_U];
       uint32_t var[VK_U];
-      bool pass[VK_U];
+      bool pass[VK_U], odd[VK_U];
 #pragma unroll
       for (int u = 0; u < VK_U; u++) {
         const uint32_t t = tb + u * 32 + c.lane;
         pass[u] = t < ninner;
         hv[u] = 0;
+        odd[u] = true;
         var[u] = var_iv;
         if (pass[u]) {
           const uint32_t jj = t / S1, wp = t - jj * S1;
           const uint32_t j = i + 1 + jj;
           const uint32_t w = sub_residue(wp, sres[j]);
           hv[u] = base2 ^ s.zo[j] ^ z[j * SIGMA + w];
+          odd[u] = j & 1;  // free position of the inner loop: same word for every w and every j of this parity
           var[u] = var_iv | (w << 8) | (j << 22);
         }
       }
-      if (P.use_bloom) {
-        unsigned long long w[VK_U];
+      filter_step(P, hv, odd, pass);
 #pragma unroll
-        for (int u = 0; u < VK_U; u++)
-          w[u] = pass[u] ? __ldg(P.bloom + bloom_block(hv[u], P.bloom_blocks)) : 0ull;
-#pragma unroll
-        for (int u = 0; u < VK_U; u++) pass[u] = pass[u] && bloom_word_test(w[u], hv[u], P.bloom_k2);
+      for (int u = 0; u < VK_U; u++) {
+        const uint32_t v = var[u];
+        submit(P, c, pass[u], hv[u], [v] { return v; }, slocal);
       }
-#pragma unroll
-      for (int u = 0; u < VK_U; u++) submit(P, c, pass[u], hv[u], var[u], slocal);
     }
   }
 }
@@ -318,7 +394,7 @@ __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const 
 struct VkLayout {
   uint32_t lpad;        // per-seed scratch entries (>= lmax + 2, multiple of 8)
   size_t z_u64;         // Zobrist rows
-  size_t warp_bytes;    // per-warp block: two queues + seed scratch
+  size_t warp_bytes;    // per-warp block: survivor ring + seed scratch
   size_t blk_u64;       // staged seed batches, all warps: metas (4 u64 each) + hashes
   size_t res_per_warp;  // bytes of staged residues per warp
   size_t total;
@@ -329,7 +405,9 @@ __host__ __device__ inline VkLayout vk_layout(uint32_t zrows, uint32_t sigma, ui
   VkLayout l;
   l.lpad = (lmax + 2 + 7) & ~7u;
   l.z_u64 = (size_t)zrows * sigma;
-  l.warp_bytes = 2 * VK_Q_BYTES + (size_t)l.lpad * (indels ? 4 : 1) * 8;
+  // scratch in u64 units of lpad: scans (4 or 1); d = 1 adds base2 + word2 (2 or 1 each), dh, wd, cmp2 (bytes, <= 1)
+  const size_t units = (indels ? 4 : 1) + (staged ? (indels ? 4 : 2) + 2 + 1 : 0);
+  l.warp_bytes = VK_Q_BYTES + (size_t)l.lpad * units * 8;
   l.blk_u64 = staged ? (size_t)VK_WARPS * VK_WB * 5 : 0;
   l.res_per_warp = staged ? (((size_t)VK_WB * lmax + 15) & ~(size_t)15) : l.lpad;
   l.total = l.z_u64 * 8 + VK_WARPS * l.warp_bytes + l.blk_u64 * 8 + VK_WARPS * l.res_per_warp;
@@ -342,15 +420,11 @@ __device__ __forceinline__ void carve_warp(const VkLayout& l, unsigned char* sme
                                            uint64_t*& blk, uint8_t*& bytes) {
   z = reinterpret_cast<uint64_t*>(smem);
   c.wb = smem + l.z_u64 * 8 + warp * l.warp_bytes;
-  s.zo = reinterpret_cast<uint64_t*>(c.wb + 2 * VK_Q_BYTES);
+  s.zo = reinterpret_cast<uint64_t*>(c.wb + VK_Q_BYTES);
   s.lpad = l.lpad;
   blk = reinterpret_cast<uint64_t*>(smem + l.z_u64 * 8 + VK_WARPS * l.warp_bytes);
   bytes = reinterpret_cast<uint8_t*>(blk + l.blk_u64);
-  c.q1.head = c.q1.count = c.q2.head = c.q2.count = 0;
-  c.pd.valid = false;
-  c.pd.hv = 0;
-  c.pd.w = 0;
-  c.pd.var = c.pd.seed = 0;
+  c.head = c.count = 0;
   c.lane = lane;
   c.nmatch = c.npass = 0;
 }
@@ -410,11 +484,12 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant1_kernel(const __grid_co
       const uint8_t* sres = b_res + (uint32_t)((off_len & ((1ull << 40) - 1)) - res0);
       __syncwarp();  // all lanes are done with the previous seed's scratch
       const uint64_t vjh = prepare_seed<SIGMA, INDELS>(z, sres, L, h, lane, sc);
-      phase_a<SIGMA, INDELS>(P, c, z, sres, sc, L, h, vjh, (uint32_t)(first + k));
+      finalize_seed<SIGMA, INDELS>(P, sres, L, h, vjh, lane, sc);
+      phase_d1<SIGMA, INDELS>(P, c, z, sres, sc, L, (uint32_t)(first + k));
     }
   }
   finish(P, c);
-  flush_counters(P, 0, P.count_bloom ? c.npass : 0);
+  flush_counters(P, 0, (P.count_bloom && lane == 0) ? c.npass : 0);
 }
 
 // ---- d = 2 -------------------------------------------------------------------------------------------
@@ -457,7 +532,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant2_kernel(const __grid_co
     phase_b<SIGMA, false>(P, c, z, sres, sc, L, h, slocal, part, P.split);
   }
   finish(P, c);
-  flush_counters(P, 0, P.count_bloom ? c.npass : 0);
+  flush_counters(P, 0, (P.count_bloom && lane == 0) ? c.npass : 0);
 }
 
 // ---- K4: the table stage ----------------------------------------------------------------------------
@@ -515,9 +590,10 @@ static int launch_one(K kern, const ProbeParams& p, size_t smem, uint64_t work_c
   // The rate of random 8-byte loads an SM sustains has a cliff in the shared-memory carve-out
   // (tools/bench_l2_random.cu on B200: 268-290 G loads/s chip-wide up to a 100 KB carve-out,
   // 139-158 G loads/s from 132 KB on, whatever the occupancy) — the L1 side that tracks the
-  // misses in flight shrinks with it.  The Bloom stage is nothing but such loads, so: no more
-  // resident CTAs than fit 100 KB of shared memory (1 KB per CTA is the system's), and ask for
-  // exactly that carve-out instead of the driver's "room for the most CTAs" default.
+  // misses in flight shrinks with it, and with the parity filters L1 is also what serves the
+  // repeated filter words.  So: no more resident CTAs than fit 100 KB of shared memory (1 KB per
+  // CTA is the system's), and ask for exactly that carve-out instead of the driver's "room for
+  // the most CTAs" default.
   constexpr size_t kCarveCliff = 100 * 1024;
   const int fit = (int)(kCarveCliff / (smem + 1024));
   if (fit >= 2 || (fit == 1 && per_sm == 1)) {
