@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcompairr_b200.so")
+# COMPAIRR_B200_LIB: another build of the same library (A/B runs of kernel variants, tools/)
+LIB_PATH = os.environ.get("COMPAIRR_B200_LIB") or os.path.join(_HERE, "libcompairr_b200.so")
 
 ABI_VERSION = 2
 

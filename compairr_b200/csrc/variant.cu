@@ -32,6 +32,9 @@ constexpr int VK_WARPS = VK_THREADS / 32;
 constexpr int VK_QCAP = 64;  // ring entries per warp
 constexpr int VK_U = 4;      // probes per lane per step: 4 independent filter loads in flight per lane
 constexpr int VK_WB = 8;     // seeds per warp batch (d = 1)
+#ifndef VK_D1_CTAS
+#define VK_D1_CTAS 3          // resident CTAs per SM the d = 1 kernel is compiled for
+#endif
 
 // Per-warp shared-memory block, addressed from ONE base pointer to keep the register footprint of
 // the enumeration loop small:
@@ -99,8 +102,9 @@ __device__ __forceinline__ void submit(const ProbeParams& P, WarpCtx& c, bool pa
 // shifts of the word instead of a mask built from six variable shifts: no branches, 14 instructions.
 __device__ __forceinline__ bool pattern_hit(unsigned long long w, uint32_t f) {
   const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-  const uint32_t a = (lo >> (f & 31)) & (lo >> ((f >> 5) & 31)) & (lo >> ((f >> 10) & 31));
-  const uint32_t b = (hi >> ((f >> 15) & 31)) & (hi >> ((f >> 20) & 31)) & (hi >> ((f >> 25) & 31));
+  // __funnelshift_r(x, 0, s) = x >> (s & 31): the wrap mode of SHF does the "& 31"
+  const uint32_t a = __funnelshift_r(lo, 0u, f) & __funnelshift_r(lo, 0u, f >> 5) & __funnelshift_r(lo, 0u, f >> 10);
+  const uint32_t b = __funnelshift_r(hi, 0u, f >> 15) & __funnelshift_r(hi, 0u, f >> 20) & __funnelshift_r(hi, 0u, f >> 25);
   return (a & b & 1u) != 0u;
 }
 
@@ -257,72 +261,41 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
   }
 }
 
-// d = 1: per-slot bases, filter words and forbidden residues of one seed (see SeedScratch).  The
-// filter words are fetched HERE, once per slot — one or two coalesced loads per lane per seed —
-// because a slot's word does not depend on the residue placed there (parity filters, common.cuh):
-// the enumeration loop below then runs on shared memory alone.
-template <int SIGMA, bool INDELS>
-__device__ __forceinline__ void finalize_seed(const ProbeParams& P, const uint8_t* sres, uint32_t L, uint64_t h,
-                                              uint64_t vjh, uint32_t lane, const SeedScratch<SIGMA, INDELS>& s) {
-  const uint32_t nslots = INDELS ? 2 * L + 1 : L;
-  const bool filt = P.use_bloom;
-  for (uint32_t pp = lane; pp < nslots; pp += 32) {
-    uint64_t b;
-    uint32_t pos, cmp;
-    if (pp < L) {
-      pos = pp;
-      b = h ^ s.zo[pp];
-      cmp = sres[pp];
-    } else {
-      pos = pp - L;
-      b = vjh ^ s.pre()[pos] ^ s.sp()[pos];
-      cmp = pos == 0 ? 255u : sres[pos - 1];
-    }
-    // the free residue sits at position pos: it cannot change the field that picks the word
-    const unsigned long long w = filt ? __ldg(P.bloom + pfilter_word(b, P.bloom_blocks, pos & 1)) : ~0ull;
-    s.base2()[pp] = b;
-    s.word2()[pp] = w;
-    s.cmp2()[pp] = (uint8_t)cmp;
-  }
-  const uint32_t nd = INDELS ? L + 1 : 1;  // deletions, then the identical candidate
-  for (uint32_t t = lane; t < nd; t += 32) {
-    const uint64_t hv = (INDELS && t < L) ? (vjh ^ s.pre()[t] ^ s.sm()[t + 1]) : h;
-    s.dh()[t] = hv;
-    s.wd()[t] = filt ? __ldg(P.bloom + pfilter_word(hv, P.bloom_blocks, true)) : ~0ull;
-  }
-  __syncwarp();
-}
-
-// d = 1 enumeration.  Substitutions and insertions share one index space of SIGMA candidates per
-// slot (a substitution's own residue is one masked candidate in 20 — cheaper than a second decode):
-// q -> slot pp = q / SIGMA, residue r = q % SIGMA; hash = base2[pp] ^ Z(pos, r).  Then one step
-// for the deletions (one per run of equal residues, only if L > 1) and the identical candidate.
-template <int SIGMA, bool INDELS>
-__device__ __forceinline__ void phase_d1(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
-                                         const uint8_t* sres, const SeedScratch<SIGMA, INDELS>& s,
-                                         uint32_t L, uint32_t slocal) {
-  const uint32_t nslots = INDELS ? 2 * L + 1 : L;
-  const uint32_t Q = nslots * SIGMA;
-  for (uint32_t base = 0; base < Q; base += 32 * VK_U) {
-    uint64_t hv[VK_U];
-    uint32_t code[VK_U];
-    bool pass[VK_U];
+// d = 1.  Everything a candidate needs is laid out per slot first (SeedScratch); the filter words
+// are fetched once per slot, because a slot's word does not depend on the residue placed there
+// (parity filters, common.cuh), and the enumeration loops then run on shared memory and registers:
+//   * the two words of ALL substitution slots (even / odd positions) depend only on the seed's
+//     hash: they are fetched when the batch is staged (variant1_kernel) and arrive as ws_even/odd;
+//   * the words of the insertion and deletion slots need the scans: their loads are ISSUED before
+//     the substitution loop and CONSUMED after it, so their latency hides behind ~45 % of the
+//     seed's work instead of stalling the warp.
+template <int SIGMA, bool INDELS, int U>
+__device__ __forceinline__ void enumerate_slots(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
+                                                const SeedScratch<SIGMA, INDELS>& s, uint32_t L,
+                                                uint32_t q0, uint32_t q1, bool subs,
+                                                unsigned long long ws_even, unsigned long long ws_odd,
+                                                uint32_t slocal) {
+  // candidates q in [q0, q1) of the slot space: slot pp = q / SIGMA, residue r = q % SIGMA
+  for (uint32_t base = q0; base < q1; base += 32 * U) {
+    uint64_t hv[U];
+    uint32_t code[U];
+    bool pass[U];
 #pragma unroll
-    for (int u = 0; u < VK_U; u++) {
+    for (int u = 0; u < U; u++) {
       const uint32_t q = base + u * 32 + c.lane;
-      const bool in = q < Q;
-      const uint32_t qq = in ? q : 0u;
+      const bool in = q < q1;
+      const uint32_t qq = in ? q : q0;
       const uint32_t pp = qq / SIGMA, r = qq - pp * SIGMA;
-      const uint32_t pos = pp - (pp >= L ? L : 0u);
+      const uint32_t pos = subs ? pp : pp - L;
       const uint64_t b = s.base2()[pp];
-      const unsigned long long w = s.word2()[pp];
       const uint32_t cmp = s.cmp2()[pp];
+      const unsigned long long w = subs ? ((pos & 1) ? ws_odd : ws_even) : s.word2()[pp];
       hv[u] = b ^ z[pos * SIGMA + r];
       code[u] = qq;
       pass[u] = in & (r != cmp) & pattern_hit(w, (pos & 1) ? field_odd(hv[u]) : field_even(hv[u]));
     }
 #pragma unroll
-    for (int u = 0; u < VK_U; u++) {
+    for (int u = 0; u < U; u++) {
       const uint32_t qq = code[u];
       submit(P, c, pass[u], hv[u], [qq, L] {
         const uint32_t pp = qq / SIGMA, r = qq - pp * SIGMA;
@@ -330,22 +303,86 @@ __device__ __forceinline__ void phase_d1(const ProbeParams& P, WarpCtx& c, const
       }, slocal);
     }
   }
+}
+
+// Two candidates per lane per step: the loop has no global load left to overlap, and a small body
+// matters more — with four (and a separate tail loop) a quarter of all stall samples were
+// instruction-cache misses (profiles/r01_h_*).
+constexpr int VK_U1 = 2;
+template <int SIGMA, bool INDELS>
+__device__ __forceinline__ void enumerate_range(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
+                                                const SeedScratch<SIGMA, INDELS>& s, uint32_t L,
+                                                uint32_t q0, uint32_t q1, bool subs,
+                                                unsigned long long ws_even, unsigned long long ws_odd,
+                                                uint32_t slocal) {
+  enumerate_slots<SIGMA, INDELS, VK_U1>(P, c, z, s, L, q0, q1, subs, ws_even, ws_odd, slocal);
+}
+
+template <int SIGMA, bool INDELS>
+__device__ __forceinline__ void seed_d1(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
+                                        const uint8_t* sres, const SeedScratch<SIGMA, INDELS>& s,
+                                        uint32_t L, uint64_t h, uint64_t vjh,
+                                        unsigned long long ws_even, unsigned long long ws_odd,
+                                        uint32_t slocal) {
+  const bool filt = P.use_bloom;
+  const uint32_t lane = c.lane;
+  // substitution slots
+  for (uint32_t pp = lane; pp < L; pp += 32) {
+    s.base2()[pp] = h ^ s.zo[pp];
+    s.cmp2()[pp] = sres[pp];
+  }
+  // insertion slots (pp = L + pos) and deletions: bases now, words in flight.  The first 32 of
+  // each are prefetched into registers; longer seeds fetch the rest when the words are stored.
+  unsigned long long wi0 = ~0ull, wd0 = ~0ull;
+  if (INDELS) {
+    for (uint32_t pos = lane; pos <= L; pos += 32) {
+      const uint64_t b = vjh ^ s.pre()[pos] ^ s.sp()[pos];
+      s.base2()[L + pos] = b;
+      s.cmp2()[L + pos] = (uint8_t)(pos == 0 ? 255u : sres[pos - 1]);
+      // the inserted residue sits at position pos: it cannot change the field that picks the word
+      if (pos < 32 && filt) wi0 = __ldg(P.bloom + pfilter_word(b, P.bloom_blocks, pos & 1));
+    }
+    for (uint32_t t = lane; t < L; t += 32) {
+      const uint64_t hv = vjh ^ s.pre()[t] ^ s.sm()[t + 1];
+      s.dh()[t] = hv;
+      if (t < 32 && filt) wd0 = __ldg(P.bloom + pfilter_word(hv, P.bloom_blocks, true));
+    }
+  }
+  __syncwarp();
+  enumerate_range<SIGMA, INDELS>(P, c, z, s, L, 0, L * SIGMA, true, ws_even, ws_odd, slocal);
+  if (INDELS) {
+    for (uint32_t pos = lane; pos <= L; pos += 32)
+      s.word2()[L + pos] = pos < 32 ? wi0
+                           : (filt ? __ldg(P.bloom + pfilter_word(s.base2()[L + pos], P.bloom_blocks, pos & 1)) : ~0ull);
+    for (uint32_t t = lane; t < L; t += 32)
+      s.wd()[t] = t < 32 ? wd0 : (filt ? __ldg(P.bloom + pfilter_word(s.dh()[t], P.bloom_blocks, true)) : ~0ull);
+    __syncwarp();
+    enumerate_range<SIGMA, INDELS>(P, c, z, s, L, L * SIGMA, (2 * L + 1) * SIGMA, false, ws_even, ws_odd, slocal);
+  }
+  // deletions: one per run of equal residues, only if L > 1 (variants.cc:301-325); candidate
+  // t = nd - 1 is the identical one (filter E, whose word for the seed's own hash is ws_odd)
   const uint32_t nd = INDELS ? L + 1 : 1;
   for (uint32_t t0 = 0; t0 < nd; t0 += 32) {
-    const uint32_t t = t0 + c.lane;
+    const uint32_t t = t0 + lane;
     const bool in = t < nd;
-    const uint32_t tt = in ? t : 0u;
-    const bool is_del = INDELS && tt < L;
+    const bool is_del = INDELS && t < L;
+    const uint32_t tt = is_del ? t : 0u;
     const bool valid = in && (!is_del || (L > 1 && (tt == 0 || sres[tt] != sres[tt - 1])));
-    const uint64_t hv = s.dh()[tt];
-    const bool pass = valid & pattern_hit(s.wd()[tt], field_odd(hv));
+    const uint64_t hv = is_del ? s.dh()[tt] : h;
+    const unsigned long long w = is_del ? s.wd()[tt] : ws_odd;
+    const bool pass = valid & pattern_hit(w, field_odd(hv));
     submit(P, c, pass, hv, [is_del, tt] {
       return is_del ? pack_var(VK_DELETION, tt, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0);
     }, slocal);
   }
 }
 
-// Phase B: double substitutions i < j.  Outer (i, v) warp-uniform, lanes over (j > i, w).
+// Phase B: double substitutions i < j (variants.cc:357-400).  Outer (i, v) warp-uniform, lanes over
+// the slots (j > i, r) of the second substitution: SIGMA candidates per j with the seed's own
+// residue masked, hash = base2 ^ Z(j, s[j]) ^ Z(j, r).  The second substitution cannot change the
+// filter word: for odd j all candidates read filter E's word of base2, for even j filter O's — two
+// words per outer iteration, fetched one iteration AHEAD so that their latency never stalls the
+// warp.
 template <int SIGMA, bool INDELS>
 __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
                                         const uint8_t* sres, const SeedScratch<SIGMA, INDELS>& s,
@@ -353,38 +390,32 @@ __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const 
                                         uint32_t split) {
   constexpr uint32_t S1 = SIGMA - 1;
   const uint32_t nouter = S1 * L;
+  const bool filt = P.use_bloom;
+  auto outer = [&](uint32_t o, uint32_t& i, uint32_t& v, uint64_t& b2, unsigned long long& we, unsigned long long& wo) {
+    i = o / S1;
+    v = sub_residue(o - i * S1, sres[i]);
+    b2 = h ^ s.zo[i] ^ z[i * SIGMA + v];
+    we = filt ? __ldg(P.bloom + pfilter_word(b2, P.bloom_blocks, true)) : ~0ull;
+    wo = filt ? __ldg(P.bloom + pfilter_word(b2, P.bloom_blocks, false)) : ~0ull;
+  };
+  uint32_t i = 0, v = 0, ni = 0, nv = 0;
+  uint64_t b2 = 0, nb2 = 0;
+  unsigned long long we = 0, wo = 0, nwe = 0, nwo = 0;
+  if (part < nouter) outer(part, ni, nv, nb2, nwe, nwo);
   for (uint32_t o = part; o < nouter; o += split) {
-    const uint32_t i = o / S1, vp = o - i * S1;
-    const uint32_t v = sub_residue(vp, sres[i]);
-    const uint64_t base2 = h ^ s.zo[i] ^ z[i * SIGMA + v];
-    const uint32_t var_iv = pack_var(VK_SUB_SUB, i, v, 0, 0);
-    const uint32_t ninner = S1 * (L - 1 - i);
-    for (uint32_t tb = 0; tb < ninner; tb += 32 * VK_U) {
-      uint64_t hv[VK_U];
-      uint32_t var[VK_U];
-      bool pass[VK_U], odd[VK_U];
-#pragma unroll
-      for (int u = 0; u < VK_U; u++) {
-        const uint32_t t = tb + u * 32 + c.lane;
-        pass[u] = t < ninner;
-        hv[u] = 0;
-        odd[u] = true;
-        var[u] = var_iv;
-        if (pass[u]) {
-          const uint32_t jj = t / S1, wp = t - jj * S1;
-          const uint32_t j = i + 1 + jj;
-          const uint32_t w = sub_residue(wp, sres[j]);
-          hv[u] = base2 ^ s.zo[j] ^ z[j * SIGMA + w];
-          odd[u] = j & 1;  // free position of the inner loop: same word for every w and every j of this parity
-          var[u] = var_iv | (w << 8) | (j << 22);
-        }
-      }
-      filter_step(P, hv, odd, pass);
-#pragma unroll
-      for (int u = 0; u < VK_U; u++) {
-        const uint32_t v = var[u];
-        submit(P, c, pass[u], hv[u], [v] { return v; }, slocal);
-      }
+    i = ni; v = nv; b2 = nb2; we = nwe; wo = nwo;
+    if (o + split < nouter) outer(o + split, ni, nv, nb2, nwe, nwo);
+    const uint32_t ninner = SIGMA * (L - 1 - i);
+    for (uint32_t tb = 0; tb < ninner; tb += 32) {
+      const uint32_t t = tb + c.lane;
+      const bool in = t < ninner;
+      const uint32_t tt = in ? t : 0u;
+      const uint32_t jj = tt / SIGMA, r = tt - jj * SIGMA;
+      const uint32_t j = in ? i + 1 + jj : i;  // inactive lanes read a valid row
+      const uint32_t cmp = sres[j];
+      const uint64_t hv = b2 ^ s.zo[j] ^ z[j * SIGMA + r];
+      const bool pass = in & (r != cmp) & pattern_hit((j & 1) ? we : wo, (j & 1) ? field_odd(hv) : field_even(hv));
+      submit(P, c, pass, hv, [i, v, j, r] { return pack_var(VK_SUB_SUB, i, v, j, r); }, slocal);
     }
   }
 }
@@ -408,7 +439,7 @@ __host__ __device__ inline VkLayout vk_layout(uint32_t zrows, uint32_t sigma, ui
   // scratch in u64 units of lpad: scans (4 or 1); d = 1 adds base2 + word2 (2 or 1 each), dh, wd, cmp2 (bytes, <= 1)
   const size_t units = (indels ? 4 : 1) + (staged ? (indels ? 4 : 2) + 2 + 1 : 0);
   l.warp_bytes = VK_Q_BYTES + (size_t)l.lpad * units * 8;
-  l.blk_u64 = staged ? (size_t)VK_WARPS * VK_WB * 5 : 0;
+  l.blk_u64 = staged ? (size_t)VK_WARPS * VK_WB * 7 : 0;
   l.res_per_warp = staged ? (((size_t)VK_WB * lmax + 15) & ~(size_t)15) : l.lpad;
   l.total = l.z_u64 * 8 + VK_WARPS * l.warp_bytes + l.blk_u64 * 8 + VK_WARPS * l.res_per_warp;
   return l;
@@ -439,7 +470,7 @@ __device__ __forceinline__ void carve_warp(const VkLayout& l, unsigned char* sme
 // profiles/r01_d_*).
 
 template <int SIGMA, bool INDELS>
-__global__ void __launch_bounds__(VK_THREADS, 3) variant1_kernel(const __grid_constant__ ProbeParams P) {
+__global__ void __launch_bounds__(VK_THREADS, VK_D1_CTAS) variant1_kernel(const __grid_constant__ ProbeParams P) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const VkLayout lay = vk_layout(P.zrows, SIGMA, P.lmax, INDELS, true);
@@ -449,9 +480,10 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant1_kernel(const __grid_co
   uint64_t* blk;
   uint8_t* bytes;
   carve_warp<SIGMA, INDELS>(lay, smem_raw, warp, lane, z, sc, c, blk, bytes);
-  uint64_t* const my = blk + warp * (VK_WB * 5);                 // this warp's staging area
+  uint64_t* const my = blk + warp * (VK_WB * 7);                 // this warp's staging area
   SeqRec* const b_meta = reinterpret_cast<SeqRec*>(my);          // VK_WB records of 32 B
   uint64_t* const b_hash = my + VK_WB * 4;
+  unsigned long long* const b_ws = reinterpret_cast<unsigned long long*>(my + VK_WB * 5);  // [seed][even, odd]
   uint8_t* const b_res = bytes + warp * lay.res_per_warp;
 
   for (uint32_t i = threadIdx.x; i < P.zrows * SIGMA; i += VK_THREADS) z[i] = P.ztab[i];
@@ -469,12 +501,20 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant1_kernel(const __grid_co
     if (lane < nb * 2)
       reinterpret_cast<uint4*>(b_meta)[lane] =
           __ldg(reinterpret_cast<const uint4*>(P.a.meta + P.a_first + first) + lane);
-    if (lane >= 16 && lane < 16 + nb) b_hash[lane - 16] = __ldg(P.a.hash + P.a_first + first + (lane - 16));
+    // hashes, and with them the two filter words of each seed's substitution slots: filter O for
+    // even positions, filter E for odd ones (the word index ignores the substituted residue)
+    unsigned long long ws = ~0ull;
+    if (lane < 2 * nb) {
+      const uint64_t hk = __ldg(P.a.hash + P.a_first + first + (lane >> 1));
+      if (lane & 1) b_hash[lane >> 1] = hk;
+      if (P.use_bloom) ws = __ldg(P.bloom + pfilter_word(hk, P.bloom_blocks, lane & 1));
+    }
     __syncwarp();
     const uint64_t res0 = b_meta[0].off_len & ((1ull << 40) - 1);
     const uint64_t last = b_meta[nb - 1].off_len;
     const uint32_t res_n = (uint32_t)((last & ((1ull << 40) - 1)) + (last >> 40) - res0);
     for (uint32_t i = lane; i < res_n; i += 32) b_res[i] = __ldg(P.a.res + res0 + i);
+    if (lane < 2 * nb) b_ws[lane] = ws;
     __syncwarp();
 
     for (uint32_t k = 0; k < nb; k++) {
@@ -484,8 +524,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant1_kernel(const __grid_co
       const uint8_t* sres = b_res + (uint32_t)((off_len & ((1ull << 40) - 1)) - res0);
       __syncwarp();  // all lanes are done with the previous seed's scratch
       const uint64_t vjh = prepare_seed<SIGMA, INDELS>(z, sres, L, h, lane, sc);
-      finalize_seed<SIGMA, INDELS>(P, sres, L, h, vjh, lane, sc);
-      phase_d1<SIGMA, INDELS>(P, c, z, sres, sc, L, (uint32_t)(first + k));
+      seed_d1<SIGMA, INDELS>(P, c, z, sres, sc, L, h, vjh, b_ws[2 * k], b_ws[2 * k + 1], (uint32_t)(first + k));
     }
   }
   finish(P, c);
@@ -587,18 +626,15 @@ static int launch_one(K kern, const ProbeParams& p, size_t smem, uint64_t work_c
     *err = "variant kernel does not fit on an SM";
     return -1;
   }
-  // The rate of random 8-byte loads an SM sustains has a cliff in the shared-memory carve-out
-  // (tools/bench_l2_random.cu on B200: 268-290 G loads/s chip-wide up to a 100 KB carve-out,
-  // 139-158 G loads/s from 132 KB on, whatever the occupancy) — the L1 side that tracks the
-  // misses in flight shrinks with it, and with the parity filters L1 is also what serves the
-  // repeated filter words.  So: no more resident CTAs than fit 100 KB of shared memory (1 KB per
-  // CTA is the system's), and ask for exactly that carve-out instead of the driver's "room for
-  // the most CTAs" default.
-  constexpr size_t kCarveCliff = 100 * 1024;
-  const int fit = (int)(kCarveCliff / (smem + 1024));
-  if (fit >= 2 || (fit == 1 && per_sm == 1)) {
-    per_sm = std::min(per_sm, fit);
-    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, (int)(kCarveCliff * 100 / (228 * 1024)));
+  // Shared-memory carve-out = what the resident CTAs need (+1 KB per CTA for the system), not the
+  // driver's "room for the most CTAs" default: the rest of the 228 KB stays L1, which serves the
+  // repeated filter words and the staged loads.  (With a single randomly probed filter the
+  // carve-out had to stay under 100 KB — the rate of random 8-byte loads an SM sustains halves
+  // beyond it, tools/bench_l2_random.cu; with the parity filters such loads are a few dozen per seed.)
+  {
+    const size_t need = (size_t)per_sm * (smem + 1024);
+    cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                         (int)std::min<size_t>(100, (need * 100 + 228 * 1024 - 1) / (228 * 1024)));
   }
   uint64_t grid = (uint64_t)sm_count * per_sm;  // persistent: whole waves of resident CTAs
   if (work_ctas < grid) grid = work_ctas;
