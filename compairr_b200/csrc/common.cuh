@@ -2,7 +2,7 @@
 //
 // Everything in here is plain integer arithmetic that both the kernels (kernels.cu) and the
 // host side of the engine (engine.cu: table generation, probe counting) use.  The functions
-// marked CB_HD are also compiled by g++ in tests/ (tests/hd_check.cpp) so that the variant
+// marked CB_HD are also compiled by g++ in tests/ (tests/csrc/hd_check.cpp) so that the variant
 // decoding rules can be checked against the oracle without a GPU; that harness is a test of
 // this header, not a product path.
 //
@@ -128,9 +128,10 @@ CB_HD uint64_t vj_hash(uint64_t seed, uint32_t v, uint32_t j) {
   return splitmix64(splitmix64(seed ^ 0x7E11C0DEull) ^ (((uint64_t)v << 32) | j));
 }
 
-// Home slot (hashtable.h:36-41 takes the upper half of the hash): hash bits 61 downwards, the same
-// bits that pick the Bloom block, so keys ordered by those bits touch the table AND the filters in
-// address order — what the partitioned build relies on to keep its working set in L2.
+// Home slot (hashtable.h:36-41 takes the upper half of the hash): hash bits 61 downwards — bits of
+// the high half, which depends on every position (zobrist_gen).  Keys ordered by those bits touch
+// the table in address order, what the partitioned build relies on; the two filter updates of a
+// key are picked by the parity fields and stay random.
 CB_HD uint64_t table_home(uint64_t h, uint64_t mask) {
 #if defined(__CUDA_ARCH__)
   const int bits = __popcll(mask);
@@ -148,8 +149,8 @@ constexpr int CB_PARTITION_TOP_BIT = 62;  // partition keys are hash bits [62 - 
 // A variant may be looked up in either (no false negatives in both).  The enumeration kernels use
 // filter E for a variant whose free residue sits at an odd position and filter O for an even one:
 // the 19 (or 20) variants at that position — and those at every other position of the same
-// parity — then read the SAME word, so a warp's 32 lookups coalesce into one or two sectors that
-// stay in L1 instead of 32 random L2 sectors.  Word choice by multiply-shift (any word count);
+// parity — then read the SAME word: it is fetched once per slot, not once per candidate
+// (variant.cu), where a single filter cost one random L2 sector per candidate.  Word choice by multiply-shift (any word count);
 // normal polarity (1 = present; the reference's is inverted, an implementation detail).
 CB_HD uint32_t mulhi32(uint32_t x, uint32_t n) {
 #if defined(__CUDA_ARCH__)
@@ -162,14 +163,6 @@ CB_HD uint32_t mulhi32(uint32_t x, uint32_t n) {
 CB_HD uint64_t pfilter_word(uint64_t h, uint32_t nblocks, bool odd_free) {
   return odd_free ? (uint64_t)mulhi32(field_even(h), nblocks) : (uint64_t)nblocks + mulhi32(field_odd(h), nblocks);
 }
-CB_HD uint32_t bloom_block(uint64_t h, uint32_t nblocks) {
-  uint32_t x = (uint32_t)(h >> 30);
-#if defined(__CUDA_ARCH__)
-  return __umulhi(x, nblocks);
-#else
-  return (uint32_t)(((uint64_t)x * nblocks) >> 32);
-#endif
-}
 CB_HD uint32_t bloom_pat_lo(uint64_t h) {
   uint32_t x = (uint32_t)h;
   return (1u << (x & 31)) | (1u << ((x >> 5) & 31)) | (1u << ((x >> 10) & 31));
@@ -177,12 +170,6 @@ CB_HD uint32_t bloom_pat_lo(uint64_t h) {
 CB_HD uint32_t bloom_pat_hi(uint64_t h) {
   uint32_t x = (uint32_t)h;
   return (1u << ((x >> 15) & 31)) | (1u << ((x >> 20) & 31)) | (1u << ((x >> 25) & 31));
-}
-// Low-bits-per-key geometry of a capped first-level filter: one bit per half (k = 2).
-CB_HD uint32_t bloom1_pat_lo(uint64_t h) { return 1u << ((uint32_t)h & 31); }
-CB_HD uint32_t bloom1_pat_hi(uint64_t h) { return 1u << (((uint32_t)h >> 15) & 31); }
-CB_HD uint64_t bloom1_pattern(uint64_t h) {
-  return (uint64_t)bloom1_pat_lo(h) | ((uint64_t)bloom1_pat_hi(h) << 32);
 }
 CB_HD uint64_t bloom_pattern(uint64_t h) {
   return (uint64_t)bloom_pat_lo(h) | ((uint64_t)bloom_pat_hi(h) << 32);

@@ -184,8 +184,6 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   cudaDeviceProp prop;
   CU_CREATE(cudaGetDeviceProperties(&prop, c->device));
   c->sm_count = prop.multiProcessorCount;
-  c->l2_persist_max = (size_t)prop.persistingL2CacheMaxSize;
-  c->l2_window_max = (size_t)prop.accessPolicyMaxWindowSize;
 
   {
     cudaMemPool_t pool;
@@ -349,14 +347,16 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
 // Insert sequences [first, first + n) (hashes at d_hash[first..]) into the table and filter(s).
 //
 // A table much larger than L2 filled in input order is bound by DRAM row activations: every CAS,
-// every slot store and every second-level filter update is a random 32-byte sector (measured on
-// B200 at 10^8 keys / 4.3 GB: 21 G CAS/s, 22 G stores/s, 49 G RED/s, together 11.4 ms; the same
-// operations in address order 2.4 ms — tools/bench_atomics.cu).  So a batch that is a sizeable part
-// of the table is first sorted by the hash bits that pick the home slot (and the Bloom blocks) down
-// to segments of 16 slots — three 8-bit radix passes over (hash, index) pairs, 0.85 ms each at
-// 10^8 — and the build kernel then sweeps table and filters in address order.  Measured, whole
-// cb_build_b at 10^8: 21 ms -> 9.9 ms.  Small batches (the chunks of the upload pipeline, which
-// hide behind the PCIe copy anyway) keep the direct path.
+// every slot store and every filter update is a random 32-byte sector (measured on B200 at 10^8
+// keys / 4.3 GB: 21 G CAS/s, 22 G stores/s, 49 G RED/s, together 11.4 ms; the same operations in
+// address order 2.4 ms — tools/bench_atomics.cu).  So a batch that is a sizeable part of the
+// table is first sorted by the hash bits that pick the home slot down to segments of 16 slots —
+// three 8-bit radix passes over (hash, index) pairs, 0.85 ms each at 10^8 — and the build kernel
+// then sweeps the table in address order.  The two parity-filter updates of a key are picked by
+// other hash fields and stay random REDs (2 x 2 ms at 10^8).  Measured, whole cb_build_b at 10^8:
+// 21 ms unsorted, 9.9 ms sorted with one address-ordered filter, 14.5 ms sorted with the parity
+// filters.  Small batches (the chunks of the upload pipeline, which hide behind the PCIe copy
+// anyway) keep the direct path.
 void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n) {
   const uint64_t table_bytes = t.slots * sizeof(Slot);
   uint64_t* part_hash = nullptr;

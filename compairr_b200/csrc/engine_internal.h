@@ -53,9 +53,6 @@ struct cb_ctx {
   cb_config cfg{};
   int device = 0;
   int sm_count = 148;
-  size_t l2_persist_max = 0;  // persisting-L2 carve-out granted (0 = unavailable)
-  size_t l2_window_max = 0;
-  size_t l2_persist_set = 0;  // carve-out currently configured on the device
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D side of the pipelined upload

@@ -467,7 +467,7 @@ __device__ __forceinline__ void carve_warp(const VkLayout& l, unsigned char* sme
 // coalesced loads: the dependent global loads (dispenser -> metadata -> residues) are paid once
 // per batch, not once per seed, and nothing waits on a CTA-wide barrier (a block-synchronous
 // variant lost a third of its time at __syncthreads behind whichever warp was in the slow path,
-// profiles/r01_d_*).
+// measured this round).
 
 template <int SIGMA, bool INDELS>
 __global__ void __launch_bounds__(VK_THREADS, VK_D1_CTAS) variant1_kernel(const __grid_constant__ ProbeParams P) {
