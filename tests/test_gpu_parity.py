@@ -146,6 +146,55 @@ def test_upload_of_a_slice_and_long_sequences():
         assert _pairs(eng.drain_pairs()) == _pairs(po)
 
 
+def _long_mutant_sets(nucleotides, seed=71, n=240, lo=36, hi=90):
+    """Set A: long random sequences; set B: for each of them one single-edit mutant (substitution,
+    insertion or deletion at a position drawn over the WHOLE length, so most edits sit beyond
+    position 32), plus exact copies and double-substitution mutants."""
+    from compairr_b200.seqset import SeqSet
+    rng = np.random.default_rng(seed)
+    sigma = 4 if nucleotides else 20
+    seqs_a = [rng.integers(0, sigma, int(rng.integers(lo, hi + 1))).astype(np.uint8) for _ in range(n)]
+    seqs_b = []
+    for k, q in enumerate(seqs_a):
+        q = q.copy()
+        kind = k % 5
+        p = int(rng.integers(0, q.size))
+        if kind == 0:
+            q[p] = (q[p] + 1 + rng.integers(0, sigma - 1)) % sigma
+        elif kind == 1:
+            q = np.insert(q, p, rng.integers(0, sigma))
+        elif kind == 2:
+            q = np.delete(q, p)
+        elif kind == 3:
+            p2 = int(rng.integers(0, q.size))
+            q[p] = (q[p] + 1) % sigma
+            q[p2] = (q[p2] + 2) % sigma
+        seqs_b.append(q.astype(np.uint8))
+
+    def mk(seqs, reps):
+        off = np.zeros(len(seqs) + 1, dtype=np.uint64)
+        np.cumsum([x.size for x in seqs], out=off[1:])
+        m = len(seqs)
+        return SeqSet(np.concatenate(seqs), off, np.zeros(m, np.uint32), np.zeros(m, np.uint32),
+                      (np.arange(m) % reps).astype(np.uint32), rng.integers(1, 5, m).astype(np.uint64), reps,
+                      nucleotides=nucleotides)
+    return mk(seqs_a, 3), mk(seqs_b, 2)
+
+
+@pytest.mark.parametrize("nucleotides", [False, True])
+@pytest.mark.parametrize("d,indels", [(1, False), (1, True), (2, False)])
+def test_long_sequences_with_edits_beyond_position_32(d, indels, nucleotides):
+    """True matches whose edit lies anywhere in sequences of 36-90 residues: the per-slot filter
+    words of insertion and deletion slots >= 32 take a different path in the d=1 kernel (fetched
+    when stored, not prefetched), and the parity of far positions must pick the right filter."""
+    a, b = _long_mutant_sets(nucleotides)
+    mo, po, io = orc.overlap(a, b, differences=d, indels=indels, want_pairs=True)
+    assert io["matches"] >= (90 if d == 1 and not indels else 140)   # the construction really matches
+    m, p, info = overlap(a, b, OverlapOptions(differences=d, indels=indels, want_pairs=True, nucleotides=nucleotides))
+    assert np.array_equal(m, mo) and _pairs(p) == _pairs(po)
+    assert info["run"]["probes"] == io["probes"]
+
+
 @pytest.mark.parametrize("d", [3, 4])
 @pytest.mark.parametrize("nucleotides", [False, True])
 def test_d3_tensor_core_path(d, nucleotides):
