@@ -122,9 +122,9 @@ struct PairWriter {
       buf += d.keep(i);
     }
   }
-  // rows formatted on o.threads host threads, written in the order of p[] (row_writer.h)
+  // rows formatted on the host threads (-t, default: all), written in the order of p[] (row_writer.h)
   void write(const cb_pair* p, size_t n) const {
-    write_rows_parallel(f, n, (int)o.threads, [&](uint64_t k0, uint64_t k1, std::string& buf) {
+    write_rows_parallel(f, n, host_threads(o.threads), [&](uint64_t k0, uint64_t k1, std::string& buf) {
       for (uint64_t k = k0; k < k1; k++) {
         const uint64_t a = p[k].a, b = p[k].b;
         side(buf, d1, a);

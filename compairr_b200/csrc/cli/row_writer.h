@@ -58,6 +58,15 @@ void write_rows_parallel(FILE* f, uint64_t n_rows, int threads, Fn fn, uint64_t 
   for (auto& t : th) t.join();
 }
 
+// Host threads for the reader and the writers: -t N if given, else the machine's (at most 32).
+// The reference's -t 1 default means "one worker"; here the workers are on the GPU and -t only
+// sizes the host-side parsing and formatting, which never change a byte of the output.
+inline int host_threads(int64_t opt_threads) {
+  if (opt_threads > 1) return (int)opt_threads;
+  const unsigned hw = std::thread::hardware_concurrency();
+  return (int)std::max(1u, std::min(hw, 32u));
+}
+
 // decimal digits of an unsigned value, appended (std::to_string allocates)
 inline void append_u64(std::string& s, uint64_t v) {
   char tmp[24];
