@@ -163,16 +163,46 @@ CB_HD uint32_t mulhi32(uint32_t x, uint32_t n) {
 CB_HD uint64_t pfilter_word(uint64_t h, uint32_t nblocks, bool odd_free) {
   return odd_free ? (uint64_t)mulhi32(field_even(h), nblocks) : (uint64_t)nblocks + mulhi32(field_odd(h), nblocks);
 }
+// Bits per key in each 32-bit half of a filter word: 3 (default) or 2 (compile-time knob for A/B
+// runs of the enumeration kernels: four fewer instructions per candidate, ~2.5x the false positives).
+#ifndef CB_PATTERN_HALF_BITS
+#define CB_PATTERN_HALF_BITS 3
+#endif
 CB_HD uint32_t bloom_pat_lo(uint64_t h) {
   uint32_t x = (uint32_t)h;
-  return (1u << (x & 31)) | (1u << ((x >> 5) & 31)) | (1u << ((x >> 10) & 31));
+  uint32_t p = (1u << (x & 31)) | (1u << ((x >> 5) & 31));
+  if (CB_PATTERN_HALF_BITS >= 3) p |= 1u << ((x >> 10) & 31);
+  return p;
 }
 CB_HD uint32_t bloom_pat_hi(uint64_t h) {
   uint32_t x = (uint32_t)h;
-  return (1u << ((x >> 15) & 31)) | (1u << ((x >> 20) & 31)) | (1u << ((x >> 25) & 31));
+  uint32_t p = (1u << ((x >> 15) & 31)) | (1u << ((x >> 20) & 31));
+  if (CB_PATTERN_HALF_BITS >= 3) p |= 1u << ((x >> 25) & 31);
+  return p;
 }
 CB_HD uint64_t bloom_pattern(uint64_t h) {
   return (uint64_t)bloom_pat_lo(h) | ((uint64_t)bloom_pat_hi(h) << 32);
+}
+// x >> (s mod 32): on the device one funnel shift in wrap mode, no separate "& 31"
+CB_HD uint32_t shr_wrap(uint32_t x, uint32_t s) {
+#if defined(__CUDA_ARCH__)
+  return __funnelshift_r(x, 0u, s);
+#else
+  return x >> (s & 31);
+#endif
+}
+// Does filter word w contain bloom_pattern(f)?  The same test as (w & pattern) == pattern, written
+// as shifts of the word instead of a mask built from six variable shifts (tests/csrc/hd_check.cpp
+// checks the equivalence): no branches, 14 instructions.
+CB_HD bool pattern_hit(unsigned long long w, uint32_t f) {
+  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
+  uint32_t a = shr_wrap(lo, f) & shr_wrap(lo, f >> 5);
+  uint32_t b = shr_wrap(hi, f >> 15) & shr_wrap(hi, f >> 20);
+  if (CB_PATTERN_HALF_BITS >= 3) {
+    a &= shr_wrap(lo, f >> 10);
+    b &= shr_wrap(hi, f >> 25);
+  }
+  return (a & b & 1u) != 0u;
 }
 // bit pattern of h in the same filter: from the field the word index does not use
 CB_HD uint64_t pfilter_pattern(uint64_t h, bool odd_free) {

@@ -57,9 +57,7 @@ __device__ __forceinline__ bool seq_equal(const uint8_t* __restrict__ res, uint6
 // Parity-filter lookup of hash h (common.cuh): word from the filter that serves a free position of
 // the given parity, 3 + 3 bits from the field that word index does not use.
 __device__ __forceinline__ bool pfilter_word_test(unsigned long long w, uint64_t h, bool odd_free) {
-  const uint32_t f = odd_free ? field_odd(h) : field_even(h);
-  const uint32_t plo = bloom_pat_lo(f), phi = bloom_pat_hi(f);
-  return (((uint32_t)w & plo) == plo) & (((uint32_t)(w >> 32) & phi) == phi);
+  return pattern_hit(w, odd_free ? field_odd(h) : field_even(h));
 }
 
 __device__ __forceinline__ bool pfilter_test(const unsigned long long* __restrict__ bloom,

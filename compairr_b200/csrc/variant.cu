@@ -98,16 +98,6 @@ __device__ __forceinline__ void submit(const ProbeParams& P, WarpCtx& c, bool pa
   if (c.count >= 32) ring_drain(P, c, 32);
 }
 
-// 3 + 3 bit test of filter word w for pattern field f (common.cuh bloom_pat_lo/hi), written as
-// shifts of the word instead of a mask built from six variable shifts: no branches, 14 instructions.
-__device__ __forceinline__ bool pattern_hit(unsigned long long w, uint32_t f) {
-  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-  // __funnelshift_r(x, 0, s) = x >> (s & 31): the wrap mode of SHF does the "& 31"
-  const uint32_t a = __funnelshift_r(lo, 0u, f) & __funnelshift_r(lo, 0u, f >> 5) & __funnelshift_r(lo, 0u, f >> 10);
-  const uint32_t b = __funnelshift_r(hi, 0u, f >> 15) & __funnelshift_r(hi, 0u, f >> 20) & __funnelshift_r(hi, 0u, f >> 25);
-  return (a & b & 1u) != 0u;
-}
-
 __device__ __forceinline__ void finish(const ProbeParams& P, WarpCtx& c) {
   __syncwarp();
   while (c.count) ring_drain(P, c, c.count < 32 ? c.count : 32);
@@ -308,7 +298,9 @@ __device__ __forceinline__ void enumerate_slots(const ProbeParams& P, WarpCtx& c
 // Two candidates per lane per step: the loop has no global load left to overlap, and a small body
 // matters more — with four (and a separate tail loop) a quarter of all stall samples were
 // instruction-cache misses (profiles/r01_h_*).
-constexpr int VK_U1 = 2;
+#ifndef VK_U1
+#define VK_U1 2
+#endif
 template <int SIGMA, bool INDELS>
 __device__ __forceinline__ void enumerate_range(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
                                                 const SeedScratch<SIGMA, INDELS>& s, uint32_t L,

@@ -99,6 +99,14 @@ int main() {
       }
     }
   }
+  // pattern_hit(w, f) is (w & bloom_pattern(f)) == bloom_pattern(f), for sparse and dense words
+  for (int it = 0; it < 200000; it++) {
+    const uint32_t f = (uint32_t)rnd();
+    unsigned long long w = rnd();
+    if (it % 3 == 0) w |= rnd() | rnd();
+    if (it % 5 == 0) w |= bloom_pattern(f);
+    CHECK(pattern_hit(w, f) == ((w & bloom_pattern(f)) == bloom_pattern(f)));
+  }
   // 5: probe_count against a literal enumeration of distinct variant strings + the rules
   for (int it = 0; it < 200; it++) {
     const int sigma = (it & 1) ? 4 : 20;
