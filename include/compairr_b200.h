@@ -154,12 +154,12 @@ typedef struct cb_pair {
 typedef struct cb_stats {
   uint64_t seeds;           /* set-A sequences processed                                          */
   uint64_t probes;          /* variant hashes enumerated (= variants the reference generates)     */
-  uint64_t bloom_pass;      /* probes that passed the Bloom prefilter (0 unless counting enabled) */
+  uint64_t bloom_pass;      /* probes that passed the filter stage (reach the table stage)       */
   uint64_t matches;         /* verified (seed, hit) matches (reference all_matches, overlap.cc:230) */
   uint64_t pairs;           /* pairs stored for cb_drain_pairs                                    */
   uint64_t table_slots;     /* hash-table slots                                                   */
-  uint64_t bloom_bytes;     /* first-level Bloom bitmap bytes                                     */
-  uint64_t bloom2_bytes;    /* second-level (HBM) Bloom bitmap bytes, 0 if single-level          */
+  uint64_t bloom_bytes;     /* bytes of parity filter E (word picked by the even-position field) */
+  uint64_t bloom2_bytes;    /* bytes of parity filter O (word picked by the odd-position field)  */
   float ms_hash_b;          /* device time, CUDA events on the engine's stream                    */
   float ms_build_b;
   float ms_dups_b;
