@@ -43,7 +43,7 @@ class OverlapOptions:
     table_load_pct: int = 0
     pairs_capacity: int = 0
     flags: int = int(__import__("os").environ.get("CB_FLAGS", "0"))
-    bloom_l2_cap_kib: int = int(__import__("os").environ.get("CB_L2CAP_KIB", "0"))
+    bloom_l2_cap_kib: int = 0   # accepted and ignored by the engine (field of the former two-level filter)
 
 
 def _ptr(a: Optional[np.ndarray]):
