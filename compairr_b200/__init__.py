@@ -7,8 +7,19 @@ Layout (only what the path needs):
   engine.py        host-side mirror of the reference's overlap() seam on numpy arrays
   seqset.py        sequence sets in structure-of-arrays form, AIRR TSV <-> arrays
   synth.py         seeded synthetic repertoires
-"""
-from .seqset import SeqSet, NarrowSet, encode_sequences, AA_ALPHABET, NT_ALPHABET  # noqa: F401
-from .engine import Engine, OverlapOptions, overlap, dedup, cluster, SCORES  # noqa: F401
 
-__all__ = ["SeqSet", "Engine", "OverlapOptions", "overlap", "dedup", "cluster", "SCORES", "encode_sequences"]
+The engine names (Engine, overlap, ...) load libcompairr_b200.so when first touched; the data
+modules (seqset, synth, report) are plain numpy and import without it, so that a process which
+only generates inputs — the reference arm of bench.py — never maps the CUDA library."""
+from .seqset import SeqSet, NarrowSet, encode_sequences, AA_ALPHABET, NT_ALPHABET  # noqa: F401
+
+_ENGINE_NAMES = ("Engine", "OverlapOptions", "overlap", "dedup", "cluster", "SCORES", "EngineError")
+__all__ = ["SeqSet", "NarrowSet", "encode_sequences", *_ENGINE_NAMES]
+
+
+def __getattr__(name):
+    if name in _ENGINE_NAMES or name in ("engine", "cabi"):
+        import importlib
+        mod = importlib.import_module(".engine" if name != "cabi" else ".cabi", __name__)
+        return mod if name in ("engine", "cabi") else getattr(mod, name)
+    raise AttributeError(f"module {__name__!r} has no attribute {name!r}")

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # COMPAIRR_B200_LIB: another build of the same library (A/B runs of kernel variants, tools/)
 LIB_PATH = os.environ.get("COMPAIRR_B200_LIB") or os.path.join(_HERE, "libcompairr_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 
 class cb_config(C.Structure):
@@ -21,7 +21,7 @@ class cb_config(C.Structure):
         ("ignore_counts", C.c_int32), ("score", C.c_int32), ("mode", C.c_int32),
         ("no_matrix", C.c_int32), ("want_pairs", C.c_int32), ("n_reps_a", C.c_uint32),
         ("seed", C.c_uint64), ("bloom_bits_per_key_x16", C.c_uint32), ("table_load_pct", C.c_uint32),
-        ("pairs_capacity", C.c_uint64), ("flags", C.c_uint32), ("bloom_l2_cap_kib", C.c_uint32),
+        ("pairs_capacity", C.c_uint64), ("flags", C.c_uint32), ("queue_capacity", C.c_uint32),
     ]
 
 

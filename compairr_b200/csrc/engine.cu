@@ -37,10 +37,12 @@ int cb_fail(cb_ctx* c, int code, const char* fmt, ...) {
 #define ensure_ztab cb_ensure_ztab
 
 static thread_local cudaStream_t g_alloc_stream = nullptr;
+static thread_local cudaMemPool_t g_alloc_pool = nullptr;
 
 cudaError_t cb_dmalloc_raw(void** p, size_t bytes) {
   *p = nullptr;
-  return cudaMallocAsync(p, bytes ? bytes : 1, g_alloc_stream);
+  if (!g_alloc_pool) return cudaErrorInvalidValue;  // no context bound to this thread
+  return cudaMallocFromPoolAsync(p, bytes ? bytes : 1, g_alloc_pool, g_alloc_stream);
 }
 
 cudaError_t cb_dfree(void* p) { return p ? cudaFreeAsync(p, g_alloc_stream) : cudaSuccess; }
@@ -48,6 +50,7 @@ cudaError_t cb_dfree(void* p) { return p ? cudaFreeAsync(p, g_alloc_stream) : cu
 int cb_bind_device(cb_ctx* c) {
   CU(c, cudaSetDevice(c->device));
   g_alloc_stream = c->stream;
+  g_alloc_pool = c->pool;
   return CB_OK;
 }
 #define bind cb_bind_device
@@ -168,7 +171,6 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   if (c->cfg.bloom_bits_per_key_x16 == 0) c->cfg.bloom_bits_per_key_x16 = 24 * 16;
   if (c->cfg.table_load_pct == 0 || c->cfg.table_load_pct > 90) c->cfg.table_load_pct = 50;
   if (c->cfg.pairs_capacity == 0) c->cfg.pairs_capacity = 1ull << 24;
-  if (c->cfg.bloom_l2_cap_kib == 0) c->cfg.bloom_l2_cap_kib = 48 * 1024;
   if (c->cfg.seed == 0) c->cfg.seed = 1;
   c->device = cfg->device;
 #define CU_CREATE(expr)                                                                  \
@@ -186,15 +188,22 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   c->sm_count = prop.multiProcessorCount;
 
   {
-    cudaMemPool_t pool;
-    CU_CREATE(cudaDeviceGetDefaultMemPool(&pool, c->device));
-    uint64_t keep = ~0ull;  // never hand cached blocks back to the driver between calls
-    CU_CREATE(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    // the engine's own stream-ordered pool (the device's default pool and its attributes belong
+    // to the host application); cached blocks are never handed back between calls
+    cudaMemPoolProps props{};
+    props.allocType = cudaMemAllocationTypePinned;
+    props.handleTypes = cudaMemHandleTypeNone;
+    props.location.type = cudaMemLocationTypeDevice;
+    props.location.id = c->device;
+    CU_CREATE(cudaMemPoolCreate(&c->pool, &props));
+    uint64_t keep = ~0ull;
+    CU_CREATE(cudaMemPoolSetAttribute(c->pool, cudaMemPoolAttrReleaseThreshold, &keep));
   }
   CU_CREATE(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CU_CREATE(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   g_alloc_stream = c->stream;
+  g_alloc_pool = c->pool;
   for (auto& ev : c->ev) CU_CREATE(cudaEventCreate(&ev));
   CU_CREATE(cb_dmalloc(&c->d_counters, CTR_COUNT * sizeof(unsigned long long)));
   CU_CREATE(cudaMemset(c->d_counters, 0, CTR_COUNT * sizeof(unsigned long long)));
@@ -218,6 +227,7 @@ extern "C" void cb_destroy(cb_ctx* c) {
   if (!c) return;
   cudaSetDevice(c->device);
   g_alloc_stream = c->stream ? c->stream : c->own_stream;
+  g_alloc_pool = c->pool;
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   if (c->stream && c->stream != c->own_stream) cudaStreamSynchronize(c->stream);
   if (c->b_owned) cb_free_dset(c->b);
@@ -234,11 +244,9 @@ extern "C" void cb_destroy(cb_ctx* c) {
   for (auto& ev : c->ev)
     if (ev) cudaEventDestroy(ev);
   if (g_alloc_stream) cudaStreamSynchronize(g_alloc_stream);
-  {
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, c->device) == cudaSuccess) cudaMemPoolTrimTo(pool, 0);
-  }
+  if (c->pool) cudaMemPoolDestroy(c->pool);
   g_alloc_stream = nullptr;
+  g_alloc_pool = nullptr;
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
@@ -251,6 +259,7 @@ extern "C" int cb_set_stream(cb_ctx* c, void* s) {
   cudaStreamSynchronize(c->stream);
   c->stream = s ? (cudaStream_t)s : c->own_stream;
   g_alloc_stream = c->stream;
+  g_alloc_pool = c->pool;
   return CB_OK;
 }
 
@@ -307,9 +316,7 @@ static uint32_t blocks_for_bits(unsigned __int128 bits) {
 
 // Table + the two parity filters (common.cuh) sized for n keys: bloom_bits_per_key bits per key in
 // EACH filter.  Their size no longer has to fit L2: a warp's lookups fall into one or two words per
-// step, not 32 random ones, so the filters are read a few dozen sectors per seed.  (Until the
-// parity filters a single filter was capped to stay L2-resident and backed by a second level in
-// HBM; cfg.bloom_l2_cap_kib is accepted and ignored.)
+// step, not 32 random ones, so the filters are read a few dozen sectors per seed.
 int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
   BuiltTable t;
   t.slots = 8;
@@ -623,13 +630,32 @@ static int run_hash_path(cb_ctx* c, ProbeParams& p, uint64_t count, int* launche
     *launches += l;
     return CB_OK;
   }
-  // global candidate queue: 2^26 entries (1 GiB) unless the run is small
-  const uint64_t cap = 1ull << 26;
-  if (!c->d_gq_hv) {
+  const double L = p.a.n ? (double)c->run_res_bytes / (double)p.a.n : 1.0;
+  const double s1 = p.sigma - 1.0;
+  double probes = 1.0 + s1 * L + (p.indels ? (L + p.sigma * (L + 1.0)) : 0.0);
+  if (p.differences == 2) probes += s1 * s1 * L * (L - 1.0) / 2.0;
+  // Global candidate queue (16 B per entry).  cfg.queue_capacity if given; else sized for the whole
+  // run at ~3 % of its probes reaching the table stage, between 2^16 and 2^26 entries (1 GiB).  It
+  // only grows: a context that has seen a large run keeps its queue.
+  uint64_t cap = c->cfg.queue_capacity;
+  if (cap == 0) {
+    const double want = (double)count * probes * 0.03 * 2.0;
+    cap = 1ull << 16;
+    while (cap < (1ull << 26) && (double)cap < want) cap <<= 1;
+  }
+  cap = std::max<uint64_t>(cap, 64);
+  if (c->cfg.queue_capacity ? c->gq_cap != cap : c->gq_cap < cap) {
+    cb_dfree(c->d_gq_hv);
+    cb_dfree(c->d_gq_vs);
+    c->d_gq_hv = nullptr;
+    c->d_gq_vs = nullptr;
+    c->gq_cap = 0;
     CU(c, cb_dmalloc(&c->d_gq_hv, cap * sizeof(uint64_t)));
     CU(c, cb_dmalloc(&c->d_gq_vs, cap * sizeof(uint2)));
-    CU(c, cb_dmalloc(&c->d_overflow, 64 * sizeof(uint32_t)));
+    c->gq_cap = cap;
   }
+  cap = c->gq_cap;
+  if (!c->d_overflow) CU(c, cb_dmalloc(&c->d_overflow, 64 * sizeof(uint32_t)));
   p.gq_hv = c->d_gq_hv;
   p.gq_vs = c->d_gq_vs;
   p.gq_cap = cap;
@@ -638,10 +664,6 @@ static int run_hash_path(cb_ctx* c, ProbeParams& p, uint64_t count, int* launche
   // data (it depends on d, on the filters' false-positive rate and on how much the sets overlap);
   // the rest runs in chunks sized to fill the queue at most half.  Few, large chunks matter for
   // d = 2, where one seed is ~36 000 probes and every kernel tail costs.
-  const double L = p.a.n ? (double)c->run_res_bytes / (double)p.a.n : 1.0;
-  const double s1 = p.sigma - 1.0;
-  double probes = 1.0 + s1 * L + (p.indels ? (L + p.sigma * (L + 1.0)) : 0.0);
-  if (p.differences == 2) probes += s1 * s1 * L * (L - 1.0) / 2.0;
   const uint64_t guess = (uint64_t)std::max(1.0, (double)(cap / 2) / (probes * 0.03));
   const uint64_t first_n = std::min<uint64_t>(count, std::min<uint64_t>(guess, std::max<uint64_t>(count / 32, 4096)));
   int rc = run_chunks(c, p, 0, first_n, first_n, 0, launches);
@@ -655,6 +677,8 @@ static int run_hash_path(cb_ctx* c, ProbeParams& p, uint64_t count, int* launche
 extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count) {
   if (!c || !a) return fail(c, CB_ERR_INVALID, "cb_run: NULL argument");
   if (!c->b) return fail(c, CB_ERR_STATE, "cb_run: set B has not been built (cb_build_b / cb_set_b)");
+  if (c->cfg.differences <= MAXDIFF_HASH && !c->d_table && c->b->n)
+    return fail(c, CB_ERR_STATE, "cb_run: set B has no table (the last cb_build_b / cb_set_b failed)");
   if (count >= 0xffffffffull)
     return fail(c, CB_ERR_LIMIT, "cb_run: at most 2^32-1 sequences per call; run the set in chunks");
   if (first > a->n || count > a->n - first)

@@ -27,8 +27,8 @@ struct cb_dset {
   std::vector<uint64_t> pack_off;      // n_buckets + 1 word offsets into d_packed
 };
 
-// Device memory comes from the device's stream-ordered pool (cudaMallocAsync) with an unlimited
-// release threshold: repeated set-B builds and set-A uploads reuse cached blocks instead of paying
+// Device memory comes from a stream-ordered pool owned by the context (cudaMallocFromPoolAsync)
+// with an unlimited release threshold: repeated set-B builds and set-A uploads reuse cached blocks instead of paying
 // cudaMalloc/cudaFree of multi-GB buffers every call (that was ~100 ms per bench step).  Ordered
 // on the stream of the context bound to the calling thread (cb_bind_device).
 cudaError_t cb_dmalloc_raw(void** p, size_t bytes);
@@ -56,6 +56,7 @@ struct cb_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D side of the pipelined upload
+  cudaMemPool_t pool = nullptr;        // the context's own stream-ordered memory pool
   cudaEvent_t ev[8]{};
   std::string err;
 
@@ -80,6 +81,7 @@ struct cb_ctx {
   uint64_t* d_gq_hv = nullptr;      // global candidate queue (enumeration kernel -> table kernel)
   uint2* d_gq_vs = nullptr;
   uint32_t* d_overflow = nullptr;
+  uint64_t gq_cap = 0;              // entries
   uint64_t run_res_bytes = 0;
   cb::PairOut* d_pairs = nullptr;
   uint64_t pairs_cap = 0;

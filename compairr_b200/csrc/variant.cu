@@ -46,7 +46,6 @@ struct WarpCtx {
   unsigned char* wb;  // per-warp block
   uint32_t head, count;  // ring state
   uint32_t lane;
-  uint32_t nmatch, npass;
 };
 
 __device__ __forceinline__ uint64_t* q_hv(unsigned char* wb) { return reinterpret_cast<uint64_t*>(wb); }
@@ -54,7 +53,7 @@ __device__ __forceinline__ uint32_t* q_var(unsigned char* wb) { return reinterpr
 __device__ __forceinline__ uint32_t* q_seed(unsigned char* wb) { return reinterpret_cast<uint32_t*>(wb + VK_QCAP * 12); }
 
 // mkvar() builds the 31-bit variant descriptor; it runs for survivors only (a fraction of a percent
-// of the candidates), so the enumeration loop itself never packs one.  c.npass is warp-uniform.
+// of the candidates), so the enumeration loop itself never packs one.
 template <typename MkVar>
 __device__ __forceinline__ void ring_push(WarpCtx& c, bool pass, uint64_t hv, MkVar mkvar, uint32_t seed) {
   const unsigned m = __ballot_sync(FULL, pass);
@@ -66,7 +65,6 @@ __device__ __forceinline__ void ring_push(WarpCtx& c, bool pass, uint64_t hv, Mk
     q_seed(c.wb)[e] = seed;
   }
   c.count += __popc(m);
-  c.npass += __popc(m);
   __syncwarp();
 }
 
@@ -449,7 +447,6 @@ __device__ __forceinline__ void carve_warp(const VkLayout& l, unsigned char* sme
   bytes = reinterpret_cast<uint8_t*>(blk + l.blk_u64);
   c.head = c.count = 0;
   c.lane = lane;
-  c.nmatch = c.npass = 0;
 }
 
 // ---- d = 1 -------------------------------------------------------------------------------------------
@@ -520,7 +517,6 @@ __global__ void __launch_bounds__(VK_THREADS, VK_D1_CTAS) variant1_kernel(const 
     }
   }
   finish(P, c);
-  flush_counters(P, 0, (P.count_bloom && lane == 0) ? c.npass : 0);
 }
 
 // ---- d = 2 -------------------------------------------------------------------------------------------
@@ -563,7 +559,6 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant2_kernel(const __grid_co
     phase_b<SIGMA, false>(P, c, z, sres, sc, L, h, slocal, part, P.split);
   }
   finish(P, c);
-  flush_counters(P, 0, (P.count_bloom && lane == 0) ? c.npass : 0);
 }
 
 // ---- K4: the table stage ----------------------------------------------------------------------------
@@ -580,6 +575,9 @@ __global__ void __launch_bounds__(256) table_kernel(const __grid_constant__ Prob
     }
     return;
   }
+  // candidates that passed the filter stage = entries of a queue that is consumed (a chunk that
+  // overflowed is redone and counted then)
+  if (P.count_bloom && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.counters + CTR_BLOOM_PASS, filled);
   uint32_t nmatch = 0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); i0 < filled; i0 += stride) {

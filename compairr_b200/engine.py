@@ -43,7 +43,7 @@ class OverlapOptions:
     table_load_pct: int = 0
     pairs_capacity: int = 0
     flags: int = int(__import__("os").environ.get("CB_FLAGS", "0"))
-    bloom_l2_cap_kib: int = 0   # accepted and ignored by the engine (field of the former two-level filter)
+    queue_capacity: int = 0     # candidate-queue entries (0 = sized from the run); overflow only costs time
 
 
 def _ptr(a: Optional[np.ndarray]):
@@ -118,7 +118,7 @@ class Engine:
         cfg.table_load_pct = opts.table_load_pct
         cfg.pairs_capacity = opts.pairs_capacity
         cfg.flags = opts.flags
-        cfg.bloom_l2_cap_kib = opts.bloom_l2_cap_kib
+        cfg.queue_capacity = opts.queue_capacity
         self.opts = opts
         self._ctx = C.c_void_p()
         rc = cabi.lib.cb_create(C.byref(cfg), C.byref(self._ctx))

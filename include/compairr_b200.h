@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define CB_ABI_VERSION 2
+#define CB_ABI_VERSION 3
 
 typedef enum cb_status {
   CB_OK = 0,
@@ -80,8 +80,10 @@ typedef struct cb_config {
   uint32_t table_load_pct;          /* max hash-table load in percent (default 50)               */
   uint64_t pairs_capacity;          /* device pair-buffer capacity per launch, in pairs          */
   uint32_t flags;                   /* CB_FLAG_*                                                  */
-  uint32_t bloom_l2_cap_kib;        /* accepted and ignored (ABI v2 field of the former two-level */
-                                    /* filter; the parity filters need no L2-residency cap)       */
+  uint32_t queue_capacity;          /* d = 1, 2: entries of the candidate queue between the      */
+                                    /* enumeration and the table kernel (16 B each); 0 = sized    */
+                                    /* from the run, at most 2^26.  A queue that overflows only   */
+                                    /* costs time: the chunk of seeds is redone in smaller pieces */
 } cb_config;
 
 #define CB_FLAG_NO_SMEM_TILE 1u   /* accumulate straight into the global matrix (A/B testing)    */

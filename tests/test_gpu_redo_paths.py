@@ -1,0 +1,198 @@
+"""GPU parity for the product paths that only fire at size or under pressure, each forced at a size
+the CPU oracle finishes in seconds (reference semantics: src/overlap.cc:168-251 probe/accumulate,
+:455-507 pairs, :861-873 build):
+
+  * candidate-queue overflow -> the chunk is skipped by the table kernel and redone in smaller
+    pieces (engine.cu run_chunks), forced with cb_config.queue_capacity
+  * pair-buffer overflow -> second pass into an exact-size buffer (engine.cu cb_run), forced with
+    cb_config.pairs_capacity
+  * radix-partitioned table build (engine.cu cb_table_insert: table >= 256 MiB, >= 2^22 keys) — the
+    build every C3-sized bench step takes
+  * the BASELINE.json config shapes C4 (-d 2 -g -s min) and C5 (-x -n -d 2 -p --no-matrix, and the
+    d = 3 tensor-core path with (length, V, J) buckets)
+"""
+import numpy as np
+import pytest
+
+from compairr_b200 import Engine, OverlapOptions, cluster, overlap, synth
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def _pairs(p):
+    return sorted(map(tuple, np.asarray(p).tolist()))
+
+
+@pytest.fixture(scope="module")
+def dense_pair():
+    pool = synth.make_pool(101, 4000)
+    a = synth.make_set(102, 5, 3000, pool=pool, indel_mutants=True)
+    b = synth.make_set(103, 6, 3000, pool=pool, indel_mutants=True)
+    return a, b
+
+
+@pytest.mark.parametrize("d,indels", [(1, False), (1, True), (2, False)])
+@pytest.mark.parametrize("existence", [False, True])
+def test_queue_overflow_redo(dense_pair, d, indels, existence):
+    """A 256-entry candidate queue overflows on every chunk of more than a few dozen seeds: the
+    result must not change, whatever the number of redo levels."""
+    a, b = dense_pair
+    if existence:   # -x: set A is one repertoire (a view of the fixture with its own repertoire column)
+        a = a.slice(0, 4000)
+        a.rep = np.zeros(a.n, np.uint32)
+        a.n_reps = 1
+    kw = dict(differences=d, indels=indels, existence=existence)
+    mo, po, io = orc.overlap(a, b, want_pairs=True, threads=4, **kw)
+    for cap in (256, 4096):
+        m, p, info = overlap(a, b, OverlapOptions(want_pairs=True, queue_capacity=cap, **kw))
+        assert np.array_equal(m, mo)
+        assert _pairs(p) == _pairs(po)
+        assert info["run"]["matches"] == io["matches"] and info["run"]["probes"] == io["probes"]
+    m, _, info0 = overlap(a, b, OverlapOptions(**kw))
+    assert np.array_equal(m, mo)
+    # the redo really happened: more launches than the plain run
+    assert info["run"]["kernel_launches"] >= info0["run"]["kernel_launches"]
+
+
+@pytest.mark.parametrize("d,indels", [(0, False), (1, True), (2, False), (3, False)])
+@pytest.mark.parametrize("no_matrix", [False, True])
+def test_pairs_overflow_second_pass(dense_pair, d, indels, no_matrix):
+    """pairs_capacity = 16: every run overflows the device pair buffer and is redone for the pairs
+    alone; matrix and match counts come from the first pass and must not be touched by the second."""
+    a, b = dense_pair
+    kw = dict(differences=d, indels=indels)
+    mo, po, io = orc.overlap(a, b, want_pairs=True, threads=4, **kw)
+    assert len(po) > 16
+    m, p, info = overlap(a, b, OverlapOptions(want_pairs=True, pairs_capacity=16, no_matrix=no_matrix,
+                                              queue_capacity=4096 if d in (1, 2) else 0, **kw))
+    assert _pairs(p) == _pairs(po)
+    assert info["run"]["matches"] == io["matches"] and info["run"]["pairs"] == len(po)
+    if no_matrix:
+        assert m is None
+    else:
+        assert np.array_equal(m, mo)
+
+
+def test_pairs_overflow_across_chunked_runs(dense_pair):
+    """Several cb_run calls on one context, each overflowing the pair buffer: pending pairs
+    accumulate across calls, the matrix accumulates once per call."""
+    a, b = dense_pair
+    mo, po, _ = orc.overlap(a, b, differences=1, indels=True, want_pairs=True, threads=4)
+    with Engine(OverlapOptions(differences=1, indels=True, want_pairs=True, pairs_capacity=64,
+                               queue_capacity=1024), n_reps_a=a.n_reps) as eng:
+        db, da = eng.upload(b), eng.upload(a)
+        eng.build_b(db)
+        for first in range(0, a.n, 4000):
+            eng.run(da, first, min(4000, a.n - first))
+        assert np.array_equal(eng.matrix(), mo)
+        assert _pairs(eng.drain_pairs()) == _pairs(po)
+
+
+@pytest.mark.parametrize("d,indels", [(1, True), (2, False)])
+def test_cluster_network_with_tiny_queue_and_pair_buffer(d, indels):
+    """-c builds its network through the same kernels in pairs mode (cluster.cu): tiny queue and
+    pair buffer must give the reference's clusters."""
+    pool = synth.make_pool(111, 1500)
+    s = synth.make_set(112, 3, 1500, pool=pool, indel_mutants=True)
+    o_order, o_no, o_size, o_ncl, o_edges = orc.cluster(s, d, indels, False)
+    order, no, size, info = cluster(s, OverlapOptions(differences=d, indels=indels, queue_capacity=512,
+                                                      pairs_capacity=32))
+    assert info["clusters"] == o_ncl and info["edges"] == o_edges
+    assert np.array_equal(order, o_order) and np.array_equal(no, o_no) and np.array_equal(size, o_size)
+
+
+@pytest.fixture(scope="module")
+def partition_sized():
+    """Set B large enough for the partitioned build: 4.4e6 keys -> 2^24 slots = 256 MiB."""
+    pool = synth.make_pool(121, 400_000)
+    b = synth.make_set(122, 44, 100_000, pool=pool, indel_mutants=True, workers=4)
+    a = synth.make_set(123, 8, 10_000, pool=pool, indel_mutants=True)
+    return a, b
+
+
+@pytest.mark.parametrize("kw", [dict(differences=0), dict(differences=1, indels=True), dict(differences=2, ignore_genes=True)])
+def test_partitioned_build_vs_oracle(partition_sized, kw):
+    a, b = partition_sized
+    if kw["differences"] == 2:
+        a = a.slice(0, 20_000)
+    with Engine(OverlapOptions(**kw), n_reps_a=a.n_reps) as eng:
+        db = eng.upload(b)
+        eng.build_b(db)
+        st = eng.stats()
+        assert st["table_slots"] * 16 >= 256 << 20
+        assert st["kernel_launches"] >= 3 + 4       # clear, reset, insert, dups + iota and the radix passes
+        dups = eng.dups_b()
+        da = eng.upload(a)
+        eng.run(da)
+        m, run = eng.matrix(), eng.stats()
+        # the same set built WITHOUT the partition sort gives the same table contents
+        with Engine(OverlapOptions(flags=8, **kw), n_reps_a=a.n_reps) as eng2:
+            db2 = eng2.upload(b)
+            eng2.build_b(db2)
+            assert eng2.stats()["kernel_launches"] < st["kernel_launches"]
+            assert eng2.dups_b() == dups
+            da2 = eng2.upload(a)
+            eng2.run(da2)
+            assert np.array_equal(eng2.matrix(), m)
+    mo, _, io = orc.overlap(a, b, threads=8, **kw)
+    assert np.array_equal(m, mo)
+    assert run["matches"] == io["matches"] and run["probes"] == io["probes"]
+    assert dups == orc.count_dups(b, ignore_genes=kw.get("ignore_genes", False))
+
+
+def test_c4_shape_d2_ignore_genes_min(partition_sized):
+    """BASELINE config 4: -m -d 2 -g -s min (Jaccard's summand), two sets."""
+    a, b = partition_sized
+    a_s, b_s = a.slice(0, 30_000), b.slice(0, 600_000)
+    m, _, info = overlap(a_s, b_s, OverlapOptions(differences=2, ignore_genes=True, score="min"))
+    mo, _, io = orc.overlap(a_s, b_s, differences=2, ignore_genes=True, score="min", threads=8)
+    assert np.array_equal(m, mo)
+    assert info["run"]["matches"] == io["matches"] and info["run"]["probes"] == io["probes"]
+    assert info["run"]["matches"] > a_s.n // 4
+
+
+@pytest.fixture(scope="module")
+def c5_sets():
+    """BASELINE config 5: a nucleotide query set in ONE repertoire against a multi-repertoire set."""
+    pool = synth.make_pool(131, 30_000)
+    b = synth.make_set(132, 20, 10_000, pool=pool, nucleotides=True)
+    q = synth.make_set(133, 10, 10_000, pool=pool, nucleotides=True, single_repertoire=True)
+    return q, b
+
+
+def test_c5_shape_existence_nt_d2_pairs_no_matrix(c5_sets):
+    """-x -n -d 2 -p --no-matrix on 10^5 queries: the pair list is the whole result."""
+    q, b = c5_sets
+    kw = dict(differences=2, existence=True)
+    m, p, info = overlap(q, b, OverlapOptions(nucleotides=True, want_pairs=True, no_matrix=True,
+                                              pairs_capacity=1 << 12, **kw))
+    _, po, io = orc.overlap(q, b, want_pairs=True, want_matrix=False, threads=8, **kw)
+    assert m is None
+    assert _pairs(p) == _pairs(po)
+    assert info["run"]["matches"] == io["matches"] and info["run"]["probes"] == io["probes"]
+    # with the matrix: rows are query sequences (overlap.cc:226)
+    m, _, _ = overlap(q.slice(0, 20_000), b, OverlapOptions(nucleotides=True, **kw))
+    mo, _, _ = orc.overlap(q.slice(0, 20_000), b, threads=8, **kw)
+    assert m.shape == (20_000, b.n_reps) and np.array_equal(m, mo)
+
+
+@pytest.mark.parametrize("nucleotides", [True, False])
+def test_d3_tensor_core_with_vj_buckets(nucleotides):
+    """d = 3 WITHOUT -g: the joins are (length, V, J) buckets.  Few genes make them large enough for
+    the tcgen05 kernel; the result must equal the CUDA-core kernel's and the oracle's."""
+    pool = synth.make_pool(141, 3000)
+    a = synth.make_set(142, 4, 4000, pool=pool, nucleotides=nucleotides, single_repertoire=False)
+    b = synth.make_set(143, 5, 6000, pool=pool, nucleotides=nucleotides)
+    for s in (a, b):
+        s.v_gene %= 3
+        s.j_gene %= 2
+    kw = dict(differences=3)
+    m, p, info = overlap(a, b, OverlapOptions(want_pairs=True, nucleotides=nucleotides, **kw))
+    mo, po, io = orc.overlap(a, b, want_pairs=True, threads=8, **kw)
+    assert np.array_equal(m, mo) and _pairs(p) == _pairs(po)
+    assert info["run"]["matches"] == io["matches"]
+    m2, p2, info2 = overlap(a, b, OverlapOptions(want_pairs=True, nucleotides=nucleotides, flags=4, **kw))
+    assert np.array_equal(m2, mo) and _pairs(p2) == _pairs(po)
+    # the two runs really took different kernels
+    assert info["run"]["kernel_launches"] != info2["run"]["kernel_launches"]
