@@ -51,7 +51,7 @@ class cb_stats(C.Structure):
         ("matches", C.c_uint64), ("pairs", C.c_uint64), ("table_slots", C.c_uint64),
         ("bloom_bytes", C.c_uint64), ("bloom2_bytes", C.c_uint64), ("ms_hash_b", C.c_float), ("ms_build_b", C.c_float),
         ("ms_dups_b", C.c_float), ("ms_hash_a", C.c_float), ("ms_probe", C.c_float),
-        ("ms_total_run", C.c_float), ("kernel_launches", C.c_uint32), ("reserved", C.c_uint32),
+        ("ms_total_run", C.c_float), ("kernel_launches", C.c_uint32), ("ms_gather_b", C.c_float),
     ]
 
     def as_dict(self):
@@ -75,6 +75,7 @@ SYMBOLS = [
     ("cb_get_hashes", C.c_int, [P, P, P]),
     ("cb_build_b", C.c_int, [P, P]),
     ("cb_dups_b", C.c_uint64, [P]),
+    ("cb_resident_b", P, [P]),
     ("cb_count_dups", C.c_int, [P, P, C.POINTER(C.c_uint64)]),
     ("cb_dedup", C.c_int, [P, P, P, P, C.POINTER(C.c_uint64)]),
     ("cb_cluster", C.c_int, [P, P, P, P, P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
@@ -83,6 +84,13 @@ SYMBOLS = [
     ("cb_set_b_cols", C.c_int, [P, C.POINTER(cb_set_cols)]),
     ("cb_run_a", C.c_int, [P, C.POINTER(cb_set)]),
     ("cb_run_a_cols", C.c_int, [P, C.POINTER(cb_set_cols)]),
+    ("cb_comm_unique_id", C.c_int, [P]),
+    ("cb_comm_init_rank", C.c_int, [P, P, C.c_int, C.c_int]),
+    ("cb_comm_init_all", C.c_int, [C.POINTER(P), C.c_int]),
+    ("cb_comm_rank", C.c_int, [P, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("cb_shard_range", None, [C.c_uint64, C.c_int, C.c_int, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
+    ("cb_set_b_sharded", C.c_int, [P, C.POINTER(cb_set_cols), C.c_uint64]),
+    ("cb_allreduce_matrix", C.c_int, [P]),
     ("cb_matrix_dims", C.c_int, [P, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]),
     ("cb_get_matrix", C.c_int, [P, P, C.c_size_t]),
     ("cb_clear_matrix", C.c_int, [P]),
@@ -96,7 +104,24 @@ SYMBOLS = [
 ]
 
 
+def _preload_nccl():
+    """libcompairr_b200.so links libnccl.so.2.  In a process that also imports torch the NCCL that
+    torch was built against (the wheel's nvidia/nccl/lib) must be the one both use, whichever of the
+    two is imported first: map it before our library so the loader resolves the soname to it."""
+    try:
+        import importlib.util
+        spec = importlib.util.find_spec("nvidia.nccl")
+        for d in (spec.submodule_search_locations if spec else []):
+            so = os.path.join(d, "lib", "libnccl.so.2")
+            if os.path.exists(so):
+                C.CDLL(so, mode=C.RTLD_GLOBAL)
+                return
+    except Exception:
+        pass   # the system libnccl.so.2 is used
+
+
 def load():
+    _preload_nccl()
     if not os.path.exists(LIB_PATH):
         raise ImportError(
             f"{LIB_PATH} is not built. This package has no CPU fallback; build the CUDA library "

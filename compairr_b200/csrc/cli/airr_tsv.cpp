@@ -458,7 +458,7 @@ void read_airr_tsv(const char* filename, const Options& o, bool require_sequence
   const size_t body = (size_t)(end - p);
   unsigned hw = std::thread::hardware_concurrency();
   if (hw == 0) hw = 1;
-  unsigned n_thr = o.threads > 1 ? (unsigned)o.threads : std::min(hw, 32u);
+  unsigned n_thr = (o.threads_given || o.threads > 1) ? (unsigned)o.threads : std::min(hw, 32u);
   size_t min_bytes = 1 << 20;  // per thread; COMPAIRR_B200_READ_MIN_BYTES lets tests split small files
   if (const char* e = getenv("COMPAIRR_B200_READ_MIN_BYTES")) min_bytes = std::max<size_t>(1, strtoull(e, nullptr, 10));
   n_thr = (unsigned)std::max<size_t>(1, std::min<size_t>(n_thr, body / min_bytes));

@@ -139,7 +139,7 @@ void cluster_command(const Options& o, FILE* outfile) {
   progress_begin(o, "Writing clusters: ");
   fprintf(outfile, "#cluster_no\tcluster_size\trepertoire_id\tsequence_id\tduplicate_count\tv_call\tj_call\t%s\n",
           o.seq_header);
-  write_rows_parallel(outfile, n, host_threads(o.threads), [&](uint64_t k0, uint64_t k1, std::string& buf) {
+  write_rows_parallel(outfile, n, host_threads(o.threads, o.threads_given), [&](uint64_t k0, uint64_t k1, std::string& buf) {
     for (uint64_t k = k0; k < k1; k++) {
       const uint64_t a = order[k];
       append_u64(buf, no[k]);
@@ -188,7 +188,7 @@ void dedup_command(const Options& o, FILE* outfile) {
   fprintf(g_log, "Duplicates merged: %lu\n", (unsigned long)merged);
 
   progress_begin(o, "Writing output:   ");
-  write_rows_parallel(outfile, n, host_threads(o.threads), [&](uint64_t i0, uint64_t i1, std::string& buf) {
+  write_rows_parallel(outfile, n, host_threads(o.threads, o.threads_given), [&](uint64_t i0, uint64_t i1, std::string& buf) {
     for (uint64_t i = i0; i < i1; i++) {
       if (leader[i] != i) continue;  // a group is reported once, at its first member
       buf += d.rep_names[d.rep[i]];

@@ -184,7 +184,10 @@ void parse_args(int argc, char** argv, Options& o) {
       case 'o': o.output = optarg; break;
       case 'p': o.pairs = optarg; break;
       case 's': o.score_string = optarg; break;
-      case 't': o.threads = parse_long(optarg, "-t or --threads"); break;
+      case 't':
+        o.threads = parse_long(optarg, "-t or --threads");
+        o.threads_given = true;
+        break;
       case 'u': o.ignore_unknown = true; break;
       case 'v': o.version = true; break;
       case 'x': o.existence = true; break;

@@ -21,6 +21,7 @@ struct Options {
   int64_t differences = 0;
   int64_t score = 0;  // reference enum order: product ratio min max mean mh jaccard
   int64_t threads = 1;
+  bool threads_given = false;  // an explicit -t (also -t 1) sizes the host-side reader and writers
   const char* input1 = nullptr;
   const char* input2 = nullptr;
   const char* seq_header = "junction_aa";

@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -124,7 +125,7 @@ struct PairWriter {
   }
   // rows formatted on the host threads (-t, default: all), written in the order of p[] (row_writer.h)
   void write(const cb_pair* p, size_t n) const {
-    write_rows_parallel(f, n, host_threads(o.threads), [&](uint64_t k0, uint64_t k1, std::string& buf) {
+    write_rows_parallel(f, n, host_threads(o.threads, o.threads_given), [&](uint64_t k0, uint64_t k1, std::string& buf) {
       for (uint64_t k = k0; k < k1; k++) {
         const uint64_t a = p[k].a, b = p[k].b;
         side(buf, d1, a);
@@ -211,8 +212,10 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
 
   const uint64_t R1 = d1.rep_names.size(), R2 = d2.rep_names.size(), N1 = d1.n();
   const int ngpu = std::min<int>(o.gpus, std::max(1, cb_device_count() - o.device));
+  if (ngpu != o.gpus) fprintf(g_log, "GPUs used:         %d (of %d requested)\n", ngpu, o.gpus);
 
-  // ---- engine: one context per GPU, set B replicated, set A sharded --------------------------
+  // ---- engine: one context per GPU joined in an NCCL communicator; every GPU gets all of set B
+  // (each uploads 1/ngpu of it, all-gather over NVLink) and a shard of set A ----------------------
   cb_config cfg{};
   cfg.abi_version = CB_ABI_VERSION;
   cfg.alphabet_size = o.alphabet_size;
@@ -234,22 +237,38 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
     cfg.device = o.device + g;
     if (cb_create(&cfg, &ctx[g])) engine_fatal(nullptr);
   }
+  if (ngpu > 1 && cb_comm_init_all(ctx.data(), ngpu)) engine_fatal(ctx[0]);
   mark("contexts created");
-  const cb_set whole_b = as_cb_set(d2, 0, d2.n());
-  std::vector<cb_dset*> dev_b(ngpu, nullptr);
+  // a failure on one GPU ends the command at once: the other ranks may be waiting in a collective
+  auto rank_fatal = [&](cb_ctx* c) {
+    fprintf(stderr, "\nError: %s\n", cb_last_error(c));
+    cli_exit(1);
+  };
+  auto cols_of = [](const SeqDb& d, uint64_t first, uint64_t n) {
+    cb_set_cols s{};
+    s.n = n;
+    s.residues = d.residues.data();
+    s.offsets = {d.offsets.data() + first, 8, 0};
+    s.v_gene = {d.v.data() + first, 4, 0};
+    s.j_gene = {d.j.data() + first, 4, 0};
+    s.rep = {d.rep.data() + first, 4, 0};
+    s.count = {d.count.data() + first, 8, 0};
+    s.n_reps = (uint32_t)d.rep_names.size();
+    s.index_base = first;
+    return s;
+  };
 
-  progress_begin(o, "Hashing sequences:");  // upload + hash + table/Bloom build + duplicate check
+  progress_begin(o, "Hashing sequences:");  // upload + hash (+ all-gather) + table/filter build + duplicate check
   {
     std::vector<std::thread> th;
-    std::vector<int> rc(ngpu, 0);
     for (int g = 0; g < ngpu; g++)
       th.emplace_back([&, g] {
-        rc[g] = cb_upload(ctx[g], &whole_b, &dev_b[g]);
-        if (!rc[g]) rc[g] = cb_build_b(ctx[g], dev_b[g]);
+        uint64_t first = 0, count = d2.n();
+        cb_shard_range(d2.n(), g, ngpu, &first, &count);
+        const cb_set_cols shard = cols_of(d2, first, count);
+        if (cb_set_b_sharded(ctx[g], &shard, d2.n())) rank_fatal(ctx[g]);
       });
     for (auto& t : th) t.join();
-    for (int g = 0; g < ngpu; g++)
-      if (rc[g]) engine_fatal(ctx[g]);
   }
   progress_end(o, "Hashing sequences:");
   mark("set B uploaded + built");
@@ -291,8 +310,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
     bound[ngpu] = N1;
   }
   const uint64_t chunk = o.pairs || o.existence ? (1u << 20) : N1 + 1;  // bound host memory for pairs / -x rows
-  std::vector<std::string> errors(ngpu);
-  std::vector<std::vector<cb_pair>> pair_out(ngpu);
+  std::mutex pairs_mu;  // pairs of every GPU go to the file chunk by chunk (their order is unspecified, README.md:163)
   {
     std::vector<std::thread> th;
     for (int g = 0; g < ngpu; g++)
@@ -300,55 +318,41 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
         cb_ctx* c = ctx[g];
         const bool self_dev = !two_sets;  // set A is the resident set B
         cb_dset* da = nullptr;
-        if (bound[g + 1] == bound[g]) return;
         const bool reuse = whole_a_dev != nullptr;  // one GPU: the dup check left set 1 resident
-        if (self_dev) {
-          da = dev_b[g];
-        } else if (reuse) {
-          da = whole_a_dev;
-        } else {
-          const cb_set shard = as_cb_set(d1, bound[g], bound[g + 1] - bound[g]);
-          if (cb_upload(c, &shard, &da)) { errors[g] = cb_last_error(c); return; }
+        if (bound[g + 1] > bound[g]) {
+          if (self_dev) {
+            da = cb_resident_b(c);
+          } else if (reuse) {
+            da = whole_a_dev;
+          } else {
+            const cb_set shard = as_cb_set(d1, bound[g], bound[g + 1] - bound[g]);
+            if (cb_upload(c, &shard, &da)) rank_fatal(c);
+          }
         }
-        const uint64_t base = self_dev ? bound[g] : 0;  // range inside the device set
+        const uint64_t base = (self_dev || reuse) ? bound[g] : 0;  // range inside the device set
+        std::vector<cb_pair> pair_out;
         for (uint64_t at = bound[g]; at < bound[g + 1]; at += chunk) {
           const uint64_t n = std::min(chunk, bound[g + 1] - at);
-          if (cb_run(c, da, base + (at - bound[g]), n)) { errors[g] = cb_last_error(c); break; }
-          if (o.existence && !o.no_matrix) {
-            if (cb_get_matrix(c, matrix.data() + at * R2, n * R2)) { errors[g] = cb_last_error(c); break; }
-          }
+          if (cb_run(c, da, base + (at - bound[g]), n)) rank_fatal(c);
+          if (o.existence && !o.no_matrix && cb_get_matrix(c, matrix.data() + at * R2, n * R2)) rank_fatal(c);
           if (o.pairs) {
             uint64_t np = 0;
             cb_pairs_pending(c, &np);
-            const size_t old = pair_out[g].size();
-            pair_out[g].resize(old + np);
+            pair_out.resize(np);
             size_t got = 0;
-            cb_drain_pairs(c, pair_out[g].data() + old, np, &got);
-            if (ngpu == 1) {  // single GPU: stream pairs out chunk by chunk
-              pw.write(pair_out[g].data(), pair_out[g].size());
-              pair_out[g].clear();
-            }
+            cb_drain_pairs(c, pair_out.data(), np, &got);
+            std::lock_guard<std::mutex> lk(pairs_mu);
+            pw.write(pair_out.data(), got);
           }
         }
-        if (!self_dev && !reuse) cb_free_set(c, da);
+        if (da && !self_dev && !reuse) cb_free_set(c, da);
+        // -m: the sum of the partial matrices (sim_thread's merge, overlap.cc:510-527) is an NCCL
+        // all-reduce; every rank joins, also one whose shard was empty
+        if (!o.existence && !o.no_matrix && ngpu > 1 && cb_allreduce_matrix(c)) rank_fatal(c);
       });
     for (auto& t : th) t.join();
   }
-  for (int g = 0; g < ngpu; g++)
-    if (!errors[g].empty()) {
-      fprintf(stderr, "\nError: %s\n", errors[g].c_str());
-      cli_exit(1);
-    }
-  if (!o.existence && !o.no_matrix) {  // sum of the per-GPU partial matrices
-    std::vector<double> part(rows * R2);
-    for (int g = 0; g < ngpu; g++) {
-      if (bound[g + 1] == bound[g]) continue;
-      if (cb_get_matrix(ctx[g], part.data(), part.size())) engine_fatal(ctx[g]);
-      for (size_t k = 0; k < part.size(); k++) matrix[k] += part[k];
-    }
-  }
-  if (o.pairs && ngpu > 1)
-    for (int g = 0; g < ngpu; g++) pw.write(pair_out[g].data(), pair_out[g].size());
+  if (!o.existence && !o.no_matrix && cb_get_matrix(ctx[0], matrix.data(), matrix.size())) engine_fatal(ctx[0]);
   progress_end(o, "Analysing:        ");
   mark("analysis done");
   // The engines are not torn down: main() leaves with _exit() once the files are on disk, and
@@ -357,7 +361,6 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
   if (getenv("COMPAIRR_B200_TEARDOWN")) {
     for (int g = 0; g < ngpu; g++) {
       if (g == 0 && whole_a_dev) cb_free_set(ctx[0], whole_a_dev);
-      cb_free_set(ctx[g], dev_b[g]);
       cb_destroy(ctx[g]);
     }
     mark("contexts destroyed");

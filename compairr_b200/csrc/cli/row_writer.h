@@ -58,11 +58,11 @@ void write_rows_parallel(FILE* f, uint64_t n_rows, int threads, Fn fn, uint64_t 
   for (auto& t : th) t.join();
 }
 
-// Host threads for the reader and the writers: -t N if given, else the machine's (at most 32).
-// The reference's -t 1 default means "one worker"; here the workers are on the GPU and -t only
-// sizes the host-side parsing and formatting, which never change a byte of the output.
-inline int host_threads(int64_t opt_threads) {
-  if (opt_threads > 1) return (int)opt_threads;
+// Host threads for the reader and the writers: -t N if given (also -t 1), else the machine's (at
+// most 32).  The reference's -t 1 default means "one worker"; here the workers are on the GPU and
+// -t only sizes the host-side parsing and formatting, which never change a byte of the output.
+inline int host_threads(int64_t opt_threads, bool given) {
+  if (given || opt_threads > 1) return (int)std::max<int64_t>(opt_threads, 1);
   const unsigned hw = std::thread::hardware_concurrency();
   return (int)std::max(1u, std::min(hw, 32u));
 }

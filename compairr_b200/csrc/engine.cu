@@ -230,6 +230,7 @@ extern "C" void cb_destroy(cb_ctx* c) {
   g_alloc_pool = c->pool;
   if (c->own_stream) cudaStreamSynchronize(c->own_stream);
   if (c->stream && c->stream != c->own_stream) cudaStreamSynchronize(c->stream);
+  cb_comm_release(c);
   if (c->b_owned) cb_free_dset(c->b);
   cb_dfree(c->d_ztab);
   cb_dfree(c->d_counters);
@@ -474,6 +475,8 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
 
 extern "C" uint64_t cb_dups_b(const cb_ctx* c) { return c ? c->dups_b : 0; }
 
+extern "C" cb_dset* cb_resident_b(cb_ctx* c) { return c ? c->b : nullptr; }
+
 extern "C" int cb_count_dups(cb_ctx* c, cb_dset* s, uint64_t* out) {
   if (!c || !s || !out) return fail(c, CB_ERR_INVALID, "cb_count_dups: NULL argument");
   int rc = bind(c);
@@ -570,13 +573,36 @@ static int ensure_pairs(cb_ctx* c, uint64_t cap) {
   return CB_OK;
 }
 
+// (Re)allocate the global candidate queue (16 B per entry) and point the launch parameters at it.
+static int size_queue(cb_ctx* c, ProbeParams& p, uint64_t cap) {
+  if (c->gq_cap != cap) {
+    cb_dfree(c->d_gq_hv);
+    cb_dfree(c->d_gq_vs);
+    c->d_gq_hv = nullptr;
+    c->d_gq_vs = nullptr;
+    c->gq_cap = 0;
+    CU(c, cb_dmalloc(&c->d_gq_hv, cap * sizeof(uint64_t)));
+    CU(c, cb_dmalloc(&c->d_gq_vs, cap * sizeof(uint2)));
+    c->gq_cap = cap;
+  }
+  if (!c->d_overflow) CU(c, cb_dmalloc(&c->d_overflow, 64 * sizeof(uint32_t)));
+  p.gq_hv = c->d_gq_hv;
+  p.gq_vs = c->d_gq_vs;
+  p.gq_cap = c->gq_cap;
+  p.overflow_chunks = c->d_overflow;
+  return CB_OK;
+}
+
 // d <= 2.  d = 0 is one kernel.  d = 1, 2 run in chunks of seeds: the enumeration kernel fills the
 // global candidate queue, the table kernel drains it.  A chunk whose candidates did not fit is
-// skipped by the table kernel (nothing accumulated) and redone here in smaller pieces.
+// skipped by the table kernel (nothing accumulated) and redone here in smaller pieces; if a single
+// seed does not fit (a hub sequence with more neighbours than the queue has entries) the queue
+// grows instead.
 static int run_chunks(cb_ctx* c, ProbeParams& p, uint64_t w_first, uint64_t w_count, uint64_t per_chunk,
                       int depth, int* launches) {
   std::vector<std::pair<uint64_t, uint64_t>> chunks;
   for (uint64_t at = 0; at < w_count; at += per_chunk) chunks.emplace_back(w_first + at, std::min(per_chunk, w_count - at));
+  if (chunks.size() > 64) return fail(c, CB_ERR_LIMIT, "cb_run: internal: more than 64 chunks in one pass");
   CU(c, cudaMemsetAsync(c->d_counters + CTR_OVERFLOW, 0, sizeof(unsigned long long), c->stream));
   for (size_t k = 0; k < chunks.size(); k++) {
     p.w_first = chunks[k].first;
@@ -599,19 +625,19 @@ static int run_chunks(cb_ctx* c, ProbeParams& p, uint64_t w_first, uint64_t w_co
   if (rc) return rc;
   const uint64_t over = c->h_counters[CTR_OVERFLOW];
   if (over == 0) return CB_OK;
-  if (depth >= 6 || per_chunk <= 1)
-    return fail(c, CB_ERR_LIMIT, "cb_run: candidate queue too small even for single seeds");
-  std::vector<uint32_t> ids(std::min<uint64_t>(over, 64));
+  std::vector<uint32_t> ids(std::min<uint64_t>(over, 64));  // <= 64 chunks per pass: every id was recorded
   CU(c, cudaMemcpyAsync(ids.data(), c->d_overflow, ids.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  if (over > 64) {  // more than we recorded: nothing of those chunks was accumulated, but we do not
-    // know which — cannot happen with <= 64 chunks; guard anyway
-    return fail(c, CB_ERR_LIMIT, "cb_run: too many overflowed chunks");
-  }
-  const uint64_t saved_matches = c->h_counters[CTR_MATCHES];
-  (void)saved_matches;
   for (uint32_t id : ids) {
-    rc = run_chunks(c, p, chunks[id].first, chunks[id].second, std::max<uint64_t>(per_chunk / 8, 1), depth + 1, launches);
+    if (per_chunk <= 1 || depth >= 8) {  // cannot cut finer: a bigger queue, same pieces
+      if (c->gq_cap >= (1ull << 30))
+        return fail(c, CB_ERR_LIMIT, "cb_run: one sequence has more than 2^30 candidate matches");
+      rc = size_queue(c, p, c->gq_cap * 4);
+      c->gq_cap_grown = true;
+      if (!rc) rc = run_chunks(c, p, chunks[id].first, chunks[id].second, per_chunk, depth, launches);
+    } else {
+      rc = run_chunks(c, p, chunks[id].first, chunks[id].second, std::max<uint64_t>(per_chunk / 8, 1), depth + 1, launches);
+    }
     if (rc) return rc;
   }
   return CB_OK;
@@ -644,22 +670,11 @@ static int run_hash_path(cb_ctx* c, ProbeParams& p, uint64_t count, int* launche
     while (cap < (1ull << 26) && (double)cap < want) cap <<= 1;
   }
   cap = std::max<uint64_t>(cap, 64);
-  if (c->cfg.queue_capacity ? c->gq_cap != cap : c->gq_cap < cap) {
-    cb_dfree(c->d_gq_hv);
-    cb_dfree(c->d_gq_vs);
-    c->d_gq_hv = nullptr;
-    c->d_gq_vs = nullptr;
-    c->gq_cap = 0;
-    CU(c, cb_dmalloc(&c->d_gq_hv, cap * sizeof(uint64_t)));
-    CU(c, cb_dmalloc(&c->d_gq_vs, cap * sizeof(uint2)));
-    c->gq_cap = cap;
-  }
+  if (!c->cfg.queue_capacity) cap = std::max(cap, c->gq_cap);  // it only grows
+  else if (c->gq_cap > cap && c->gq_cap_grown) cap = c->gq_cap;  // ... also past a configured size, once a seed needed it
+  int rcq = size_queue(c, p, cap);
+  if (rcq) return rcq;
   cap = c->gq_cap;
-  if (!c->d_overflow) CU(c, cb_dmalloc(&c->d_overflow, 64 * sizeof(uint32_t)));
-  p.gq_hv = c->d_gq_hv;
-  p.gq_vs = c->d_gq_vs;
-  p.gq_cap = cap;
-  p.overflow_chunks = c->d_overflow;
   // Seeds per chunk.  A small first chunk measures how many candidates a seed produces on this
   // data (it depends on d, on the filters' false-positive rate and on how much the sets overlap);
   // the rest runs in chunks sized to fill the queue at most half.  Few, large chunks matter for

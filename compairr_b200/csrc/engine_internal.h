@@ -82,11 +82,16 @@ struct cb_ctx {
   uint2* d_gq_vs = nullptr;
   uint32_t* d_overflow = nullptr;
   uint64_t gq_cap = 0;              // entries
+  bool gq_cap_grown = false;        // a single seed overflowed the configured queue: it was enlarged
   uint64_t run_res_bytes = 0;
   cb::PairOut* d_pairs = nullptr;
   uint64_t pairs_cap = 0;
   std::vector<cb_pair> pending;
   bool network_mode = false;  // cb_cluster: pairs carry their variant descriptor (cluster.cu)
+
+  // multi-GPU (comm.cu): NCCL communicator over the contexts that share the work
+  void* comm = nullptr;  // ncclComm_t
+  int rank = 0, world = 1;
 
   cb_stats stats{};
 };
@@ -109,6 +114,19 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out);
 void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n);
 int cb_adopt_table(cb_ctx* c, cb_dset* b, BuiltTable& t, bool owned);  // sets ctx fields, counts dups
 void cb_free_dset(cb_dset* s);
+
+// upload.cu: pack + hash one shard of a larger set at its place in device arrays sized for the whole
+struct cb_placement {
+  uint64_t n_total;    // sequences of the whole set (cb_dset.n)
+  uint64_t n_alloc;    // entries the record / hash arrays are allocated for (>= n_total)
+  uint64_t seq_first;  // index of the shard's first sequence
+  uint64_t res_total;  // bytes of the residue arena
+  uint64_t res_first;  // arena offset of the shard's first residue
+};
+int cb_upload_shard(cb_ctx* c, const cb_set_cols* shard, const cb_placement* pl, cb_dset** out);
+
+// comm.cu
+void cb_comm_release(cb_ctx* c);
 
 // brute.cu
 int cb_run_brute(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t count, bool pairs_only,

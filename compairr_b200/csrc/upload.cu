@@ -93,8 +93,10 @@ struct Staging {  // one of the two device staging buffers of the pipeline
   }
 };
 
-// The pipeline.  If `table` is given, every chunk is also inserted into it (set B).
-int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** out) {
+// The pipeline.  If `table` is given, every chunk is also inserted into it (set B).  With a
+// placement the host columns are one SHARD of a larger set: the device arrays are sized for the
+// whole set and the shard is packed and hashed at its place in them (comm.cu fills in the rest).
+int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** out, const cb_placement* pl = nullptr) {
   *out = nullptr;
   const bool len_mode = h.lengths.data != nullptr;
   if (h.n && !h.residues) return cb_fail(c, CB_ERR_INVALID, "upload: residues is NULL");
@@ -113,11 +115,12 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
   if (rc) return rc;
   cb_dset* s = new (std::nothrow) cb_dset;
   if (!s) return cb_fail(c, CB_ERR_NOMEM, "upload: out of host memory");
-  s->n = h.n;
+  s->n = pl ? pl->n_total : h.n;
   s->index_base = h.index_base;
   s->n_reps = h.n_reps;
   const uint64_t n = h.n;
-  if (n == 0) {
+  const uint64_t seq0 = pl ? pl->seq_first : 0, res0 = pl ? pl->res_first : 0;
+  if (pl ? pl->n_total == 0 : n == 0) {
     *out = s;
     return CB_OK;
   }
@@ -126,7 +129,7 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
 
   // chunking: ~16 chunks, between 256 Ki and 8 Mi sequences
   uint64_t chunk = std::min<uint64_t>(std::max<uint64_t>((n + 15) / 16, 1ull << 18), 1ull << 23);
-  const uint64_t n_chunks = (n + chunk - 1) / chunk;
+  const uint64_t n_chunks = n ? (n + chunk - 1) / chunk : 0;
   std::vector<uint64_t> res_begin(n_chunks + 1, 0);  // residue index where each chunk starts
   if (len_mode) {
     // per-chunk residue counts on the host, one thread per chunk (10^8 one-byte lengths are 16 ms
@@ -146,11 +149,15 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
       sum_range(0, n_chunks);
     }
     for (uint64_t k = 0; k < n_chunks; k++) res_begin[k + 1] = res_begin[k] + part[k];
-  } else {
+  } else if (n) {
     for (uint64_t k = 0; k <= n_chunks; k++) res_begin[k] = off[std::min(k * chunk, n)] - off[0];
   }
-  const uint64_t res_base = len_mode ? 0 : off[0];
+  const uint64_t res_base = (len_mode || !n) ? 0 : off[0];
   s->res_bytes = res_begin[n_chunks];
+  if (pl && res0 + s->res_bytes > pl->res_total) {
+    delete s;
+    return cb_fail(c, CB_ERR_INVALID, "upload: the shard's residues do not fit its place in the arena");
+  }
 
   Staging st[2];
   cudaStream_t cs = c->copy_stream, ks = c->stream;
@@ -170,9 +177,9 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
       return bail(e__ == cudaErrorMemoryAllocation ? CB_ERR_NOMEM : CB_ERR_CUDA, #expr, e__);         \
   } while (0)
 
-  UP(cb_dmalloc(&s->d_res, s->res_bytes + 16));
-  UP(cb_dmalloc(&s->d_meta, n * sizeof(SeqRec)));
-  UP(cb_dmalloc(&s->d_hash, n * sizeof(uint64_t)));
+  UP(cb_dmalloc(&s->d_res, (pl ? pl->res_total : s->res_bytes) + 16));
+  UP(cb_dmalloc(&s->d_meta, (pl ? pl->n_alloc : n) * sizeof(SeqRec)));
+  UP(cb_dmalloc(&s->d_hash, (pl ? pl->n_alloc : n) * sizeof(uint64_t)));
   for (auto& b : st) {
     UP(cb_dmalloc(&b.starts, (chunk + 1) * 8));
     if (len_mode) {
@@ -214,7 +221,7 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
     const uint64_t first = k * chunk, cn = std::min(chunk, n - first);
     if (k >= 2) UP(cudaStreamWaitEvent(cs, b.consumed, 0));
     const uint64_t rb = res_begin[k], rn = res_begin[k + 1] - rb;
-    UP(cudaMemcpyAsync(s->d_res + rb, h.residues + res_base + rb, rn, cudaMemcpyHostToDevice, cs));
+    UP(cudaMemcpyAsync(s->d_res + res0 + rb, h.residues + res_base + rb, rn, cudaMemcpyHostToDevice, cs));
     if (len_mode)
       UP(cudaMemcpyAsync(b.lengths, col_at(h.lengths, first), cn * h.lengths.width, cudaMemcpyHostToDevice, cs));
     else
@@ -235,17 +242,17 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
       UP(cub::DeviceScan::ExclusiveSum(b.scan_tmp, b.scan_bytes, b.wide, b.starts, (int64_t)cn, ks));
       pc.lengths = b.lengths;
       pc.len_w = h.lengths.width;
-      pc.res_add = rb;
+      pc.res_add = res0 + rb;
     } else {
-      pc.off_sub = res_base;
+      pc.off_sub = res_base - res0;  // wraps when the shard sits further up the arena than in the host's: off = o - off_sub still holds
     }
     pc.v = b.v; pc.v_w = h.v.width;
     pc.j = b.j; pc.j_w = h.j.width;
     pc.rep = b.rep; pc.rep_w = h.rep.width;
     pc.count = b.count; pc.count_w = h.count.width;
-    launch_pack_meta(pc, cn, s->d_meta + first, c->d_counters, ks);
-    launch_hash(s->d_meta + first, s->d_res, cn, c->d_ztab, zrows_used, sigma, c->cfg.seed,
-                c->cfg.ignore_genes != 0, s->d_hash + first, ks);
+    launch_pack_meta(pc, cn, s->d_meta + seq0 + first, c->d_counters, ks);
+    launch_hash(s->d_meta + seq0 + first, s->d_res, cn, c->d_ztab, zrows_used, sigma, c->cfg.seed,
+                c->cfg.ignore_genes != 0, s->d_hash + seq0 + first, ks);
     if (table) cb_table_insert(c, *table, s, first, cn);
     UP(cudaGetLastError());
     UP(cudaEventRecord(b.consumed, ks));
@@ -275,8 +282,8 @@ int upload_pipeline(cb_ctx* c, const HostCols& h, BuiltTable* table, cb_dset** o
       cb_free_dset(s);
       return rc;
     }
-    launch_hash(s->d_meta, s->d_res, n, c->d_ztab, c->zrows, sigma, c->cfg.seed, c->cfg.ignore_genes != 0,
-                s->d_hash, ks);
+    launch_hash(s->d_meta + seq0, s->d_res, n, c->d_ztab, c->zrows, sigma, c->cfg.seed, c->cfg.ignore_genes != 0,
+                s->d_hash + seq0, ks);
     if (table) {
       BuiltTable fresh;
       rc = cb_table_alloc(c, n, true, &fresh);
@@ -326,6 +333,15 @@ int set_b_impl(cb_ctx* c, const HostCols& h) {
   c->stats.kernel_launches = 0;
   return CB_OK;
 }
+
+}  // namespace
+
+// One shard of a larger set into its place (comm.cu).
+int cb_upload_shard(cb_ctx* c, const cb_set_cols* shard, const cb_placement* pl, cb_dset** out) {
+  return upload_pipeline(c, from_cols(shard), nullptr, out, pl);
+}
+
+namespace {
 
 int run_a_impl(cb_ctx* c, const HostCols& h) {
   cb_dset* d = nullptr;

@@ -1,17 +1,34 @@
-"""Multi-GPU plumbing: one process per GPU (torch.distributed), set A sharded, set B replicated,
-partial matrices summed with one allreduce (NCCL over NVLink on GPUs; gloo in the CPU tests).
+"""Multi-GPU driver: one rank per GPU, each with its own Engine joined in an NCCL communicator that
+lives INSIDE the library (csrc/comm.cu).  The path shards by set-A sequences — they are independent
+units against a read-only set-B table, which is how the reference threads it
+(src/overlap.cc:421-448):
 
-The path shards naturally — set-A sequences are independent units against a read-only set-B
-table, which is how the reference threads it (src/overlap.cc:421-448) — so the only collective is
-the sum of the R1 x R2 partial matrices (the reference's serial merge, overlap.cc:510-527).
-Existence mode shards matrix ROWS, so it needs a gather, not a reduce; pairs stay per rank."""
+  set B   every rank uploads 1/world of it over its own PCIe link (shard_range), the ranks
+          all-gather over NVLink and each builds the whole table          Engine.set_b_sharded
+  set A   contiguous ranges balanced by expected probes (plan_shards)     Engine.run_a
+  result  -m: sum of the partial matrices (the reference's merge, overlap.cc:510-527)
+                                                                          Engine.allreduce_matrix
+          -x: rows follow the A shards -> concatenated on the host; pairs stay per rank
+
+`overlap_rank` is that sequence for one rank.  It talks to the engine through the five methods named
+above, so the CPU test-suite can drive the same code with world_size-2 gloo processes and a host
+stand-in for the engine (tests/test_dist_gloo.py); bench.py and the multi-GPU tests pass the real
+Engine.  torch.distributed is only the host channel for the 128-byte communicator id."""
 from __future__ import annotations
 
-from typing import Callable, List, Optional, Tuple
+from typing import List, Optional, Tuple
 
 import numpy as np
 
-from .seqset import SeqSet
+from .seqset import NarrowSet, SeqSet
+
+
+def shard_range(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """(first, count) of set B that `rank` uploads: equal shards of ceil(n_total / world), the last
+    short or empty — the layout cb_set_b_sharded's in-place all-gather needs (= cb_shard_range)."""
+    per = -(-n_total // world) if world > 0 else n_total
+    first = min(n_total, per * max(rank, 0))
+    return first, min(per, n_total - first)
 
 
 def probe_weights(lengths: np.ndarray, sigma: int, differences: int, indels: bool) -> np.ndarray:
@@ -45,43 +62,43 @@ def plan_shards(lengths: np.ndarray, world: int, sigma: int = 20, differences: i
     return [(cuts[r], cuts[r + 1] - cuts[r]) for r in range(world)]
 
 
-def allreduce_matrix(matrix, group=None):
-    """Sum a partial matrix over all ranks, in place.  `matrix` is a torch tensor (CUDA for NCCL,
-    CPU for gloo)."""
-    import torch.distributed as dist
-    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(matrix, op=dist.ReduceOp.SUM, group=group)
-    return matrix
-
-
-def gather_rows(rows, counts: List[int], group=None):
-    """Existence mode: concatenate the per-rank row blocks (rank order = shard order)."""
+def exchange_unique_id(make_id, group=None) -> bytes:
+    """Rank 0 of the torch.distributed group makes the communicator id (make_id() -> 128 bytes,
+    Engine.comm_unique_id), everybody gets it.  Works over gloo (CPU tensor) and nccl (CUDA tensor)."""
     import torch
     import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return make_id()
+    dev = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
+    if dist.get_rank(group) == 0:
+        t = torch.frombuffer(bytearray(make_id()), dtype=torch.uint8).to(dev)
+    else:
+        t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=0, group=group)
+    return bytes(t.cpu().numpy().tobytes())
+
+
+def gather_rows(rows: np.ndarray, group=None) -> np.ndarray:
+    """Existence mode: concatenate the per-rank row blocks in rank order (= shard order)."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return rows
-    world = dist.get_world_size(group)
-    cols = rows.shape[1]
-    most = max(counts)   # all_gather wants equal shapes: pad to the largest shard, trim after
-    mine = torch.zeros((most, cols), dtype=rows.dtype, device=rows.device)
-    mine[: rows.shape[0]] = rows
-    bufs = [torch.empty((most, cols), dtype=rows.dtype, device=rows.device) for _ in range(world)]
-    dist.all_gather(bufs, mine, group=group)
-    return torch.cat([bufs[r][: counts[r]] for r in range(world)], dim=0)
+    parts = [None] * dist.get_world_size(group)
+    dist.all_gather_object(parts, rows, group=group)
+    return np.concatenate(parts, axis=0)
 
 
-def sharded_overlap(a: SeqSet, b: Optional[SeqSet], compute: Callable, rank: int, world: int,
-                    differences: int = 1, indels: bool = False, existence: bool = False,
-                    device="cpu", group=None):
-    """Rank-local driver: run `compute(a_shard, b) -> (rows x cols numpy matrix)` on this rank's
-    shard of set A and combine.  In matrix mode every rank returns the full summed matrix; in
-    existence mode the full row-concatenated matrix.  `compute` is the GPU engine in production
-    (see bench.py) and anything with the same signature in tests."""
-    import torch
-    shards = plan_shards(a.lengths, world, a.sigma, differences, indels)
-    first, count = shards[rank]
-    part = compute(a.slice(first, count), b if b is not None else a)
-    t = torch.as_tensor(np.ascontiguousarray(part), device=device)
+def overlap_rank(eng, a: SeqSet, b: SeqSet, rank: int, world: int, differences: int = 1, indels: bool = False,
+                 existence: bool = False, group=None) -> Optional[np.ndarray]:
+    """This rank's part of `compairr -m/-x a b` on `world` GPUs; returns the complete matrix (on
+    every rank).  `eng` has joined the communicator already (Engine.comm_init_rank)."""
+    first, count = shard_range(b.n, rank, world)
+    shard = NarrowSet.from_seqset(b.slice(first, count))
+    shard.n_reps = b.n_reps
+    eng.set_b_sharded(shard, b.n)
+    f, c = plan_shards(a.lengths, world, a.sigma, differences, indels)[rank]
+    eng.run_a(a.slice(f, c))        # the slice carries index_base = f: pairs and -x rows are global
     if existence:
-        return gather_rows(t, [c for _, c in shards], group).cpu().numpy()
-    return allreduce_matrix(t, group).cpu().numpy()
+        return gather_rows(eng.matrix(), group)
+    eng.allreduce_matrix()
+    return eng.matrix()

@@ -182,6 +182,39 @@ class Engine:
             cs = _cb_set_cols(s)
             self._check(cabi.lib.cb_set_b_cols(self._ctx, C.byref(cs)))
 
+    # -- multi-GPU: NCCL communicator inside the library (csrc/comm.cu)
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(128)
+        rc = cabi.lib.cb_comm_unique_id(buf)
+        if rc:
+            raise EngineError(rc, cabi.lib.cb_global_error().decode())
+        return buf.raw
+
+    def comm_init_rank(self, unique_id: bytes, rank: int, world: int):
+        """Collective: every rank's engine calls it with the id made by one of them."""
+        self._check(cabi.lib.cb_comm_init_rank(self._ctx, C.c_char_p(unique_id), rank, world))
+
+    def comm_rank(self):
+        r, w = C.c_int(), C.c_int()
+        self._check(cabi.lib.cb_comm_rank(self._ctx, C.byref(r), C.byref(w)))
+        return r.value, w.value
+
+    def set_b_sharded(self, shard, n_total: int):
+        """shard: NarrowSet of this rank's cb_shard_range of set B (n_reps of the WHOLE set).
+        Collective: upload 1/world over PCIe, all-gather over NVLink, build locally."""
+        cs = _cb_set_cols(shard)
+        self._check(cabi.lib.cb_set_b_sharded(self._ctx, C.byref(cs), n_total))
+
+    def allreduce_matrix(self):
+        """Collective: sum of the partial matrices of all ranks, in place (ncclAllReduce)."""
+        self._check(cabi.lib.cb_allreduce_matrix(self._ctx))
+
+    def resident_b(self) -> Optional[DeviceSet]:
+        """The context's set B as a DeviceSet (not to be freed), for self-comparison runs."""
+        h = cabi.lib.cb_resident_b(self._ctx)
+        return DeviceSet(self, None if not h else C.c_void_p(h), 0, 0) if h else None
+
     def dups_b(self) -> int:
         return int(cabi.lib.cb_dups_b(self._ctx))
 
@@ -255,6 +288,21 @@ class Engine:
         st = cabi.cb_stats()
         self._check(cabi.lib.cb_get_stats(self._ctx, C.byref(st)))
         return st.as_dict()
+
+
+def comm_init_all(engines):
+    """All engines in this process (one per GPU) -> one communicator, engines[i] = rank i."""
+    arr = (C.c_void_p * len(engines))(*[e._ctx for e in engines])
+    rc = cabi.lib.cb_comm_init_all(arr, len(engines))
+    if rc:
+        raise EngineError(rc, (cabi.lib.cb_last_error(engines[0]._ctx) or cabi.lib.cb_global_error()).decode())
+
+
+def shard_range(n_total: int, rank: int, world: int):
+    """cb_shard_range: the slice of a set that `rank` uploads in set_b_sharded."""
+    f, n = C.c_uint64(), C.c_uint64()
+    cabi.lib.cb_shard_range(n_total, rank, world, C.byref(f), C.byref(n))
+    return int(f.value), int(n.value)
 
 
 def probe_count(residues: np.ndarray, sigma: int, differences: int, indels: bool) -> int:

@@ -14,9 +14,10 @@
  *     available from cb_last_error().  The library never calls exit() (the reference's
  *     fatal(), src/util.cc:84-88, is the CLI's job).
  *   - one context drives ONE GPU and must be used from one host thread at a time.  Multi-GPU is
- *     one context (one process, or one host thread) per GPU, each given a shard of set A and
- *     the whole of set B; partial matrices are summed by the caller (NCCL allreduce on
- *     cb_matrix_device(), or host add).
+ *     one context (one process, or one host thread) per GPU joined in an NCCL communicator
+ *     (cb_comm_*): every context gets the whole of set B — each rank uploads 1/world of it and the
+ *     ranks all-gather over NVLink (cb_set_b_sharded) — and a shard of set A; the partial
+ *     matrices are summed by cb_allreduce_matrix.
  *   - there is no CPU fallback: if no CUDA device is usable, cb_create() fails.
  */
 #ifndef COMPAIRR_B200_H
@@ -169,7 +170,7 @@ typedef struct cb_stats {
   float ms_probe;           /* enumerate + Bloom + probe + verify + accumulate kernel(s)          */
   float ms_total_run;       /* whole cb_run_* device span                                         */
   uint32_t kernel_launches; /* kernels launched by the call                                       */
-  uint32_t reserved;
+  float ms_gather_b;        /* cb_set_b_sharded: the NVLink all-gather of records, hashes, residues */
 } cb_stats;
 
 typedef struct cb_ctx cb_ctx;
@@ -212,6 +213,10 @@ int cb_get_hashes(cb_ctx *ctx, const cb_dset *set, uint64_t *out);
    Bloom filter over every sequence of the set and counts exact duplicates (dup2). The context
    keeps a reference to the set; free it only after the context is done with it. */
 int cb_build_b(cb_ctx *ctx, cb_dset *b);
+/* The context's current set B as a resident set (NULL if none), e.g. to run it against itself
+   after cb_set_b / cb_set_b_sharded (self-comparison, overlap.cc:799-825).  Owned by the context
+   when it came from host arrays: do not free it. */
+cb_dset *cb_resident_b(cb_ctx *ctx);
 /* Exact duplicates found while building (reference dup2, overlap.cc:861-873). */
 uint64_t cb_dups_b(const cb_ctx *ctx);
 /* Replaces check_duplicates() (overlap.cc:579-605) for an arbitrary resident set (dup1). */
@@ -251,6 +256,34 @@ int cb_set_b_cols(cb_ctx *ctx, const cb_set_cols *b);
 int cb_run_a(cb_ctx *ctx, const cb_set *a);
 int cb_run_a_cols(cb_ctx *ctx, const cb_set_cols *a);
 
+/* ---- multi-GPU: one context per GPU, NCCL over NVLink ---------------------------------------- */
+
+#define CB_UNIQUE_ID_BYTES 128
+/* A fresh communicator id (ncclGetUniqueId) into out[CB_UNIQUE_ID_BYTES]: made by one rank, carried
+   to the others by the caller (any host channel), passed by all to cb_comm_init_rank. */
+int cb_comm_unique_id(void *out);
+/* One process (or host thread) per GPU: join a communicator of `world` contexts as `rank`.
+   Collective: returns when all ranks have called it.  All contexts must have been created with
+   the same options and seed. */
+int cb_comm_init_rank(cb_ctx *ctx, const void *unique_id, int rank, int world);
+/* All contexts in ONE process (the CLI's --gpus N): ctxs[i] becomes rank i of n. */
+int cb_comm_init_all(cb_ctx **ctxs, int n);
+int cb_comm_rank(const cb_ctx *ctx, int *rank, int *world);
+/* The shard of a set of n_total sequences that `rank` of `world` holds for cb_set_b_sharded:
+   [first, first + count) with equal shards of ceil(n_total / world) (the last may be short or
+   empty).  Host helper, no GPU work. */
+void cb_shard_range(uint64_t n_total, int rank, int world, uint64_t *first, uint64_t *count);
+/* cb_set_b for a communicator: `shard` = this rank's cb_shard_range of set B (columns as in
+   cb_set_b_cols; n_reps = repertoires of the WHOLE set).  Each rank copies only its shard across
+   PCIe, packs and hashes it; records, hashes and residues are all-gathered over NVLink; every
+   rank then builds the table and the filters of the whole set (the reference's one shared table,
+   src/overlap.cc:861-873, replicated per GPU).  Collective.  Sequence indices (pairs, existence
+   rows) are those of the whole set. */
+int cb_set_b_sharded(cb_ctx *ctx, const cb_set_cols *shard, uint64_t n_total);
+/* Sum the partial matrices of all ranks in place (ncclAllReduce, f64): replaces the merge of the
+   per-thread matrices, src/overlap.cc:510-527.  Matrix mode.  Collective; a no-op for world 1. */
+int cb_allreduce_matrix(cb_ctx *ctx);
+
 /* ---- results ------------------------------------------------------------------------------- */
 
 /* Matrix mode: n_reps_a x n_reps_b doubles, row-major, indexed by the repertoire numbers the
@@ -259,13 +292,12 @@ int cb_run_a_cols(cb_ctx *ctx, const cb_set_cols *a);
 int cb_matrix_dims(const cb_ctx *ctx, uint64_t *rows, uint64_t *cols);
 int cb_get_matrix(cb_ctx *ctx, double *out, size_t n_values);
 int cb_clear_matrix(cb_ctx *ctx);
-/* Device pointer of the matrix (for an NCCL allreduce in the caller's process); valid until
-   the next call that reallocates it (cb_run in existence mode) or cb_destroy. */
+/* Device pointer of the matrix; valid until the next call that reallocates it (cb_run in
+   existence mode) or cb_destroy. */
 void *cb_matrix_device(cb_ctx *ctx);
 /* Accumulate into a caller-owned DEVICE buffer of rows x cols doubles instead of the context's
-   own (matrix mode only; rows must equal n_reps_a).  Lets the caller's process run an NCCL
-   allreduce on its own allocation.  The buffer is not cleared and not freed by the engine;
-   NULL returns to the engine-owned matrix. */
+   own (matrix mode only; rows must equal n_reps_a).  The buffer is not cleared and not freed by
+   the engine; NULL returns to the engine-owned matrix. */
 int cb_bind_matrix(cb_ctx *ctx, void *device_ptr, uint64_t rows, uint64_t cols);
 /* Host → device: overwrite the matrix (used after an external reduction). */
 int cb_set_matrix(cb_ctx *ctx, const double *in, size_t n_values);

@@ -65,6 +65,8 @@ def lib():
         _lib.orc_enumerate.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_void_p,
                                        C.c_void_p, C.c_uint32, C.c_uint64]
         _lib.orc_free.argtypes = [C.c_void_p]
+        _lib.orc_write_tsv.restype = C.c_int
+        _lib.orc_write_tsv.argtypes = [C.POINTER(orc_set), C.c_char_p, C.c_char_p, C.c_int, C.c_uint64]
     return _lib
 
 
@@ -107,6 +109,15 @@ def overlap(a, b=None, differences=0, indels=False, ignore_genes=False, ignore_c
     info = {"probes": res.probes, "bloom_pass": res.bloom_pass, "matches": res.matches,
             "seconds_build": res.seconds_build, "seconds_probe": res.seconds_probe}
     return m, pairs, info
+
+
+def write_tsv(s, path: str, id_prefix: str = "s") -> None:
+    """SeqSet -> AIRR TSV, the same bytes as SeqSet.write_tsv for sets with default names, ~100x
+    faster (10^8-line bench inputs)."""
+    assert s.rep_names is None and s.v_names is None and s.j_names is None and s.seq_ids is None
+    ss = _set(s)
+    if lib().orc_write_tsv(C.byref(ss), path.encode(), id_prefix.encode(), int(s.nucleotides), s.index_base):
+        raise OSError(f"cannot write {path}")
 
 
 def count_dups(s, ignore_genes=False) -> int:

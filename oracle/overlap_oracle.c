@@ -14,6 +14,7 @@
 #include "overlap_oracle.h"
 
 #include <pthread.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <time.h>
@@ -488,3 +489,55 @@ uint64_t orc_enumerate(const uint8_t *seq, uint32_t len, int alphabet_size, int 
 }
 
 void orc_free(void *p) { free(p); }
+
+/* ---- AIRR TSV writer for bench inputs (the reference binary and the CLI read files) ----------- */
+/* Same text as SeqSet.write_tsv (compairr_b200/seqset.py): columns repertoire_id, sequence_id,
+   duplicate_count, v_call, j_call, junction_aa|junction; names R%04u, <prefix><index>, TRBV%02u,
+   TRBJ%02u.  Plain buffered formatting: ~10^7 lines per second. */
+static char *put_u64(char *p, uint64_t v) {
+  char t[24];
+  int n = 0;
+  do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  while (n) *p++ = t[--n];
+  return p;
+}
+static char *put_pad(char *p, uint64_t v, int width) {
+  char t[24];
+  int n = 0;
+  do { t[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+  for (int k = n; k < width; k++) *p++ = '0';
+  while (n) *p++ = t[--n];
+  return p;
+}
+int orc_write_tsv(const orc_set *s, const char *path, const char *id_prefix, int nucleotides,
+                  uint64_t index_base) {
+  FILE *f = fopen(path, "w");
+  if (!f) return -1;
+  const char *alpha = nucleotides ? "ACGT" : "ACDEFGHIKLMNPQRSTVWY";
+  const size_t cap = 1u << 22, plen = strlen(id_prefix);
+  char *buf = malloc(cap + 4096);
+  if (!buf) { fclose(f); return -1; }
+  char *p = buf;
+  p += sprintf(p, "repertoire_id\tsequence_id\tduplicate_count\tv_call\tj_call\t%s\n", nucleotides ? "junction" : "junction_aa");
+  int bad = 0;
+  for (uint64_t i = 0; i < s->n && !bad; i++) {
+    const uint64_t len = s->offsets[i + 1] - s->offsets[i];
+    if ((size_t)(p - buf) + len + 256 + plen > cap) {
+      bad |= fwrite(buf, 1, (size_t)(p - buf), f) != (size_t)(p - buf);
+      p = buf;
+      if (len + 256 + plen > cap) { bad = 1; break; }
+    }
+    *p++ = 'R'; p = put_pad(p, s->rep[i], 4); *p++ = '\t';
+    memcpy(p, id_prefix, plen); p += plen; p = put_u64(p, i + index_base); *p++ = '\t';
+    p = put_u64(p, s->count ? s->count[i] : 1); *p++ = '\t';
+    memcpy(p, "TRBV", 4); p += 4; p = put_pad(p, (uint64_t)(s->v_gene ? s->v_gene[i] : 0) + 1, 2); *p++ = '\t';
+    memcpy(p, "TRBJ", 4); p += 4; p = put_pad(p, (uint64_t)(s->j_gene ? s->j_gene[i] : 0) + 1, 2); *p++ = '\t';
+    const uint8_t *r = s->residues + s->offsets[i];
+    for (uint64_t k = 0; k < len; k++) *p++ = alpha[r[k]];
+    *p++ = '\n';
+  }
+  if (!bad) bad |= fwrite(buf, 1, (size_t)(p - buf), f) != (size_t)(p - buf);
+  free(buf);
+  if (fclose(f)) bad = 1;
+  return bad ? -1 : 0;
+}

@@ -71,6 +71,11 @@ uint64_t orc_enumerate(const uint8_t *seq, uint32_t len, int alphabet_size, int 
 
 void orc_free(void *p);
 
+/* Write a set as an AIRR TSV file (inputs of the reference binary / the CLI in bench.py and the
+   tests): the same text as SeqSet.write_tsv.  Returns 0 on success. */
+int orc_write_tsv(const orc_set *s, const char *path, const char *id_prefix, int nucleotides,
+                  uint64_t index_base);
+
 #ifdef __cplusplus
 }
 #endif

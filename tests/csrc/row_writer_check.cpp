@@ -43,7 +43,7 @@ int main() {
           return 1;
         }
   }
-  if (host_threads(7) != 7 || host_threads(1) < 1) return 3;
+  if (host_threads(7, true) != 7 || host_threads(1, false) < 1 || host_threads(1, true) != 1) return 3;
   printf("row_writer_check ok\n");
   return 0;
 }
