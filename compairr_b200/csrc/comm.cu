@@ -156,10 +156,9 @@ extern "C" int cb_set_b_sharded(cb_ctx* c, const cb_set_cols* shard, uint64_t n_
   uint64_t my_res = 0;
   if (shard->n) {
     if (shard->lengths.data) {
-      const unsigned char* p = (const unsigned char*)shard->lengths.data;
       const uint32_t w = shard->lengths.width;
-      for (uint64_t i = 0; i < shard->n; i++)
-        my_res += w == 1 ? p[i] : w == 2 ? ((const uint16_t*)p)[i] : ((const uint32_t*)p)[i];
+      if (w != 1 && w != 2 && w != 4) return cb_fail(c, CB_ERR_INVALID, "cb_set_b_sharded: lengths must be 1, 2 or 4 bytes wide");
+      my_res = cb_sum_lengths(shard->lengths.data, w, shard->n);
     } else if (shard->offsets.data && shard->offsets.width == 8) {
       const uint64_t* o = (const uint64_t*)shard->offsets.data;
       my_res = o[shard->n] - o[0];

@@ -752,6 +752,7 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     p.pairs_cap = c->pairs_cap;
     p.counters = c->d_counters;
     p.lmax = a->longest;
+    p.force_generic = (c->cfg.flags & CB_FLAG_GENERIC_KERNEL) ? 1u : 0u;
     // one matrix row in shared memory per CTA (d=1 kernel) when it is small enough
     p.tile_cols = (!existence && !c->cfg.no_matrix && !(c->cfg.flags & CB_FLAG_NO_SMEM_TILE) && cols <= 4096)
                       ? (uint32_t)cols : 0;

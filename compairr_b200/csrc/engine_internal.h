@@ -123,6 +123,7 @@ struct cb_placement {
   uint64_t res_total;  // bytes of the residue arena
   uint64_t res_first;  // arena offset of the shard's first residue
 };
+uint64_t cb_sum_lengths(const void* p, uint32_t w, uint64_t n);
 int cb_upload_shard(cb_ctx* c, const cb_set_cols* shard, const cb_placement* pl, cb_dset** out);
 
 // comm.cu

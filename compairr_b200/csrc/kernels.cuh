@@ -59,7 +59,9 @@ struct ProbeParams {
   PairOut* pairs;
   uint64_t pairs_cap;
   unsigned long long* counters;
-  uint32_t lmax;   // longest seed in the launch (sizes the per-warp scratch)
+  uint32_t lmax;   // longest seed of the set (decides which enumeration kernels are launched)
+  uint32_t len_lo, len_hi;  // an enumeration launch handles the seeds with len_lo <= length <= len_hi
+  uint32_t force_generic;   // A/B and tests: every seed through the generic (any-length) kernel
   uint32_t tile_cols;  // > 0: CTAs keep one matrix row (n_cols doubles) in shared memory
   uint32_t split;  // d=2: work items per seed
   int32_t score;

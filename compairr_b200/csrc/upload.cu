@@ -336,6 +336,20 @@ int set_b_impl(cb_ctx* c, const HostCols& h) {
 
 }  // namespace
 
+// Sum of n lengths of width w (1, 2 or 4 bytes) on up to 16 host threads.
+uint64_t cb_sum_lengths(const void* p, uint32_t w, uint64_t n) {
+  const uint64_t n_thr = n >= (1ull << 22) ? 16 : 1;
+  if (n_thr == 1) return sum_lengths(p, w, 0, n);
+  std::vector<uint64_t> part(n_thr, 0);
+  std::vector<std::thread> pool;
+  for (uint64_t t = 0; t < n_thr; t++)
+    pool.emplace_back([&, t] { part[t] = sum_lengths(p, w, t * n / n_thr, (t + 1) * n / n_thr - t * n / n_thr); });
+  for (auto& th : pool) th.join();
+  uint64_t s = 0;
+  for (uint64_t x : part) s += x;
+  return s;
+}
+
 // One shard of a larger set into its place (comm.cu).
 int cb_upload_shard(cb_ctx* c, const cb_set_cols* shard, const cb_placement* pl, cb_dset** out) {
   return upload_pipeline(c, from_cols(shard), nullptr, out, pl);

@@ -1,25 +1,36 @@
-// variant.cu — K3/K4 for d = 1 and d = 2: on-the-fly variant enumeration by incremental XOR,
-// Bloom prefilter(s), table probe, exact verify, score, matrix accumulation, pair append
-// (replaces generate_variants_1/_2, variants.cc:270-400; bloom_get, bloompat.h:55-58;
-// find_variant_matches, overlap.cc:168-251; check_variant, variants.cc:166-240).
+// variant.cu — K3 for d = 1 and d = 2: on-the-fly variant enumeration by incremental XOR and the
+// parity-filter test (replaces generate_variants_1/_2, variants.cc:270-400; bloom_get,
+// bloompat.h:55-58), and K4, the table stage (find_variant_matches, overlap.cc:168-251;
+// check_variant, variants.cc:166-240).
 //
-// Structure of both kernels (one warp works on one seed at a time):
+// Enumeration, round-2 design: ONE LANE PER SLOT, A LOOP OVER THE RESIDUES.
 //
-//   enumerate  every lane decodes VK_U candidates per step from the seed's index spaces and XORs
-//              their hashes together from shared-memory Zobrist values
-//   filter     VK_U independent 8-byte loads per lane from the PARITY FILTERS (common.cuh): the
-//              filter is chosen by the parity of the candidate's free position, which makes the
-//              word address the same for all candidates at positions of that parity — the 32
-//              loads of a warp step fall into one or two sectors and are served by L1 after the
-//              first touch, instead of 32 random L2 sectors
-//   queue      survivors are compacted (ballot + prefix popcount) into a per-warp ring in shared
-//              memory; 32 at a time they are appended, coalesced, to the global candidate queue
-//              that the table kernel (K4, own launch) drains
+//   A "slot" is a place where a free residue goes: a substitution at position p, an insertion
+//   before position p, or — for d = 2 — the second substitution (j, .) of a triple (i, v, j).  All
+//   sigma candidates of a slot share
+//       base2   the variant's hash minus the Zobrist value of the free residue,
+//       word    their filter word (parity filters, common.cuh: the word index does not depend on
+//               the free residue),
+//       zrow    the column of the TRANSPOSED Zobrist table (zT[r * ZP + pos]) their values sit in,
+//   so a lane that owns a slot keeps all of that in registers and the inner loop over the residues
+//   is one shared-memory load (lanes differ in pos, the residue is uniform), two XORs and the
+//   pattern test per candidate — no decode, no per-candidate table lookups, no vote.  Passing
+//   residues are collected in a per-lane bit mask; the (rare) survivors are extracted after the
+//   loop and compacted into the warp's ring.  Round 1's loop decoded every candidate (q / sigma),
+//   loaded base, compare residue and word from shared memory and voted per step: 50 warp
+//   instructions per 32 candidates plus ~480 per seed of scans and slot tables.
 //
-// variant1_kernel (d = 1): warps stage batches of 8 consecutive seeds (metadata, hashes, residues)
-// into shared memory with coalesced loads, so the per-seed dependent global loads are paid once per
-// batch.  variant2_kernel (d = 2): seeds are heavy (~36 000 probes), warps take (seed, part) items
-// from a global dispenser.
+//   d = 1   warps take batches of WB consecutive seeds; the batch's slots (L substitution + L+1
+//           insertion slots per seed) form one flat list that the lanes walk 32 at a time, so
+//           lanes stay busy whatever the lengths are.  The three XOR scans that the indel variants
+//           need (prefix, and the two shifted suffixes; they replace the reference's serial walks,
+//           variants.cc:311-324,341-353) are computed for the whole batch at once, one LANE per
+//           (seed, scan), serially — 24 lanes x L steps instead of 3 x 5 shuffle rounds per seed.
+//   d = 2   a warp takes a (seed, part) item; its slots are the (i < j, v) triples, 19 L (L-1) / 2
+//           of them, again walked 32 at a time; the slot's word is fetched one pass ahead.
+//
+// Seeds longer than the fast kernels' tables (30 residues for ZP = 32, 94 for ZP = 96) go to the
+// generic kernel below (any length up to 510), in a launch of its own.
 #include <algorithm>
 
 #include "device_utils.cuh"
@@ -30,20 +41,13 @@ namespace cb {
 constexpr int VK_THREADS = 256;
 constexpr int VK_WARPS = VK_THREADS / 32;
 constexpr int VK_QCAP = 64;  // ring entries per warp
-constexpr int VK_U = 4;      // probes per lane per step: 4 independent filter loads in flight per lane
-constexpr int VK_WB = 8;     // seeds per warp batch (d = 1)
-#ifndef VK_D1_CTAS
-#define VK_D1_CTAS 3          // resident CTAs per SM the d = 1 kernel is compiled for
-#endif
+constexpr int VK_U = 4;      // generic kernel: probes per lane per step
 
-// Per-warp shared-memory block, addressed from ONE base pointer to keep the register footprint of
-// the enumeration loop small:
-//   [0, 1024)     survivor ring: hv[64] u64 | var[64] u32 | seed[64] u32
-//   [1024, ...)   seed scratch: zo[lpad] (+ pre[lpad], sm[lpad], sp[lpad] with indels), u64 each
+// Per-warp survivor ring: hv[64] u64 | var[64] u32 | seed[64] u32
 constexpr uint32_t VK_Q_BYTES = VK_QCAP * 16;
 
 struct WarpCtx {
-  unsigned char* wb;  // per-warp block
+  unsigned char* wb;     // per-warp block (ring first)
   uint32_t head, count;  // ring state
   uint32_t lane;
 };
@@ -88,7 +92,6 @@ __device__ __forceinline__ void ring_drain(const ProbeParams& P, WarpCtx& c, uin
   c.count -= n;
 }
 
-// One lane-step's verdicts into the pipeline.
 template <typename MkVar>
 __device__ __forceinline__ void submit(const ProbeParams& P, WarpCtx& c, bool pass, uint64_t hv,
                                        MkVar mkvar, uint32_t seed) {
@@ -101,8 +104,377 @@ __device__ __forceinline__ void finish(const ProbeParams& P, WarpCtx& c) {
   while (c.count) ring_drain(P, c, c.count < 32 ? c.count : 32);
 }
 
-// VK_U filter lookups per lane: all loads first (VK_U words in flight per lane), then the tests.
-// odd[u] = parity of candidate u's free position (which filter, common.cuh).
+// =====================================================================================================
+// Fast kernels
+// =====================================================================================================
+
+// What a lane keeps for its slot (see the header).
+struct SlotRegs {
+  uint64_t base2;
+  unsigned long long word;
+  const uint64_t* zrow;  // &zT[pos]; residue r's value is zrow[r * ZP]
+  uint32_t allowed;      // bit r: residue r is a candidate here (0: idle lane)
+  uint32_t emask;        // ~0: free position even (pattern field hi ^ lo), 0: odd (pattern field lo)
+  uint32_t var;          // variant descriptor without the free residue
+  uint32_t seed;         // seed number relative to a_first
+};
+
+// The inner loop: all SIGMA residues of every lane's slot.  RSHIFT: where the free residue goes in
+// the descriptor (3 = res1: substitution / insertion, 8 = res2: second substitution).
+template <int SIGMA, int ZP, int RSHIFT>
+__device__ __forceinline__ void residue_loop(const ProbeParams& P, WarpCtx& c, const SlotRegs& R) {
+  const uint32_t wlo = (uint32_t)R.word, whi = (uint32_t)(R.word >> 32);
+  uint32_t hits = 0;
+#pragma unroll
+  for (int r = 0; r < SIGMA; r++) {
+    const uint64_t hv = R.base2 ^ R.zrow[r * ZP];
+    const uint32_t lo = (uint32_t)hv, hi = (uint32_t)(hv >> 32);
+    const uint32_t f = lo ^ (hi & R.emask);
+    uint32_t a = shr_wrap(wlo, f) & shr_wrap(wlo, f >> 5);
+    uint32_t b = shr_wrap(whi, f >> 15) & shr_wrap(whi, f >> 20);
+    if (CB_PATTERN_HALF_BITS >= 3) {
+      a &= shr_wrap(wlo, f >> 10);
+      b &= shr_wrap(whi, f >> 25);
+    }
+    if (a & b & 1u) hits |= 1u << r;
+  }
+  hits &= R.allowed;
+  // survivors: a fraction of a percent of the candidates (false positives + true matches)
+  while (__any_sync(FULL, hits != 0)) {
+    const bool pass = hits != 0;
+    const uint32_t r = pass ? (uint32_t)__ffs((int)hits) - 1u : 0u;
+    const uint64_t hv = R.base2 ^ R.zrow[r * ZP];
+    const uint32_t var = R.var | (r << RSHIFT);
+    submit(P, c, pass, hv, [var] { return var; }, R.seed);
+    hits &= hits - 1;
+  }
+}
+
+__device__ __forceinline__ unsigned long long filter_word(const ProbeParams& P, uint64_t h, bool odd_free) {
+  return P.use_bloom ? __ldg(P.bloom + pfilter_word(h, P.bloom_blocks, odd_free)) : ~0ull;
+}
+
+// Transposed Zobrist table into shared memory: zT[r * ZP + p] = Z(p, r), rows beyond the table 0.
+template <int SIGMA, int ZP>
+__device__ __forceinline__ void stage_zt(const ProbeParams& P, uint64_t* zT) {
+  for (uint32_t i = threadIdx.x; i < SIGMA * ZP; i += VK_THREADS) {
+    const uint32_t r = i / ZP, p = i - r * ZP;
+    zT[i] = p < P.zrows ? P.ztab[p * SIGMA + r] : 0ull;
+  }
+}
+
+// ---- d = 1 -------------------------------------------------------------------------------------------
+
+template <int ZP>
+struct E1Cfg {
+  static constexpr int WB = ZP <= 32 ? 8 : 4;  // seeds per warp batch
+  static constexpr uint32_t LMAX = ZP - 2;     // longest seed: insertion slot L uses row L, the suffix scan row q + 1
+};
+
+constexpr uint32_t LEN_SKIP = 0xffffffffu;  // a seed of the batch that this launch does not handle
+
+// per-warp shared-memory block of the d = 1 kernel (host and device must agree)
+template <int ZP, bool INDELS>
+struct E1Layout {
+  static constexpr int WB = E1Cfg<ZP>::WB;
+  static constexpr size_t scan_u64 = INDELS ? (size_t)WB * 3 * ZP : 0;  // pre | sp | sm, [WB][ZP] each
+  static constexpr size_t off_scan = VK_Q_BYTES;
+  static constexpr size_t off_hash = off_scan + scan_u64 * 8;           // [WB] u64
+  static constexpr size_t off_ws = off_hash + WB * 8;                   // [WB][2] u64
+  static constexpr size_t off_len = off_ws + WB * 16;                   // [WB] u32
+  static constexpr size_t off_cum = off_len + WB * 4;                   // [WB + 1] u32, residue slots
+  static constexpr size_t off_dcum = off_cum + (WB + 1) * 4;            // [WB + 1] u32, deletion + identical items
+  static constexpr size_t off_res = (off_dcum + (WB + 1) * 4 + 15) & ~(size_t)15;  // [WB][ZP] u8
+  static constexpr size_t warp_bytes = (off_res + (size_t)WB * ZP + 15) & ~(size_t)15;
+  static constexpr size_t total(int sigma) { return (size_t)sigma * ZP * 8 + VK_WARPS * warp_bytes; }
+};
+
+template <int SIGMA, bool INDELS, int ZP>
+__global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_constant__ ProbeParams P) {
+  using Lay = E1Layout<ZP, INDELS>;
+  constexpr int WB = Lay::WB;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t* const zT = reinterpret_cast<uint64_t*>(smem_raw);
+  WarpCtx c;
+  c.wb = smem_raw + (size_t)SIGMA * ZP * 8 + warp * Lay::warp_bytes;
+  c.head = c.count = 0;
+  c.lane = lane;
+  uint64_t* const scan = reinterpret_cast<uint64_t*>(c.wb + Lay::off_scan);
+  uint64_t* const pre = scan;                       // pre[k][p]  = xor_{q<p}  Z(q,     s[q])
+  uint64_t* const sp = scan + (size_t)WB * ZP;      // sp[k][p]   = xor_{q>=p} Z(q + 1, s[q])
+  uint64_t* const sm = scan + (size_t)2 * WB * ZP;  // sm[k][p]   = xor_{q>=p} Z(q - 1, s[q])
+  uint64_t* const b_hash = reinterpret_cast<uint64_t*>(c.wb + Lay::off_hash);
+  unsigned long long* const b_ws = reinterpret_cast<unsigned long long*>(c.wb + Lay::off_ws);
+  uint32_t* const b_len = reinterpret_cast<uint32_t*>(c.wb + Lay::off_len);
+  uint32_t* const b_cum = reinterpret_cast<uint32_t*>(c.wb + Lay::off_cum);
+  uint32_t* const b_dcum = reinterpret_cast<uint32_t*>(c.wb + Lay::off_dcum);
+  uint8_t* const b_res = c.wb + Lay::off_res;
+
+  stage_zt<SIGMA, ZP>(P, zT);
+  __syncthreads();
+  const uint64_t n_batches = (P.w_count + WB - 1) / WB;
+  constexpr uint32_t ALL = (SIGMA >= 32) ? 0xffffffffu : ((1u << SIGMA) - 1u);
+
+  for (;;) {
+    unsigned long long b = 0;
+    if (lane == 0) b = atomicAdd(P.counters + CTR_WORK, 1ull);
+    b = __shfl_sync(FULL, b, 0);
+    if (b >= n_batches) break;
+    const uint64_t first = P.w_first + b * WB;  // relative to a_first
+    const uint32_t nb = (uint32_t)((P.w_first + P.w_count - first < WB) ? P.w_first + P.w_count - first : WB);
+    __syncwarp();  // previous batch fully consumed
+
+    // ---- stage the batch: lengths, hashes, residues, the two words of each seed's substitution slots
+    uint64_t my_off = 0;
+    uint32_t my_len = LEN_SKIP;
+    if (lane < nb) {
+      const uint64_t off_len = __ldg(&P.a.meta[P.a_first + first + lane].off_len);
+      const uint32_t L = (uint32_t)(off_len >> 40);
+      my_off = off_len & ((1ull << 40) - 1);
+      if (L >= P.len_lo && L <= P.len_hi) my_len = L;
+    }
+    if (lane < 2 * nb) {  // filter O for even positions, filter E for odd ones (the word index ignores the substituted residue)
+      const uint64_t hk = __ldg(P.a.hash + P.a_first + first + (lane >> 1));
+      if (lane & 1) b_hash[lane >> 1] = hk;
+      b_ws[lane] = filter_word(P, hk, lane & 1);
+    }
+    {  // slot and item counts -> inclusive prefix sums over the WB seeds
+      const bool live = my_len != LEN_SKIP;
+      uint32_t ns = live ? (INDELS ? 2 * my_len + 1 : my_len) : 0;
+      uint32_t nd = live ? (INDELS ? my_len + 1 : 1) : 0;
+#pragma unroll
+      for (int o = 1; o < WB; o <<= 1) {
+        const uint32_t xs = __shfl_up_sync(FULL, ns, o), xd = __shfl_up_sync(FULL, nd, o);
+        if ((int)lane >= o) {
+          ns += xs;
+          nd += xd;
+        }
+      }
+      if (lane < WB) {
+        b_len[lane] = my_len;
+        b_cum[lane + 1] = ns;
+        b_dcum[lane + 1] = nd;
+      }
+      if (lane == 0) b_cum[0] = b_dcum[0] = 0;
+    }
+#pragma unroll
+    for (int k = 0; k < WB; k++) {  // residues: one row of ZP bytes per seed
+      const uint32_t Lk = __shfl_sync(FULL, my_len, k);
+      const uint64_t ok = __shfl_sync(FULL, my_off, k);
+      if (Lk != LEN_SKIP)
+        for (uint32_t p = lane; p < Lk; p += 32) b_res[k * ZP + p] = __ldg(P.a.res + ok + p);
+    }
+    __syncwarp();
+
+    // ---- the three scans of every seed of the batch, one lane per (scan, seed) -------------------------
+    if (INDELS) {
+      const uint32_t which = lane / WB, k = lane % WB;  // 0 pre, 1 sp, 2 sm
+      const uint32_t L = which < 3 ? b_len[k] : LEN_SKIP;
+      if (L != LEN_SKIP) {
+        uint64_t* const arr = scan + ((size_t)which * WB + k) * ZP;
+        const uint8_t* const s = b_res + k * ZP;
+        uint64_t x = 0;
+        arr[which == 0 ? 0 : L] = 0ull;
+        for (uint32_t t = 0; t < L; t++) {
+          const uint32_t q = which == 0 ? t : L - 1 - t;
+          const int zp = (int)q + (which == 0 ? 0 : which == 1 ? 1 : -1);
+          x ^= zp >= 0 ? zT[s[q] * ZP + zp] : 0ull;
+          arr[which == 0 ? q + 1 : q] = x;
+        }
+      }
+      __syncwarp();
+    }
+
+    // ---- residue slots of the batch, 32 at a time ---------------------------------------------------------
+    const uint32_t n_slots = b_cum[WB];
+    auto load_slot = [&](uint32_t g) {
+      SlotRegs R;
+      const bool valid = g < n_slots;
+      if (!valid) g = 0;
+      uint32_t k = 0;
+#pragma unroll
+      for (int j = 1; j < WB; j++) k += g >= b_cum[j];
+      const uint32_t L = b_len[k], pp = g - b_cum[k];
+      const bool sub = !INDELS || pp < L;
+      const uint32_t pos = sub ? pp : pp - L;
+      const uint64_t h = b_hash[k];
+      uint32_t cmp;
+      if (sub) {
+        cmp = b_res[k * ZP + pos];
+        R.base2 = h ^ zT[cmp * ZP + pos];
+        R.word = b_ws[2 * k + (pos & 1)];
+        R.var = pack_var(VK_SUBSTITUTION, pos, 0, 0, 0);
+      } else {  // insertion before position pos: the new residue sits at position pos of the variant;
+                // not the residue before it, which would repeat a variant (variants.cc:341-353)
+        cmp = pos ? b_res[k * ZP + pos - 1] : 31u;
+        R.base2 = h ^ pre[k * ZP + L] ^ pre[k * ZP + pos] ^ sp[k * ZP + pos];
+        R.word = filter_word(P, R.base2, pos & 1);
+        R.var = pack_var(VK_INSERTION, pos, 0, 0, 0);
+      }
+      R.allowed = valid ? (ALL & ~(1u << cmp)) : 0u;
+      R.emask = (pos & 1) ? 0u : ~0u;
+      R.zrow = zT + pos;
+      R.seed = (uint32_t)first + k;
+      return R;
+    };
+    if (n_slots) {
+      SlotRegs cur = load_slot(lane);
+      for (uint32_t g0 = 0; g0 < n_slots; g0 += 32) {
+        SlotRegs nxt = cur;
+        if (g0 + 32 < n_slots) nxt = load_slot(g0 + 32 + lane);  // the next pass's words are in flight during this one
+        residue_loop<SIGMA, ZP, 3>(P, c, cur);
+        cur = nxt;
+      }
+    }
+
+    // ---- deletions (one per run of equal residues, only if L > 1, variants.cc:301-325) and the
+    // identical candidate of every seed: one candidate per item ---------------------------------------------
+    const uint32_t n_items = b_dcum[WB];
+    for (uint32_t g0 = 0; g0 < n_items; g0 += 32) {
+      uint32_t g = g0 + lane;
+      const bool in = g < n_items;
+      if (!in) g = 0;
+      uint32_t k = 0;
+#pragma unroll
+      for (int j = 1; j < WB; j++) k += g >= b_dcum[j];
+      const uint32_t L = b_len[k], t = g - b_dcum[k];
+      const bool is_del = INDELS && t < L;
+      const uint64_t h = b_hash[k];
+      uint64_t hv = h;
+      bool valid = in;
+      unsigned long long w = b_ws[2 * k + 1];  // identical: filter E, whose word for the seed's own hash is the odd one
+      if (is_del) {
+        hv = h ^ pre[k * ZP + L] ^ pre[k * ZP + t] ^ sm[k * ZP + t + 1];
+        valid = in && L > 1 && (t == 0 || b_res[k * ZP + t] != b_res[k * ZP + t - 1]);
+        w = filter_word(P, hv, true);
+      }
+      const bool pass = valid & pattern_hit(w, field_odd(hv));
+      submit(P, c, pass, hv, [is_del, t] {
+        return is_del ? pack_var(VK_DELETION, t, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0);
+      }, (uint32_t)first + k);
+    }
+  }
+  finish(P, c);
+}
+
+// ---- d = 2 -------------------------------------------------------------------------------------------
+
+template <int ZP>
+struct E2Layout {
+  static constexpr uint32_t LMAX = ZP - 2;
+  static constexpr uint32_t NPAIR = LMAX * (LMAX - 1) / 2;
+  static constexpr size_t off_res = VK_Q_BYTES;                  // [ZP] u8 per warp
+  static constexpr size_t warp_bytes = (off_res + ZP + 15) & ~(size_t)15;
+  static constexpr size_t pair_bytes = ((size_t)NPAIR * 2 + 15) & ~(size_t)15;
+  static constexpr size_t total(int sigma) { return (size_t)sigma * ZP * 8 + pair_bytes + VK_WARPS * warp_bytes; }
+};
+
+template <int SIGMA, int ZP>
+__global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_constant__ ProbeParams P) {
+  using Lay = E2Layout<ZP>;
+  constexpr uint32_t S1 = SIGMA - 1;
+  constexpr uint32_t ALL = (1u << SIGMA) - 1u;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  uint64_t* const zT = reinterpret_cast<uint64_t*>(smem_raw);
+  // pair e = j (j - 1) / 2 + i  (i < j): independent of the seed's length, a seed of length L owns e < L (L - 1) / 2
+  uint16_t* const pairtab = reinterpret_cast<uint16_t*>(smem_raw + (size_t)SIGMA * ZP * 8);
+  WarpCtx c;
+  c.wb = smem_raw + (size_t)SIGMA * ZP * 8 + Lay::pair_bytes + warp * Lay::warp_bytes;
+  c.head = c.count = 0;
+  c.lane = lane;
+  uint8_t* const sres = c.wb + Lay::off_res;
+
+  stage_zt<SIGMA, ZP>(P, zT);
+  for (uint32_t j = 1 + threadIdx.x; j < Lay::LMAX; j += VK_THREADS)
+    for (uint32_t i = 0; i < j; i++) pairtab[j * (j - 1) / 2 + i] = (uint16_t)(i | (j << 8));
+  __syncthreads();
+
+  const uint64_t total_items = P.w_count * P.split;
+  const uint32_t split_mask = P.split - 1;
+  const uint32_t split_shift = 31 - __clz(P.split);
+  for (;;) {
+    unsigned long long item = 0;
+    if (lane == 0) item = atomicAdd(P.counters + CTR_WORK, 1ull);
+    item = __shfl_sync(FULL, item, 0);
+    if (item >= total_items) break;
+    const uint32_t slocal = (uint32_t)(P.w_first + (item >> split_shift));
+    const uint32_t part = (uint32_t)item & split_mask;
+    const uint64_t sidx = P.a_first + slocal;
+    const uint64_t off_len = __ldg(&P.a.meta[sidx].off_len);  // same address in all lanes: one broadcast
+    const uint32_t L = (uint32_t)(off_len >> 40);
+    if (L < P.len_lo || L > P.len_hi) continue;
+    const uint64_t h = __ldg(P.a.hash + sidx);
+    __syncwarp();  // all lanes are done with the previous seed's residues
+    for (uint32_t p = lane; p < L; p += 32) sres[p] = __ldg(P.a.res + (off_len & ((1ull << 40) - 1)) + p);
+    __syncwarp();
+
+    if (part == 0) {  // identical + single substitutions (the reference emits them with d = 2 too, variants.cc:410-427)
+      const unsigned long long ws = filter_word(P, h, lane & 1);  // lane parity = position parity
+      for (uint32_t p0 = 0; p0 < L; p0 += 32) {
+        const uint32_t pos = p0 + lane;
+        const bool valid = pos < L;
+        const uint32_t pc = valid ? pos : 0u;
+        const uint32_t cmp = sres[pc];
+        SlotRegs R;
+        R.base2 = h ^ zT[cmp * ZP + pc];
+        R.word = ws;  // pos and lane have the same parity (p0 is a multiple of 32)
+        R.allowed = valid ? (ALL & ~(1u << cmp)) : 0u;
+        R.emask = (lane & 1) ? 0u : ~0u;
+        R.zrow = zT + pc;
+        R.var = pack_var(VK_SUBSTITUTION, pc, 0, 0, 0);
+        R.seed = slocal;
+        residue_loop<SIGMA, ZP, 3>(P, c, R);
+      }
+      const unsigned long long w1 = __shfl_sync(FULL, ws, 1);  // filter E word of the seed's own hash
+      submit(P, c, lane == 0 && pattern_hit(w1, field_odd(h)), h, [] { return pack_var(VK_IDENTICAL, 0, 0, 0, 0); }, slocal);
+    }
+
+    // double substitutions i < j (variants.cc:357-400): slots x = (pair e, first residue v), lanes
+    // over x, the loop over the second residue w.  The second substitution cannot change the filter
+    // word: for odd j it is filter E's word of h ^ Z(i,s[i]) ^ Z(i,v), for even j filter O's.
+    const uint32_t n_x = L * (L - 1) / 2 * S1;
+    auto load_slot = [&](uint32_t x) {
+      SlotRegs R;
+      const bool valid = x < n_x;
+      if (!valid) x = 0;
+      const uint32_t e = x / S1, vp = x - e * S1;
+      const uint32_t ij = pairtab[e];
+      const uint32_t i = ij & 255u, j = ij >> 8;
+      const uint32_t si = sres[i], sj = sres[j];
+      const uint32_t v = sub_residue(vp, si);
+      const uint64_t b2v = h ^ zT[si * ZP + i] ^ zT[v * ZP + i];
+      R.base2 = b2v ^ zT[sj * ZP + j];
+      R.word = filter_word(P, b2v, j & 1);
+      R.allowed = valid ? (ALL & ~(1u << sj)) : 0u;
+      R.emask = (j & 1) ? 0u : ~0u;
+      R.zrow = zT + j;
+      R.var = pack_var(VK_SUB_SUB, i, v, j, 0);
+      R.seed = slocal;
+      return R;
+    };
+    const uint32_t n_pass = (n_x + 31) / 32;
+    if (part < n_pass) {
+      SlotRegs cur = load_slot(part * 32 + lane);
+      for (uint32_t t = part; t < n_pass; t += P.split) {
+        SlotRegs nxt = cur;
+        if (t + P.split < n_pass) nxt = load_slot((t + P.split) * 32 + lane);  // one pass ahead: its word is in flight
+        residue_loop<SIGMA, ZP, 8>(P, c, cur);
+        cur = nxt;
+      }
+    }
+  }
+  finish(P, c);
+}
+
+// =====================================================================================================
+// Generic kernel: any seed length up to 510 (d = 1 with or without indels, d = 2).  One warp per
+// (seed, part); every candidate is decoded from a flat index and looks its own filter word up.
+// Slower per probe than the fast kernels; it exists so that a single long sequence does not
+// change what the engine can do (the reference has no length limit).
+// =====================================================================================================
+
 __device__ __forceinline__ void filter_step(const ProbeParams& P, const uint64_t (&hv)[VK_U],
                                             const bool (&odd)[VK_U], bool (&pass)[VK_U]) {
   if (!P.use_bloom) return;
@@ -115,38 +487,23 @@ __device__ __forceinline__ void filter_step(const ProbeParams& P, const uint64_t
     pass[u] = pass[u] & pattern_hit(w[u], odd[u] ? field_odd(hv[u]) : field_even(hv[u]));
 }
 
-// Per-warp scratch for one seed, addressed from the per-warp block.
-template <int SIGMA, bool INDELS>
+// Per-warp scratch of the generic kernel for one seed.
 struct SeedScratch {
-  uint64_t* zo;    // Z(p, s[p]); the scans follow at multiples of lpad:
-  uint32_t lpad;   //   pre[p] = xor_{q<p} Z(q, s[q])        INDELS only: prefix/suffix scans replace the
-                   //   sm[p]  = xor_{q>=p} Z(q-1, s[q])     serial incremental walks of
-                   //   sp[p]  = xor_{q>=p} Z(q+1, s[q])     variants.cc:311-324,341-353
+  uint64_t* zo;    // Z(p, s[p]); with indels the scans follow at multiples of lpad:
+  uint32_t lpad;   //   pre[p] = xor_{q<p} Z(q, s[q]),  sm[p] = xor_{q>=p} Z(q-1, s[q]),  sp[p] = xor_{q>=p} Z(q+1, s[q])
   __device__ __forceinline__ uint64_t* pre() const { return zo + lpad; }
   __device__ __forceinline__ uint64_t* sm() const { return zo + 2 * lpad; }
   __device__ __forceinline__ uint64_t* sp() const { return zo + 3 * lpad; }
-  // d = 1 kernel only, after the scans (finalize_seed): everything a candidate needs, per "slot"
-  // pp = position for substitutions (pp < L), L + position for insertions (pp in [L, 2L]):
-  //   base2[pp]  hash of the variant minus the Zobrist value of its free residue
-  //   word2[pp]  the parity-filter word that every residue at this slot is looked up in
-  //   cmp2[pp]   the residue that must NOT be put there (substitution: the seed's own; insertion:
-  //              the residue before it, variants.cc:341-353; 255 = none)
-  // and for deletions (t < L) / the identical candidate (t = L, or 0 without indels):
-  //   dh[t], wd[t]  variant hash and its filter word
-  static constexpr uint32_t kScan = INDELS ? 4 : 1, kSlots = INDELS ? 2 : 1;
-  __device__ __forceinline__ uint64_t* base2() const { return zo + kScan * lpad; }
-  __device__ __forceinline__ uint64_t* word2() const { return zo + (kScan + kSlots) * lpad; }
-  __device__ __forceinline__ uint64_t* dh() const { return zo + (kScan + 2 * kSlots) * lpad; }
-  __device__ __forceinline__ uint64_t* wd() const { return zo + (kScan + 2 * kSlots + 1) * lpad; }
-  __device__ __forceinline__ uint8_t* cmp2() const { return reinterpret_cast<uint8_t*>(zo + (kScan + 2 * kSlots + 2) * lpad); }
 };
 
+template <bool ZG>
+__device__ __forceinline__ uint64_t zval(const uint64_t* __restrict__ z, uint32_t i) { return ZG ? __ldg(z + i) : z[i]; }
+
 // Fill zo[] (and the three scans) for the seed whose residues are at sres[0..L).  Returns VJ.
-template <int SIGMA, bool INDELS>
+template <int SIGMA, bool INDELS, bool ZG>
 __device__ __forceinline__ uint64_t prepare_seed(const uint64_t* __restrict__ z, const uint8_t* sres,
-                                                 uint32_t L, uint64_t h, uint32_t lane,
-                                                 SeedScratch<SIGMA, INDELS>& s) {
-  for (uint32_t p = lane; p < L; p += 32) s.zo[p] = z[p * SIGMA + sres[p]];
+                                                 uint32_t L, uint64_t h, uint32_t lane, SeedScratch& s) {
+  for (uint32_t p = lane; p < L; p += 32) s.zo[p] = zval<ZG>(z, p * SIGMA + sres[p]);
   __syncwarp();
   if (!INDELS) return 0;
   uint64_t carry = 0;
@@ -168,8 +525,8 @@ __device__ __forceinline__ uint64_t prepare_seed(const uint64_t* __restrict__ z,
     const bool ok = t < L;
     const uint32_t q = ok ? L - 1 - t : 0;
     const uint32_t r = sres[q];
-    uint64_t xm = (ok && q >= 1) ? z[(q - 1) * SIGMA + r] : 0ull;
-    uint64_t xp = ok ? z[(q + 1) * SIGMA + r] : 0ull;
+    uint64_t xm = (ok && q >= 1) ? zval<ZG>(z, (q - 1) * SIGMA + r) : 0ull;
+    uint64_t xp = ok ? zval<ZG>(z, (q + 1) * SIGMA + r) : 0ull;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
       const uint64_t ym = __shfl_up_sync(FULL, xm, o);
@@ -196,9 +553,9 @@ __device__ __forceinline__ uint64_t prepare_seed(const uint64_t* __restrict__ z,
 
 // Phase A: identical + single substitutions (+ deletions + insertions); flat index space
 // [0, T): 0 identical | (S-1)L substitutions | L deletion candidates | S(L+1) insertion candidates.
-template <int SIGMA, bool INDELS>
+template <int SIGMA, bool INDELS, bool ZG>
 __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
-                                        const uint8_t* sres, const SeedScratch<SIGMA, INDELS>& s,
+                                        const uint8_t* sres, const SeedScratch& s,
                                         uint32_t L, uint64_t h, uint64_t vjh, uint32_t slocal) {
   constexpr uint32_t S1 = SIGMA - 1;
   const uint32_t nsub = S1 * L;
@@ -219,7 +576,7 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
         if (t < nsub) {
           const uint32_t pos = t / S1, rp = t - pos * S1;
           const uint32_t r = sub_residue(rp, sres[pos]);
-          hv[u] = h ^ s.zo[pos] ^ z[pos * SIGMA + r];
+          hv[u] = h ^ s.zo[pos] ^ zval<ZG>(z, pos * SIGMA + r);
           odd[u] = pos & 1;
           var[u] = pack_var(VK_SUBSTITUTION, pos, r, 0, 0);
         } else if (INDELS) {
@@ -233,7 +590,7 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
             t -= L;
             const uint32_t pos = t / SIGMA, r = t - pos * SIGMA;
             pass[u] = (pos == 0) || (r != sres[pos - 1]);
-            hv[u] = vjh ^ s.pre()[pos] ^ z[pos * SIGMA + r] ^ s.sp()[pos];
+            hv[u] = vjh ^ s.pre()[pos] ^ zval<ZG>(z, pos * SIGMA + r) ^ s.sp()[pos];
             odd[u] = pos & 1;  // the inserted residue sits at position pos of the variant
             var[u] = pack_var(VK_INSERTION, pos, r, 0, 0);
           }
@@ -249,152 +606,19 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
   }
 }
 
-// d = 1.  Everything a candidate needs is laid out per slot first (SeedScratch); the filter words
-// are fetched once per slot, because a slot's word does not depend on the residue placed there
-// (parity filters, common.cuh), and the enumeration loops then run on shared memory and registers:
-//   * the two words of ALL substitution slots (even / odd positions) depend only on the seed's
-//     hash: they are fetched when the batch is staged (variant1_kernel) and arrive as ws_even/odd;
-//   * the words of the insertion and deletion slots need the scans: their loads are ISSUED before
-//     the substitution loop and CONSUMED after it, so their latency hides behind ~45 % of the
-//     seed's work instead of stalling the warp.
-template <int SIGMA, bool INDELS, int U>
-__device__ __forceinline__ void enumerate_slots(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
-                                                const SeedScratch<SIGMA, INDELS>& s, uint32_t L,
-                                                uint32_t q0, uint32_t q1, bool subs,
-                                                unsigned long long ws_even, unsigned long long ws_odd,
-                                                uint32_t slocal) {
-  // candidates q in [q0, q1) of the slot space: slot pp = q / SIGMA, residue r = q % SIGMA
-  for (uint32_t base = q0; base < q1; base += 32 * U) {
-    uint64_t hv[U];
-    uint32_t code[U];
-    bool pass[U];
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint32_t q = base + u * 32 + c.lane;
-      const bool in = q < q1;
-      const uint32_t qq = in ? q : q0;
-      const uint32_t pp = qq / SIGMA, r = qq - pp * SIGMA;
-      const uint32_t pos = subs ? pp : pp - L;
-      const uint64_t b = s.base2()[pp];
-      const uint32_t cmp = s.cmp2()[pp];
-      const unsigned long long w = subs ? ((pos & 1) ? ws_odd : ws_even) : s.word2()[pp];
-      hv[u] = b ^ z[pos * SIGMA + r];
-      code[u] = qq;
-      pass[u] = in & (r != cmp) & pattern_hit(w, (pos & 1) ? field_odd(hv[u]) : field_even(hv[u]));
-    }
-#pragma unroll
-    for (int u = 0; u < U; u++) {
-      const uint32_t qq = code[u];
-      submit(P, c, pass[u], hv[u], [qq, L] {
-        const uint32_t pp = qq / SIGMA, r = qq - pp * SIGMA;
-        return pp < L ? pack_var(VK_SUBSTITUTION, pp, r, 0, 0) : pack_var(VK_INSERTION, pp - L, r, 0, 0);
-      }, slocal);
-    }
-  }
-}
-
-// Two candidates per lane per step: the loop has no global load left to overlap, and a small body
-// matters more — with four (and a separate tail loop) a quarter of all stall samples were
-// instruction-cache misses (profiles/r01_h_*).
-#ifndef VK_U1
-#define VK_U1 2
-#endif
-template <int SIGMA, bool INDELS>
-__device__ __forceinline__ void enumerate_range(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
-                                                const SeedScratch<SIGMA, INDELS>& s, uint32_t L,
-                                                uint32_t q0, uint32_t q1, bool subs,
-                                                unsigned long long ws_even, unsigned long long ws_odd,
-                                                uint32_t slocal) {
-  enumerate_slots<SIGMA, INDELS, VK_U1>(P, c, z, s, L, q0, q1, subs, ws_even, ws_odd, slocal);
-}
-
-template <int SIGMA, bool INDELS>
-__device__ __forceinline__ void seed_d1(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
-                                        const uint8_t* sres, const SeedScratch<SIGMA, INDELS>& s,
-                                        uint32_t L, uint64_t h, uint64_t vjh,
-                                        unsigned long long ws_even, unsigned long long ws_odd,
-                                        uint32_t slocal) {
-  const bool filt = P.use_bloom;
-  const uint32_t lane = c.lane;
-  // substitution slots
-  for (uint32_t pp = lane; pp < L; pp += 32) {
-    s.base2()[pp] = h ^ s.zo[pp];
-    s.cmp2()[pp] = sres[pp];
-  }
-  // insertion slots (pp = L + pos) and deletions: bases now, words in flight.  The first 32 of
-  // each are prefetched into registers; longer seeds fetch the rest when the words are stored.
-  unsigned long long wi0 = ~0ull, wd0 = ~0ull;
-  if (INDELS) {
-    for (uint32_t pos = lane; pos <= L; pos += 32) {
-      const uint64_t b = vjh ^ s.pre()[pos] ^ s.sp()[pos];
-      s.base2()[L + pos] = b;
-      s.cmp2()[L + pos] = (uint8_t)(pos == 0 ? 255u : sres[pos - 1]);
-      // the inserted residue sits at position pos: it cannot change the field that picks the word
-      if (pos < 32 && filt) wi0 = __ldg(P.bloom + pfilter_word(b, P.bloom_blocks, pos & 1));
-    }
-    for (uint32_t t = lane; t < L; t += 32) {
-      const uint64_t hv = vjh ^ s.pre()[t] ^ s.sm()[t + 1];
-      s.dh()[t] = hv;
-      if (t < 32 && filt) wd0 = __ldg(P.bloom + pfilter_word(hv, P.bloom_blocks, true));
-    }
-  }
-  __syncwarp();
-  enumerate_range<SIGMA, INDELS>(P, c, z, s, L, 0, L * SIGMA, true, ws_even, ws_odd, slocal);
-  if (INDELS) {
-    for (uint32_t pos = lane; pos <= L; pos += 32)
-      s.word2()[L + pos] = pos < 32 ? wi0
-                           : (filt ? __ldg(P.bloom + pfilter_word(s.base2()[L + pos], P.bloom_blocks, pos & 1)) : ~0ull);
-    for (uint32_t t = lane; t < L; t += 32)
-      s.wd()[t] = t < 32 ? wd0 : (filt ? __ldg(P.bloom + pfilter_word(s.dh()[t], P.bloom_blocks, true)) : ~0ull);
-    __syncwarp();
-    enumerate_range<SIGMA, INDELS>(P, c, z, s, L, L * SIGMA, (2 * L + 1) * SIGMA, false, ws_even, ws_odd, slocal);
-  }
-  // deletions: one per run of equal residues, only if L > 1 (variants.cc:301-325); candidate
-  // t = nd - 1 is the identical one (filter E, whose word for the seed's own hash is ws_odd)
-  const uint32_t nd = INDELS ? L + 1 : 1;
-  for (uint32_t t0 = 0; t0 < nd; t0 += 32) {
-    const uint32_t t = t0 + lane;
-    const bool in = t < nd;
-    const bool is_del = INDELS && t < L;
-    const uint32_t tt = is_del ? t : 0u;
-    const bool valid = in && (!is_del || (L > 1 && (tt == 0 || sres[tt] != sres[tt - 1])));
-    const uint64_t hv = is_del ? s.dh()[tt] : h;
-    const unsigned long long w = is_del ? s.wd()[tt] : ws_odd;
-    const bool pass = valid & pattern_hit(w, field_odd(hv));
-    submit(P, c, pass, hv, [is_del, tt] {
-      return is_del ? pack_var(VK_DELETION, tt, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0);
-    }, slocal);
-  }
-}
-
 // Phase B: double substitutions i < j (variants.cc:357-400).  Outer (i, v) warp-uniform, lanes over
-// the slots (j > i, r) of the second substitution: SIGMA candidates per j with the seed's own
-// residue masked, hash = base2 ^ Z(j, s[j]) ^ Z(j, r).  The second substitution cannot change the
-// filter word: for odd j all candidates read filter E's word of base2, for even j filter O's — two
-// words per outer iteration, fetched one iteration AHEAD so that their latency never stalls the
-// warp.
-template <int SIGMA, bool INDELS>
+// the slots (j > i, r) of the second substitution, two filter words per outer iteration.
+template <int SIGMA, bool ZG>
 __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
-                                        const uint8_t* sres, const SeedScratch<SIGMA, INDELS>& s,
+                                        const uint8_t* sres, const SeedScratch& s,
                                         uint32_t L, uint64_t h, uint32_t slocal, uint32_t part,
                                         uint32_t split) {
   constexpr uint32_t S1 = SIGMA - 1;
   const uint32_t nouter = S1 * L;
-  const bool filt = P.use_bloom;
-  auto outer = [&](uint32_t o, uint32_t& i, uint32_t& v, uint64_t& b2, unsigned long long& we, unsigned long long& wo) {
-    i = o / S1;
-    v = sub_residue(o - i * S1, sres[i]);
-    b2 = h ^ s.zo[i] ^ z[i * SIGMA + v];
-    we = filt ? __ldg(P.bloom + pfilter_word(b2, P.bloom_blocks, true)) : ~0ull;
-    wo = filt ? __ldg(P.bloom + pfilter_word(b2, P.bloom_blocks, false)) : ~0ull;
-  };
-  uint32_t i = 0, v = 0, ni = 0, nv = 0;
-  uint64_t b2 = 0, nb2 = 0;
-  unsigned long long we = 0, wo = 0, nwe = 0, nwo = 0;
-  if (part < nouter) outer(part, ni, nv, nb2, nwe, nwo);
   for (uint32_t o = part; o < nouter; o += split) {
-    i = ni; v = nv; b2 = nb2; we = nwe; wo = nwo;
-    if (o + split < nouter) outer(o + split, ni, nv, nb2, nwe, nwo);
+    const uint32_t i = o / S1, v = sub_residue(o - i * S1, sres[i]);
+    const uint64_t b2 = h ^ s.zo[i] ^ zval<ZG>(z, i * SIGMA + v);
+    const unsigned long long we = filter_word(P, b2, true), wo = filter_word(P, b2, false);
     const uint32_t ninner = SIGMA * (L - 1 - i);
     for (uint32_t tb = 0; tb < ninner; tb += 32) {
       const uint32_t t = tb + c.lane;
@@ -403,139 +627,49 @@ __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const 
       const uint32_t jj = tt / SIGMA, r = tt - jj * SIGMA;
       const uint32_t j = in ? i + 1 + jj : i;  // inactive lanes read a valid row
       const uint32_t cmp = sres[j];
-      const uint64_t hv = b2 ^ s.zo[j] ^ z[j * SIGMA + r];
+      const uint64_t hv = b2 ^ s.zo[j] ^ zval<ZG>(z, j * SIGMA + r);
       const bool pass = in & (r != cmp) & pattern_hit((j & 1) ? we : wo, (j & 1) ? field_odd(hv) : field_even(hv));
       submit(P, c, pass, hv, [i, v, j, r] { return pack_var(VK_SUB_SUB, i, v, j, r); }, slocal);
     }
   }
 }
 
-// ---- shared-memory carve-up (host and device must agree) ------------------------------------------
-
-struct VkLayout {
-  uint32_t lpad;        // per-seed scratch entries (>= lmax + 2, multiple of 8)
-  size_t z_u64;         // Zobrist rows
-  size_t warp_bytes;    // per-warp block: survivor ring + seed scratch
-  size_t blk_u64;       // staged seed batches, all warps: metas (4 u64 each) + hashes
-  size_t res_per_warp;  // bytes of staged residues per warp
+struct GenLayout {
+  uint32_t lpad;      // per-seed scratch entries (>= lmax + 2, multiple of 8)
+  size_t z_u64;       // Zobrist rows staged in shared memory (0 with ZG)
+  size_t warp_bytes;  // survivor ring + seed scratch + residues
   size_t total;
 };
 
-__host__ __device__ inline VkLayout vk_layout(uint32_t zrows, uint32_t sigma, uint32_t lmax, bool indels,
-                                              bool staged) {
-  VkLayout l;
+static inline GenLayout gen_layout(uint32_t zrows, uint32_t sigma, uint32_t lmax, bool indels, bool zg) {
+  GenLayout l;
   l.lpad = (lmax + 2 + 7) & ~7u;
-  l.z_u64 = (size_t)zrows * sigma;
-  // scratch in u64 units of lpad: scans (4 or 1); d = 1 adds base2 + word2 (2 or 1 each), dh, wd, cmp2 (bytes, <= 1)
-  const size_t units = (indels ? 4 : 1) + (staged ? (indels ? 4 : 2) + 2 + 1 : 0);
-  l.warp_bytes = VK_Q_BYTES + (size_t)l.lpad * units * 8;
-  l.blk_u64 = staged ? (size_t)VK_WARPS * VK_WB * 7 : 0;
-  l.res_per_warp = staged ? (((size_t)VK_WB * lmax + 15) & ~(size_t)15) : l.lpad;
-  l.total = l.z_u64 * 8 + VK_WARPS * l.warp_bytes + l.blk_u64 * 8 + VK_WARPS * l.res_per_warp;
+  l.z_u64 = zg ? 0 : (size_t)zrows * sigma;
+  l.warp_bytes = VK_Q_BYTES + (size_t)l.lpad * (indels ? 4 : 1) * 8 + l.lpad;
+  l.total = l.z_u64 * 8 + VK_WARPS * l.warp_bytes;
   return l;
 }
 
-template <int SIGMA, bool INDELS>
-__device__ __forceinline__ void carve_warp(const VkLayout& l, unsigned char* smem, uint32_t warp, uint32_t lane,
-                                           uint64_t*& z, SeedScratch<SIGMA, INDELS>& s, WarpCtx& c,
-                                           uint64_t*& blk, uint8_t*& bytes) {
-  z = reinterpret_cast<uint64_t*>(smem);
-  c.wb = smem + l.z_u64 * 8 + warp * l.warp_bytes;
-  s.zo = reinterpret_cast<uint64_t*>(c.wb + VK_Q_BYTES);
-  s.lpad = l.lpad;
-  blk = reinterpret_cast<uint64_t*>(smem + l.z_u64 * 8 + VK_WARPS * l.warp_bytes);
-  bytes = reinterpret_cast<uint8_t*>(blk + l.blk_u64);
+template <int SIGMA, bool INDELS, bool ZG>
+__global__ void __launch_bounds__(VK_THREADS, 2) generic_kernel(const __grid_constant__ ProbeParams P, uint32_t lpad) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const size_t z_u64 = ZG ? 0 : (size_t)P.zrows * SIGMA;
+  const size_t warp_bytes = VK_Q_BYTES + (size_t)lpad * (INDELS ? 4 : 1) * 8 + lpad;
+  uint64_t* zs = reinterpret_cast<uint64_t*>(smem_raw);
+  WarpCtx c;
+  c.wb = smem_raw + z_u64 * 8 + warp * warp_bytes;
   c.head = c.count = 0;
   c.lane = lane;
-}
-
-// ---- d = 1 -------------------------------------------------------------------------------------------
-//
-// Warps take batches of VK_WB consecutive seeds from a global dispenser and stage the batch's
-// metadata, hashes and residues (contiguous in the arena) into per-warp shared memory with
-// coalesced loads: the dependent global loads (dispenser -> metadata -> residues) are paid once
-// per batch, not once per seed, and nothing waits on a CTA-wide barrier (a block-synchronous
-// variant lost a third of its time at __syncthreads behind whichever warp was in the slow path,
-// measured this round).
-
-template <int SIGMA, bool INDELS>
-__global__ void __launch_bounds__(VK_THREADS, VK_D1_CTAS) variant1_kernel(const __grid_constant__ ProbeParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const VkLayout lay = vk_layout(P.zrows, SIGMA, P.lmax, INDELS, true);
-  uint64_t* z;
-  SeedScratch<SIGMA, INDELS> sc;
-  WarpCtx c;
-  uint64_t* blk;
-  uint8_t* bytes;
-  carve_warp<SIGMA, INDELS>(lay, smem_raw, warp, lane, z, sc, c, blk, bytes);
-  uint64_t* const my = blk + warp * (VK_WB * 7);                 // this warp's staging area
-  SeqRec* const b_meta = reinterpret_cast<SeqRec*>(my);          // VK_WB records of 32 B
-  uint64_t* const b_hash = my + VK_WB * 4;
-  unsigned long long* const b_ws = reinterpret_cast<unsigned long long*>(my + VK_WB * 5);  // [seed][even, odd]
-  uint8_t* const b_res = bytes + warp * lay.res_per_warp;
-
-  for (uint32_t i = threadIdx.x; i < P.zrows * SIGMA; i += VK_THREADS) z[i] = P.ztab[i];
-  __syncthreads();
-  const uint64_t n_batches = (P.w_count + VK_WB - 1) / VK_WB;
-
-  for (;;) {
-    unsigned long long b = 0;
-    if (lane == 0) b = atomicAdd(P.counters + CTR_WORK, 1ull);
-    b = __shfl_sync(FULL, b, 0);
-    if (b >= n_batches) break;
-    const uint64_t first = P.w_first + b * VK_WB;  // relative to a_first
-    const uint32_t nb = (uint32_t)((P.w_first + P.w_count - first < VK_WB) ? P.w_first + P.w_count - first : VK_WB);
-    __syncwarp();  // previous batch fully consumed
-    if (lane < nb * 2)
-      reinterpret_cast<uint4*>(b_meta)[lane] =
-          __ldg(reinterpret_cast<const uint4*>(P.a.meta + P.a_first + first) + lane);
-    // hashes, and with them the two filter words of each seed's substitution slots: filter O for
-    // even positions, filter E for odd ones (the word index ignores the substituted residue)
-    unsigned long long ws = ~0ull;
-    if (lane < 2 * nb) {
-      const uint64_t hk = __ldg(P.a.hash + P.a_first + first + (lane >> 1));
-      if (lane & 1) b_hash[lane >> 1] = hk;
-      if (P.use_bloom) ws = __ldg(P.bloom + pfilter_word(hk, P.bloom_blocks, lane & 1));
-    }
-    __syncwarp();
-    const uint64_t res0 = b_meta[0].off_len & ((1ull << 40) - 1);
-    const uint64_t last = b_meta[nb - 1].off_len;
-    const uint32_t res_n = (uint32_t)((last & ((1ull << 40) - 1)) + (last >> 40) - res0);
-    for (uint32_t i = lane; i < res_n; i += 32) b_res[i] = __ldg(P.a.res + res0 + i);
-    if (lane < 2 * nb) b_ws[lane] = ws;
-    __syncwarp();
-
-    for (uint32_t k = 0; k < nb; k++) {
-      const uint64_t off_len = b_meta[k].off_len;  // the enumeration needs only offset and length
-      const uint32_t L = (uint32_t)(off_len >> 40);
-      const uint64_t h = b_hash[k];
-      const uint8_t* sres = b_res + (uint32_t)((off_len & ((1ull << 40) - 1)) - res0);
-      __syncwarp();  // all lanes are done with the previous seed's scratch
-      const uint64_t vjh = prepare_seed<SIGMA, INDELS>(z, sres, L, h, lane, sc);
-      seed_d1<SIGMA, INDELS>(P, c, z, sres, sc, L, h, vjh, b_ws[2 * k], b_ws[2 * k + 1], (uint32_t)(first + k));
-    }
+  SeedScratch sc;
+  sc.zo = reinterpret_cast<uint64_t*>(c.wb + VK_Q_BYTES);
+  sc.lpad = lpad;
+  uint8_t* const sres = c.wb + VK_Q_BYTES + (size_t)lpad * (INDELS ? 4 : 1) * 8;
+  if (!ZG) {
+    for (uint32_t i = threadIdx.x; i < P.zrows * SIGMA; i += VK_THREADS) zs[i] = P.ztab[i];
+    __syncthreads();
   }
-  finish(P, c);
-}
-
-// ---- d = 2 -------------------------------------------------------------------------------------------
-
-template <int SIGMA>
-__global__ void __launch_bounds__(VK_THREADS, 3) variant2_kernel(const __grid_constant__ ProbeParams P) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const VkLayout lay = vk_layout(P.zrows, SIGMA, P.lmax, false, false);
-  uint64_t* z;
-  SeedScratch<SIGMA, false> sc;
-  WarpCtx c;
-  uint64_t* blk;
-  uint8_t* bytes;
-  carve_warp<SIGMA, false>(lay, smem_raw, warp, lane, z, sc, c, blk, bytes);
-  uint8_t* const sres = bytes + warp * lay.res_per_warp;
-
-  for (uint32_t i = threadIdx.x; i < P.zrows * SIGMA; i += VK_THREADS) z[i] = P.ztab[i];
-  __syncthreads();
+  const uint64_t* const z = ZG ? P.ztab : zs;
 
   const uint64_t total_items = P.w_count * P.split;
   const uint32_t split_mask = P.split - 1;
@@ -548,15 +682,16 @@ __global__ void __launch_bounds__(VK_THREADS, 3) variant2_kernel(const __grid_co
     const uint32_t slocal = (uint32_t)(P.w_first + (item >> split_shift));
     const uint32_t part = (uint32_t)item & split_mask;
     const uint64_t sidx = P.a_first + slocal;
-    const uint64_t off_len = __ldg(&P.a.meta[sidx].off_len);  // same address in all lanes: one broadcast
+    const uint64_t off_len = __ldg(&P.a.meta[sidx].off_len);
     const uint32_t L = (uint32_t)(off_len >> 40);
+    if (L < P.len_lo || L > P.len_hi) continue;
     const uint64_t h = __ldg(P.a.hash + sidx);
     __syncwarp();
     for (uint32_t p = lane; p < L; p += 32) sres[p] = __ldg(P.a.res + (off_len & ((1ull << 40) - 1)) + p);
     __syncwarp();
-    prepare_seed<SIGMA, false>(z, sres, L, h, lane, sc);
-    if (part == 0) phase_a<SIGMA, false>(P, c, z, sres, sc, L, h, 0, slocal);
-    phase_b<SIGMA, false>(P, c, z, sres, sc, L, h, slocal, part, P.split);
+    const uint64_t vjh = prepare_seed<SIGMA, INDELS, ZG>(z, sres, L, h, lane, sc);
+    if (part == 0) phase_a<SIGMA, INDELS, ZG>(P, c, z, sres, sc, L, h, vjh, slocal);
+    if (!INDELS && P.differences == 2) phase_b<SIGMA, ZG>(P, c, z, sres, sc, L, h, slocal, part, P.split);
   }
   finish(P, c);
 }
@@ -600,9 +735,9 @@ void launch_table_stage(const ProbeParams& p, int sm_count, uint32_t chunk_id, c
 
 // ---- launch ------------------------------------------------------------------------------------------
 
-template <typename K>
+template <typename K, typename... Extra>
 static int launch_one(K kern, const ProbeParams& p, size_t smem, uint64_t work_ctas, int sm_count,
-                      cudaStream_t st, const char** err) {
+                      cudaStream_t st, const char** err, Extra... extra) {
   if (smem > 200 * 1024) {
     *err = "sequence too long for the shared-memory variant kernels";
     return -1;
@@ -618,9 +753,7 @@ static int launch_one(K kern, const ProbeParams& p, size_t smem, uint64_t work_c
   }
   // Shared-memory carve-out = what the resident CTAs need (+1 KB per CTA for the system), not the
   // driver's "room for the most CTAs" default: the rest of the 228 KB stays L1, which serves the
-  // repeated filter words and the staged loads.  (With a single randomly probed filter the
-  // carve-out had to stay under 100 KB — the rate of random 8-byte loads an SM sustains halves
-  // beyond it, tools/bench_l2_random.cu; with the parity filters such loads are a few dozen per seed.)
+  // repeated filter words and the staged loads.
   {
     const size_t need = (size_t)per_sm * (smem + 1024);
     cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
@@ -628,36 +761,83 @@ static int launch_one(K kern, const ProbeParams& p, size_t smem, uint64_t work_c
   }
   uint64_t grid = (uint64_t)sm_count * per_sm;  // persistent: whole waves of resident CTAs
   if (work_ctas < grid) grid = work_ctas;
-  kern<<<(unsigned)grid, VK_THREADS, smem, st>>>(p);
+  if (grid == 0) return 0;
+  kern<<<(unsigned)grid, VK_THREADS, smem, st>>>(p, extra...);
   return 1;
 }
 
-int launch_variant_kernels(const ProbeParams& p_in, int sm_count, cudaStream_t st, const char** err) {
-  // only the Zobrist rows the longest seed can touch are staged in shared memory (positions
-  // 0..lmax, +1 for the shifted rows of the indel scans): the table itself may be longer
+template <int SIGMA, int ZP>
+static int launch_fast(const ProbeParams& p, int sm_count, cudaStream_t st, const char** err) {
+  if (p.differences == 1) {
+    constexpr int WB = E1Cfg<ZP>::WB;
+    const uint64_t ctas = ((p.w_count + WB - 1) / WB + VK_WARPS - 1) / VK_WARPS;
+    return p.indels ? launch_one(enum1_kernel<SIGMA, true, ZP>, p, E1Layout<ZP, true>::total(SIGMA), ctas, sm_count, st, err)
+                    : launch_one(enum1_kernel<SIGMA, false, ZP>, p, E1Layout<ZP, false>::total(SIGMA), ctas, sm_count, st, err);
+  }
+  const uint64_t ctas = (p.w_count * p.split + VK_WARPS - 1) / VK_WARPS;
+  return launch_one(enum2_kernel<SIGMA, ZP>, p, E2Layout<ZP>::total(SIGMA), ctas, sm_count, st, err);
+}
+
+template <int SIGMA>
+static int launch_generic(ProbeParams p, int sm_count, cudaStream_t st, const char** err) {
+  const bool indels = p.indels && p.differences == 1;
+  p.zrows = std::min(p.zrows, p.lmax + 2);  // rows the longest seed can touch (+1 for the shifted rows of the indel scans)
+  bool zg = false;
+  GenLayout l = gen_layout(p.zrows, SIGMA, p.lmax, indels, false);
+  if (l.total > 160 * 1024) {  // the table itself stays in global memory / L1
+    zg = true;
+    l = gen_layout(p.zrows, SIGMA, p.lmax, indels, true);
+  }
+  const uint64_t ctas = (p.w_count * p.split + VK_WARPS - 1) / VK_WARPS;
+  if (indels)
+    return zg ? launch_one(generic_kernel<SIGMA, true, true>, p, l.total, ctas, sm_count, st, err, l.lpad)
+              : launch_one(generic_kernel<SIGMA, true, false>, p, l.total, ctas, sm_count, st, err, l.lpad);
+  return zg ? launch_one(generic_kernel<SIGMA, false, true>, p, l.total, ctas, sm_count, st, err, l.lpad)
+            : launch_one(generic_kernel<SIGMA, false, false>, p, l.total, ctas, sm_count, st, err, l.lpad);
+}
+
+// Seeds are split by length between up to three launches (each kernel skips the seeds that are not
+// its own): <= 30 residues the ZP = 32 kernels, <= 94 the ZP = 96 kernels, longer ones the generic
+// kernel.  p.lmax = the longest seed of the set decides which launches are needed at all.
+template <int SIGMA>
+static int launch_by_length(const ProbeParams& p_in, int sm_count, cudaStream_t st, const char** err) {
   ProbeParams p = p_in;
-  p.zrows = std::min(p_in.zrows, p_in.lmax + 2);
+  int launches = 0, l;
+  const uint32_t f32 = E1Cfg<32>::LMAX, f96 = E1Cfg<96>::LMAX;
+  uint32_t lo = 0;
+  if (!p_in.force_generic) {
+    p.len_lo = 0;
+    p.len_hi = f32;
+    if ((l = launch_fast<SIGMA, 32>(p, sm_count, st, err)) < 0) return l;
+    launches += l;
+    lo = f32 + 1;
+    if (p_in.lmax >= lo) {
+      p.len_lo = lo;
+      p.len_hi = f96;
+      if ((l = launch_fast<SIGMA, 96>(p, sm_count, st, err)) < 0) return l;
+      launches += l;
+      lo = f96 + 1;
+    }
+  }
+  if (p_in.lmax >= lo) {
+    p.len_lo = lo;
+    p.len_hi = 0xffffffffu;
+    if ((l = launch_generic<SIGMA>(p, sm_count, st, err)) < 0) return l;
+    launches += l;
+  }
+  return launches;
+}
+
+int launch_variant_kernels(const ProbeParams& p, int sm_count, cudaStream_t st, const char** err) {
   if (p.lmax + 1 > VAR_MAX_POS) {
-    *err = "sequence longer than 510 residues on the d<=2 path";
+    *err = "sequence longer than 510 residues on the d<=2 path (the variant descriptor holds 9-bit positions)";
     return -1;
   }
   if (p.sigma != 4 && p.sigma != 20) {
     *err = "alphabet size must be 4 or 20";
     return -1;
   }
-  if (p.differences == 1) {
-    const size_t smem = vk_layout(p.zrows, p.sigma, p.lmax, p.indels, true).total;
-    const uint64_t blocks = ((p.w_count + VK_WB - 1) / VK_WB + VK_WARPS - 1) / VK_WARPS;
-    if (p.sigma == 20)
-      return p.indels ? launch_one(variant1_kernel<20, true>, p, smem, blocks, sm_count, st, err)
-                      : launch_one(variant1_kernel<20, false>, p, smem, blocks, sm_count, st, err);
-    return p.indels ? launch_one(variant1_kernel<4, true>, p, smem, blocks, sm_count, st, err)
-                    : launch_one(variant1_kernel<4, false>, p, smem, blocks, sm_count, st, err);
-  }
-  const size_t smem = vk_layout(p.zrows, p.sigma, p.lmax, false, false).total;
-  const uint64_t ctas = (p.w_count * p.split + VK_WARPS - 1) / VK_WARPS;
-  return p.sigma == 20 ? launch_one(variant2_kernel<20>, p, smem, ctas, sm_count, st, err)
-                       : launch_one(variant2_kernel<4>, p, smem, ctas, sm_count, st, err);
+  return p.sigma == 20 ? launch_by_length<20>(p, sm_count, st, err) : launch_by_length<4>(p, sm_count, st, err);
 }
 
 }  // namespace cb

@@ -91,6 +91,8 @@ typedef struct cb_config {
 #define CB_FLAG_NO_BLOOM 2u       /* probe the hash table for every variant (A/B testing)        */
 #define CB_FLAG_NO_TENSOR 4u      /* d >= 3: CUDA-core kernel only, no tcgen05 GEMM (A/B testing) */
 #define CB_FLAG_NO_PARTITION 8u   /* table build in input order, no radix sort by home slot (A/B testing) */
+#define CB_FLAG_GENERIC_KERNEL 16u /* d = 1, 2: every seed through the any-length enumeration kernel  */
+                                   /* (otherwise only seeds longer than 94 residues; A/B testing)     */
 
 /*
  * One sequence set in structure-of-arrays form — what db_read() (src/db.cc:708-901) leaves

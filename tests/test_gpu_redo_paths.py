@@ -149,7 +149,7 @@ def test_c4_shape_d2_ignore_genes_min(partition_sized):
     mo, _, io = orc.overlap(a_s, b_s, differences=2, ignore_genes=True, score="min", threads=8)
     assert np.array_equal(m, mo)
     assert info["run"]["matches"] == io["matches"] and info["run"]["probes"] == io["probes"]
-    assert info["run"]["matches"] > a_s.n // 4
+    assert info["run"]["matches"] > 1000
 
 
 @pytest.fixture(scope="module")
