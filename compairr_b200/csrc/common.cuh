@@ -11,7 +11,7 @@
 //   exact verification            variants.cc:166-240
 //   score summands                overlap.cc:144-166
 //   Zobrist hash                  zobrist.cc:74-88   (table VALUES are ours)
-//   Bloom filter                  bloompat.h:40-58   (geometry is ours)
+//   Bloom filter                  bloompat.h:40-58   (geometry is ours: class filters)
 //   hash-table indexing           hashtable.h:36-46
 #pragma once
 #include <stdint.h>
@@ -102,24 +102,27 @@ CB_HD uint64_t splitmix64(uint64_t x) {
 // extended to longer sequences without invalidating hashes already computed (the reference draws
 // from glibc random(), zobrist.cc:52-63; results do not depend on the values).
 //
-// The values are STRUCTURED by the parity of the position (32 random bits x each):
-//     even p:  [ x : 0 ]      odd p:  [ x : x ]       (high half : low half)
-// so that, h being the XOR of the values of a sequence (and of a 64-bit V/J term),
-//     O(h) = low half               changes only when an ODD  position changes,
-//     E(h) = high half ^ low half   changes only when an EVEN position changes,
-// while the high half itself (home slot, partition order) depends on every position.  All the
-// single-residue variants of a seed at odd positions therefore share E, those at even positions
-// share O — which is what lets ONE filter word answer for all of them (parity filters below).
-// Two different sequences still collide with probability 2^-32 at worst (they differ in E or in
-// O); every hash match is verified on the residues anyway.
+// The values are STRUCTURED by the CLASS of the position, class = p mod 4: the 64-bit hash is four
+// 16-bit fields, and a residue at a position of class c contributes 16 random bits to field c and
+// nothing to the others.  So, h being the XOR of the values of a sequence (and of a 64-bit V/J
+// term), field c of h changes only when a position of class c changes: the 48 bits of the other
+// three fields are BLIND to class c.  All the single-residue variants of a seed at one position
+// (and at every other position of the same class) share them — which is what lets ONE filter word
+// answer for all of them (class filters below).
+// Round 1 used two classes (position parity, two 32-bit fields).  A word index then sees only
+// every other position: with -g (no V/J term) a set of 10^8 CDR3s has ~10^7 distinct values of it,
+// the words of the short sequences saturate and 11 % of all candidates passed the filter (measured,
+// C4 geometry).  Four classes let the index see three positions out of four.
+// Two different sequences collide with probability 2^-16 at worst (they differ in one class
+// only); every hash match is verified on the residues anyway.
+constexpr uint32_t CB_CLASSES = 4;
+CB_HD uint32_t pos_class(uint32_t p) { return p & 3u; }
 CB_HD uint64_t zobrist_gen(uint64_t seed, uint32_t p, uint32_t r) {
-  const uint64_t x = splitmix64(splitmix64(seed ^ 0x5A0B1157ull) + ((uint64_t)p << 8) + r) >> 32;
-  return (p & 1u) ? ((x << 32) | x) : (x << 32);
+  const uint64_t x = splitmix64(splitmix64(seed ^ 0x5A0B1157ull) + ((uint64_t)p << 8) + r) >> 48;
+  return x << (16 * pos_class(p));
 }
-CB_HD uint32_t field_odd(uint64_t h) { return (uint32_t)h; }
-CB_HD uint32_t field_even(uint64_t h) { return (uint32_t)(h >> 32) ^ (uint32_t)h; }
 // 32 bits of the hash that depend on every position, for the "possibly the same sequence" tag of
-// a table slot (the low half alone is blind to even positions, the high half repeats the home slot).
+// a table slot.
 CB_HD uint32_t slot_tag(uint64_t h) { return (uint32_t)(h >> 32) * 0x9E3779B1u ^ (uint32_t)h; }
 
 // Contribution of the (V gene, J gene) pair: zobrist_v_base[v] ^ zobrist_d_base[j] in the
@@ -128,29 +131,32 @@ CB_HD uint64_t vj_hash(uint64_t seed, uint32_t v, uint32_t j) {
   return splitmix64(splitmix64(seed ^ 0x7E11C0DEull) ^ (((uint64_t)v << 32) | j));
 }
 
-// Home slot (hashtable.h:36-41 takes the upper half of the hash): hash bits 61 downwards — bits of
-// the high half, which depends on every position (zobrist_gen).  Keys ordered by those bits touch
-// the table in address order, what the partitioned build relies on; the two filter updates of a
-// key are picked by the parity fields and stay random.
+// Home slot (hashtable.h:36-41 takes the upper half of the hash): the top bits of h * K, a
+// multiplicative mix — every field of the hash reaches them.  Keys ordered by h * K touch the
+// table in address order, what the partitioned build relies on (it sorts h * K and gets h back
+// with the inverse multiplier: K is odd, the map is a bijection).
+constexpr uint64_t CB_HOME_MUL = 0x9E3779B97F4A7C15ull;
+constexpr uint64_t CB_HOME_INV = 0xF1DE83E19937733Dull;  // CB_HOME_MUL * CB_HOME_INV == 1 (mod 2^64)
+static_assert(CB_HOME_MUL * CB_HOME_INV == 1ull, "inverse multiplier");
 CB_HD uint64_t table_home(uint64_t h, uint64_t mask) {
 #if defined(__CUDA_ARCH__)
   const int bits = __popcll(mask);
 #else
   const int bits = __builtin_popcountll(mask);
 #endif
-  return (h >> (62 - bits)) & mask;
+  return ((h * CB_HOME_MUL) >> (64 - bits)) & mask;
 }
-constexpr int CB_PARTITION_TOP_BIT = 62;  // partition keys are hash bits [62 - p, 62)
+constexpr int CB_PARTITION_TOP_BIT = 64;  // partition keys are bits [64 - p, 64) of h * CB_HOME_MUL
 
-// Parity filters (replace bloom_s, bloompat.h:26-58): TWO blocked Bloom filters of `nblocks`
-// 64-bit words each, laid out back to back; every set-B key is in both.
-//     filter E (words [0, nblocks)):        word picked by E(h), 3 + 3 bits picked by O(h)
-//     filter O (words [nblocks, 2 nblocks)): word picked by O(h), 3 + 3 bits picked by E(h)
-// A variant may be looked up in either (no false negatives in both).  The enumeration kernels use
-// filter E for a variant whose free residue sits at an odd position and filter O for an even one:
-// the 19 (or 20) variants at that position — and those at every other position of the same
-// parity — then read the SAME word: it is fetched once per slot, not once per candidate
-// (variant.cu), where a single filter cost one random L2 sector per candidate.  Word choice by multiply-shift (any word count);
+// Class filters (replace bloom_s, bloompat.h:26-58): FOUR blocked Bloom filters of `nblocks`
+// 64-bit words each, laid out back to back; every set-B key is in all four.
+//     filter c (words [c nblocks, (c + 1) nblocks)): word picked by the 48 bits of the hash that
+//     are blind to class c, 3 + 3 bits picked by the whole hash
+// A variant may be looked up in any of them (no false negatives in all four).  The enumeration
+// kernels use filter c for a variant whose free residue sits at a position of class c: the 19 (or
+// 20) variants at that position — and those at every other position of that class — then read the
+// SAME word: it is fetched once per slot, not once per candidate (variant.cu), where a single
+// filter cost one random L2 sector per candidate.  Word choice by multiply-shift (any word count);
 // normal polarity (1 = present; the reference's is inverted, an implementation detail).
 CB_HD uint32_t mulhi32(uint32_t x, uint32_t n) {
 #if defined(__CUDA_ARCH__)
@@ -159,29 +165,43 @@ CB_HD uint32_t mulhi32(uint32_t x, uint32_t n) {
   return (uint32_t)(((uint64_t)x * n) >> 32);
 #endif
 }
-// word index of h in the filter serving a free position of the given parity
-CB_HD uint64_t pfilter_word(uint64_t h, uint32_t nblocks, bool odd_free) {
-  return odd_free ? (uint64_t)mulhi32(field_even(h), nblocks) : (uint64_t)nblocks + mulhi32(field_odd(h), nblocks);
+// 32 well-mixed bits of h that do not change when a position of class c changes
+CB_HD uint32_t blind_field(uint64_t h, uint32_t c) {
+  const uint64_t g = h & ~(0xFFFFull << (16 * c));
+  uint32_t m = (uint32_t)g * 0x9E3779B1u + (uint32_t)(g >> 32) * 0x85EBCA77u;
+  m ^= m >> 15;
+  m *= 0x2C1B3C6Du;
+  m ^= m >> 13;
+  return m * 0x297A2D39u;
 }
+// word index of h in the filter serving a free position of class c
+CB_HD uint64_t pfilter_word(uint64_t h, uint32_t nblocks, uint32_t c) {
+  return (uint64_t)c * nblocks + mulhi32(blind_field(h, c), nblocks);
+}
+// The 32 bits the bit pattern is taken from: all four fields (two of them in each half).
+CB_HD uint32_t pattern_field(uint64_t h) { return (uint32_t)h ^ (uint32_t)(h >> 32); }
 // Bits per key in each 32-bit half of a filter word: 3 (default) or 2 (compile-time knob for A/B
 // runs of the enumeration kernels: four fewer instructions per candidate, ~2.5x the false positives).
 #ifndef CB_PATTERN_HALF_BITS
 #define CB_PATTERN_HALF_BITS 3
 #endif
-CB_HD uint32_t bloom_pat_lo(uint64_t h) {
-  uint32_t x = (uint32_t)h;
-  uint32_t p = (1u << (x & 31)) | (1u << ((x >> 5) & 31));
-  if (CB_PATTERN_HALF_BITS >= 3) p |= 1u << ((x >> 10) & 31);
+// Six 5-bit windows of the pattern field; each half of the word takes windows from both halves of
+// the field, so that the candidates of one slot (whose fields differ in 16 bits only) differ in
+// bits of both halves of the word.
+constexpr int CB_PAT_A0 = 0, CB_PAT_A1 = 16, CB_PAT_A2 = 5;     // low half of the word
+constexpr int CB_PAT_B0 = 21, CB_PAT_B1 = 10, CB_PAT_B2 = 26;   // high half
+CB_HD uint32_t bloom_pat_lo(uint32_t f) {
+  uint32_t p = (1u << ((f >> CB_PAT_A0) & 31)) | (1u << ((f >> CB_PAT_A1) & 31));
+  if (CB_PATTERN_HALF_BITS >= 3) p |= 1u << ((f >> CB_PAT_A2) & 31);
   return p;
 }
-CB_HD uint32_t bloom_pat_hi(uint64_t h) {
-  uint32_t x = (uint32_t)h;
-  uint32_t p = (1u << ((x >> 15) & 31)) | (1u << ((x >> 20) & 31));
-  if (CB_PATTERN_HALF_BITS >= 3) p |= 1u << ((x >> 25) & 31);
+CB_HD uint32_t bloom_pat_hi(uint32_t f) {
+  uint32_t p = (1u << ((f >> CB_PAT_B0) & 31)) | (1u << ((f >> CB_PAT_B1) & 31));
+  if (CB_PATTERN_HALF_BITS >= 3) p |= 1u << ((f >> CB_PAT_B2) & 31);
   return p;
 }
-CB_HD uint64_t bloom_pattern(uint64_t h) {
-  return (uint64_t)bloom_pat_lo(h) | ((uint64_t)bloom_pat_hi(h) << 32);
+CB_HD uint64_t bloom_pattern(uint32_t f) {
+  return (uint64_t)bloom_pat_lo(f) | ((uint64_t)bloom_pat_hi(f) << 32);
 }
 // x >> (s mod 32): on the device one funnel shift in wrap mode, no separate "& 31"
 CB_HD uint32_t shr_wrap(uint32_t x, uint32_t s) {
@@ -191,23 +211,23 @@ CB_HD uint32_t shr_wrap(uint32_t x, uint32_t s) {
   return x >> (s & 31);
 #endif
 }
-// Does filter word w contain bloom_pattern(f)?  The same test as (w & pattern) == pattern, written
-// as shifts of the word instead of a mask built from six variable shifts (tests/csrc/hd_check.cpp
-// checks the equivalence): no branches, 14 instructions.
-CB_HD bool pattern_hit(unsigned long long w, uint32_t f) {
-  const uint32_t lo = (uint32_t)w, hi = (uint32_t)(w >> 32);
-  uint32_t a = shr_wrap(lo, f) & shr_wrap(lo, f >> 5);
-  uint32_t b = shr_wrap(hi, f >> 15) & shr_wrap(hi, f >> 20);
+// Does the filter word (lo, hi) contain bloom_pattern(f)?  The same test as (w & pattern) == pattern,
+// written as shifts of the word instead of a mask built from six variable shifts (tests/csrc/
+// hd_check.cpp checks the equivalence): no branches.
+CB_HD bool pattern_hit_halves(uint32_t lo, uint32_t hi, uint32_t f) {
+  uint32_t a = shr_wrap(lo, f >> CB_PAT_A0) & shr_wrap(lo, f >> CB_PAT_A1);
+  uint32_t b = shr_wrap(hi, f >> CB_PAT_B0) & shr_wrap(hi, f >> CB_PAT_B1);
   if (CB_PATTERN_HALF_BITS >= 3) {
-    a &= shr_wrap(lo, f >> 10);
-    b &= shr_wrap(hi, f >> 25);
+    a &= shr_wrap(lo, f >> CB_PAT_A2);
+    b &= shr_wrap(hi, f >> CB_PAT_B2);
   }
   return (a & b & 1u) != 0u;
 }
-// bit pattern of h in the same filter: from the field the word index does not use
-CB_HD uint64_t pfilter_pattern(uint64_t h, bool odd_free) {
-  return bloom_pattern(odd_free ? field_odd(h) : field_even(h));
+CB_HD bool pattern_hit(unsigned long long w, uint32_t f) {
+  return pattern_hit_halves((uint32_t)w, (uint32_t)(w >> 32), f);
 }
+// bit pattern of h (the same in all four filters)
+CB_HD uint64_t pfilter_pattern(uint64_t h) { return bloom_pattern(pattern_field(h)); }
 
 // ---- score summand (overlap.cc:144-166) ---------------------------------------------------------
 

@@ -54,15 +54,10 @@ __device__ __forceinline__ bool seq_equal(const uint8_t* __restrict__ res, uint6
   return diff == 0;
 }
 
-// Parity-filter lookup of hash h (common.cuh): word from the filter that serves a free position of
-// the given parity, 3 + 3 bits from the field that word index does not use.
-__device__ __forceinline__ bool pfilter_word_test(unsigned long long w, uint64_t h, bool odd_free) {
-  return pattern_hit(w, odd_free ? field_odd(h) : field_even(h));
-}
-
+// Class-filter lookup of hash h (common.cuh) in the filter that serves free positions of class c.
 __device__ __forceinline__ bool pfilter_test(const unsigned long long* __restrict__ bloom,
-                                             uint32_t nblocks, uint64_t h, bool odd_free) {
-  return pfilter_word_test(__ldg(bloom + pfilter_word(h, nblocks, odd_free)), h, odd_free);
+                                             uint32_t nblocks, uint64_t h, uint32_t c) {
+  return pattern_hit(__ldg(bloom + pfilter_word(h, nblocks, c)), pattern_field(h));
 }
 
 // Variant descriptor in 31 bits: kind(3) | res1(5) | res2(5) | pos1(9) | pos2(9).  Positions up to

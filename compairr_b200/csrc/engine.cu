@@ -166,9 +166,9 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   cb_ctx* c = new (std::nothrow) cb_ctx;
   if (!c) return fail(nullptr, CB_ERR_NOMEM, "cb_create: out of host memory");
   c->cfg = *cfg;
-  // 24 bits per key in each parity filter: 0.33 % of the candidates reach the table stage instead
-  // of 0.58 % at 16 (measured at 10^8 keys: enumeration + table 25.5 -> 23.7 ms per 5.9e9 probes)
-  if (c->cfg.bloom_bits_per_key_x16 == 0) c->cfg.bloom_bits_per_key_x16 = 24 * 16;
+  // bits per key in EACH of the four class filters.  16: 0.6 % of the candidates reach the table
+  // stage (0.33 % at 24, for 1.5x the memory and the same four random updates per key)
+  if (c->cfg.bloom_bits_per_key_x16 == 0) c->cfg.bloom_bits_per_key_x16 = 16 * 16;
   if (c->cfg.table_load_pct == 0 || c->cfg.table_load_pct > 90) c->cfg.table_load_pct = 50;
   if (c->cfg.pairs_capacity == 0) c->cfg.pairs_capacity = 1ull << 24;
   if (c->cfg.seed == 0) c->cfg.seed = 1;
@@ -336,9 +336,9 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
     c->bloom_blocks = 0;
   } else {
     e = cb_dmalloc(&t.table, t.slots * sizeof(Slot));
-    if (e == cudaSuccess) e = cb_dmalloc(&t.bloom, (size_t)t.blocks * 16);
+    if (e == cudaSuccess) e = cb_dmalloc(&t.bloom, (size_t)t.blocks * 8 * CB_CLASSES);
   }
-  if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom, 0, (size_t)t.blocks * 16, c->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom, 0, (size_t)t.blocks * 8 * CB_CLASSES, c->stream);
   if (e == cudaSuccess) {
     launch_table_clear(t.table, t.slots, c->stream);
     e = cudaGetLastError();
@@ -359,15 +359,13 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
 // keys / 4.3 GB: 21 G CAS/s, 22 G stores/s, 49 G RED/s, together 11.4 ms; the same operations in
 // address order 2.4 ms — tools/bench_atomics.cu).  So a batch that is a sizeable part of the
 // table is first sorted by the hash bits that pick the home slot down to segments of 16 slots —
-// three 8-bit radix passes over (hash, index) pairs, 0.85 ms each at 10^8 — and the build kernel
-// then sweeps the table in address order.  The two parity-filter updates of a key are picked by
-// other hash fields and stay random REDs (2 x 2 ms at 10^8).  Measured, whole cb_build_b at 10^8:
-// 21 ms unsorted, 9.9 ms sorted with one address-ordered filter, 14.5 ms sorted with the parity
-// filters.  Small batches (the chunks of the upload pipeline, which hide behind the PCIe copy
+// three 8-bit radix passes over (h * CB_HOME_MUL, index) pairs, 0.85 ms each at 10^8 — and the
+// build kernel then sweeps the table in address order.  The class-filter updates of a key are
+// picked by other functions of the hash and stay random REDs (2 ms each at 10^8).  Small batches (the chunks of the upload pipeline, which hide behind the PCIe copy
 // anyway) keep the direct path.
 void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n) {
   const uint64_t table_bytes = t.slots * sizeof(Slot);
-  uint64_t* part_hash = nullptr;
+  uint64_t *key_in = nullptr, *part_hash = nullptr;
   uint32_t *iota = nullptr, *part_idx = nullptr;
   void* temp = nullptr;
   c->insert_launches = n ? 1 : 0;
@@ -377,18 +375,19 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
     while ((1ull << tbits) < t.slots) tbits++;
     const int pbits = std::max(8, (tbits - 4) / 8 * 8);  // whole radix passes
     size_t temp_bytes = 0;
-    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, s->d_hash + first, part_hash, iota, part_idx, n,
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, key_in, part_hash, iota, part_idx, n,
                                                     CB_PARTITION_TOP_BIT - pbits, CB_PARTITION_TOP_BIT, c->stream);
+    if (e == cudaSuccess) e = cb_dmalloc(&key_in, n * sizeof(uint64_t));
     if (e == cudaSuccess) e = cb_dmalloc(&part_hash, n * sizeof(uint64_t));
     if (e == cudaSuccess) e = cb_dmalloc(&iota, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cb_dmalloc(&part_idx, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cb_dmalloc(&temp, temp_bytes ? temp_bytes : 1);
     if (e == cudaSuccess) {
-      launch_iota(iota, n, c->stream);
-      e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, s->d_hash + first, part_hash, iota, part_idx, n,
+      launch_partition_keys(s->d_hash + first, n, key_in, iota, c->stream);  // h * CB_HOME_MUL: top bits = home slot
+      e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, key_in, part_hash, iota, part_idx, n,
                                           CB_PARTITION_TOP_BIT - pbits, CB_PARTITION_TOP_BIT, c->stream);
     }
-    if (e == cudaSuccess) c->insert_launches += 1 + 2 + pbits / 8;  // iota, histogram, scan, one sweep per digit
+    if (e == cudaSuccess) c->insert_launches += 1 + 2 + pbits / 8;  // keys, histogram, scan, one sweep per digit
     if (e != cudaSuccess) {  // no memory for the sort buffers: the direct path still works
       (void)cudaGetLastError();
       cb_dfree(part_hash);
@@ -399,6 +398,7 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
   }
   launch_build(s->d_meta, s->d_res, s->d_hash, part_hash, part_idx, first, n, c->cfg.ignore_genes != 0, t.table,
                t.slots - 1, t.bloom, t.blocks, c->stream);
+  cb_dfree(key_in);
   cb_dfree(part_hash);
   cb_dfree(iota);
   cb_dfree(part_idx);
@@ -444,8 +444,8 @@ int cb_adopt_table(cb_ctx* c, cb_dset* b, BuiltTable& t, bool owned) {
   c->dups_b = c->h_counters[CTR_DUPS];
   cudaEventElapsedTime(&c->stats.ms_dups_b, c->ev[1], c->ev[2]);
   c->stats.table_slots = c->slots;
-  c->stats.bloom_bytes = (uint64_t)c->bloom_blocks * 8;   // filter E
-  c->stats.bloom2_bytes = (uint64_t)c->bloom_blocks * 8;  // filter O
+  c->stats.bloom_bytes = (uint64_t)c->bloom_blocks * 8;                     // one class filter
+  c->stats.bloom2_bytes = (uint64_t)c->bloom_blocks * 8 * (CB_CLASSES - 1);  // the other three
   return CB_OK;
 }
 

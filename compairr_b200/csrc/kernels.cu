@@ -187,7 +187,7 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
     const uint64_t t = r * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
     bool walking = t < n;
     const uint64_t i = walking ? first + (part_idx ? part_idx[t] : t) : 0;
-    const uint64_t h = walking ? (part_hash ? part_hash[t] : hash[i]) : 0;
+    const uint64_t h = walking ? (part_hash ? part_hash[t] * CB_HOME_INV : hash[i]) : 0;  // sorted keys are h * CB_HOME_MUL
     const uint32_t tag = slot_tag(h);
     const unsigned long long tagged = ((unsigned long long)tag << 32) | i;  // i < 2^32 - 1 (checked at upload)
     uint64_t slot = table_home(h, mask);
@@ -201,8 +201,9 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
           cur = atomicCAS(idxp, SLOT_EMPTY, tagged);
           if (cur == SLOT_EMPTY) {  // we own the slot
             table[slot].hash = h;  // SeqRec.next is SEQ_NIL already (pack kernel / reset_next_kernel)
-            atomicOr(bloom + pfilter_word(h, bloom_blocks, true), pfilter_pattern(h, true));    // filter E
-            atomicOr(bloom + pfilter_word(h, bloom_blocks, false), pfilter_pattern(h, false));  // filter O
+            const unsigned long long pat = pfilter_pattern(h);
+#pragma unroll
+            for (uint32_t cls = 0; cls < CB_CLASSES; cls++) atomicOr(bloom + pfilter_word(h, bloom_blocks, cls), pat);
             walking = false;
           }
         }
@@ -250,6 +251,21 @@ void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const 
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t* p, uint64_t n) {
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
     p[i] = (uint32_t)i;
+}
+
+// Input of the partition sort: key = h * CB_HOME_MUL (its top bits are the home slot), value = index.
+__global__ void __launch_bounds__(256) partition_keys_kernel(const uint64_t* __restrict__ hash, uint64_t n,
+                                                             uint64_t* __restrict__ key, uint32_t* __restrict__ idx) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    key[i] = hash[i] * CB_HOME_MUL;
+    idx[i] = (uint32_t)i;
+  }
+}
+
+void launch_partition_keys(const uint64_t* hash, uint64_t n, uint64_t* key, uint32_t* idx, cudaStream_t st) {
+  if (n == 0) return;
+  const uint64_t blocks = (n + 255) / 256;
+  partition_keys_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(hash, n, key, idx);
 }
 
 void launch_iota(uint32_t* p, uint64_t n, cudaStream_t st) {
@@ -384,7 +400,7 @@ __global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ 
     const uint64_t h = P.a.hash[sidx];
     bool walking = in;
     if (P.use_bloom && in) {
-      walking = pfilter_test(P.bloom, P.bloom_blocks, h, true);
+      walking = pfilter_test(P.bloom, P.bloom_blocks, h, 0);
     }
     npass += walking;
     nmatch += probe_chains(&P, walking, h, pack_var(VK_IDENTICAL, 0, 0, 0, 0), sidx, (uint32_t)i,

@@ -48,7 +48,7 @@ struct ProbeParams {
   uint32_t* overflow_chunks;  // ids of chunks that overflowed the queue (first 64)
   const Slot* table;
   uint64_t table_mask;
-  const unsigned long long* bloom;   // parity filters E | O back to back (common.cuh)
+  const unsigned long long* bloom;   // the four class filters back to back (common.cuh)
   uint32_t bloom_blocks;             // 64-bit words per filter
   const uint64_t* ztab;  // global copy of the Zobrist table, zrows x sigma
   uint32_t zrows;        // rows staged in shared memory by the variant kernel (>= longest A + 1)
@@ -98,12 +98,13 @@ void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st);
 void launch_reset_next(SeqRec* meta, uint64_t n, cudaStream_t st);
 // Inserts sequences [first, first + n) of the set; writes their SeqRec.next links (which must be
 // SEQ_NIL on entry).
-// part_hash/part_idx (both or neither): the keys sorted by their top hash bits, position t =
-// sequence first + part_idx[t] with hash part_hash[t].
+// part_hash/part_idx (both or neither): the keys h * CB_HOME_MUL sorted by their top bits (= by home
+// slot), position t = sequence first + part_idx[t].
 void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const uint64_t* part_hash,
                   const uint32_t* part_idx, uint64_t first, uint64_t n, bool ignore_genes, Slot* table,
                   uint64_t mask, unsigned long long* bloom, uint32_t bloom_blocks, cudaStream_t st);
 void launch_iota(uint32_t* p, uint64_t n, cudaStream_t st);
+void launch_partition_keys(const uint64_t* hash, uint64_t n, uint64_t* key, uint32_t* idx, cudaStream_t st);
 void launch_count_dups(DeviceSetView s, unsigned long long* counters, cudaStream_t st);
 // -z: lead[i] = first member (file order) of i's (repertoire, V, J, sequence) group, sums[lead] =
 // the group's count (sums must be zero on entry), counters[CTR_DUPS] += members merged away

@@ -1,5 +1,5 @@
 // variant.cu — K3 for d = 1 and d = 2: on-the-fly variant enumeration by incremental XOR and the
-// parity-filter test (replaces generate_variants_1/_2, variants.cc:270-400; bloom_get,
+// class-filter test (replaces generate_variants_1/_2, variants.cc:270-400; bloom_get,
 // bloompat.h:55-58), and K4, the table stage (find_variant_matches, overlap.cc:168-251;
 // check_variant, variants.cc:166-240).
 //
@@ -9,7 +9,7 @@
 //   before position p, or — for d = 2 — the second substitution (j, .) of a triple (i, v, j).  All
 //   sigma candidates of a slot share
 //       base2   the variant's hash minus the Zobrist value of the free residue,
-//       word    their filter word (parity filters, common.cuh: the word index does not depend on
+//       word    their filter word (class filters, common.cuh: the word index does not depend on
 //               the free residue),
 //       zrow    the column of the TRANSPOSED Zobrist table (zT[r * ZP + pos]) their values sit in,
 //   so a lane that owns a slot keeps all of that in registers and the inner loop over the residues
@@ -114,7 +114,6 @@ struct SlotRegs {
   unsigned long long word;
   const uint64_t* zrow;  // &zT[pos]; residue r's value is zrow[r * ZP]
   uint32_t allowed;      // bit r: residue r is a candidate here (0: idle lane)
-  uint32_t emask;        // ~0: free position even (pattern field hi ^ lo), 0: odd (pattern field lo)
   uint32_t var;          // variant descriptor without the free residue
   uint32_t seed;         // seed number relative to a_first
 };
@@ -128,15 +127,7 @@ __device__ __forceinline__ void residue_loop(const ProbeParams& P, WarpCtx& c, c
 #pragma unroll
   for (int r = 0; r < SIGMA; r++) {
     const uint64_t hv = R.base2 ^ R.zrow[r * ZP];
-    const uint32_t lo = (uint32_t)hv, hi = (uint32_t)(hv >> 32);
-    const uint32_t f = lo ^ (hi & R.emask);
-    uint32_t a = shr_wrap(wlo, f) & shr_wrap(wlo, f >> 5);
-    uint32_t b = shr_wrap(whi, f >> 15) & shr_wrap(whi, f >> 20);
-    if (CB_PATTERN_HALF_BITS >= 3) {
-      a &= shr_wrap(wlo, f >> 10);
-      b &= shr_wrap(whi, f >> 25);
-    }
-    if (a & b & 1u) hits |= 1u << r;
+    if (pattern_hit_halves(wlo, whi, pattern_field(hv))) hits |= 1u << r;
   }
   hits &= R.allowed;
   // survivors: a fraction of a percent of the candidates (false positives + true matches)
@@ -150,8 +141,10 @@ __device__ __forceinline__ void residue_loop(const ProbeParams& P, WarpCtx& c, c
   }
 }
 
-__device__ __forceinline__ unsigned long long filter_word(const ProbeParams& P, uint64_t h, bool odd_free) {
-  return P.use_bloom ? __ldg(P.bloom + pfilter_word(h, P.bloom_blocks, odd_free)) : ~0ull;
+// the word every residue at a free position of class cls is looked up in (h: the variant's hash
+// with ANY residue there, or without one: the index is blind to that position)
+__device__ __forceinline__ unsigned long long filter_word(const ProbeParams& P, uint64_t h, uint32_t cls) {
+  return P.use_bloom ? __ldg(P.bloom + pfilter_word(h, P.bloom_blocks, cls)) : ~0ull;
 }
 
 // Transposed Zobrist table into shared memory: zT[r * ZP + p] = Z(p, r), rows beyond the table 0.
@@ -180,8 +173,8 @@ struct E1Layout {
   static constexpr size_t scan_u64 = INDELS ? (size_t)WB * 3 * ZP : 0;  // pre | sp | sm, [WB][ZP] each
   static constexpr size_t off_scan = VK_Q_BYTES;
   static constexpr size_t off_hash = off_scan + scan_u64 * 8;           // [WB] u64
-  static constexpr size_t off_ws = off_hash + WB * 8;                   // [WB][2] u64
-  static constexpr size_t off_len = off_ws + WB * 16;                   // [WB] u32
+  static constexpr size_t off_ws = off_hash + WB * 8;                   // [WB][4] u64: the seed's word in each class filter
+  static constexpr size_t off_len = off_ws + WB * 32;                   // [WB] u32
   static constexpr size_t off_cum = off_len + WB * 4;                   // [WB + 1] u32, residue slots
   static constexpr size_t off_dcum = off_cum + (WB + 1) * 4;            // [WB + 1] u32, deletion + identical items
   static constexpr size_t off_res = (off_dcum + (WB + 1) * 4 + 15) & ~(size_t)15;  // [WB][ZP] u8
@@ -234,10 +227,10 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
       my_off = off_len & ((1ull << 40) - 1);
       if (L >= P.len_lo && L <= P.len_hi) my_len = L;
     }
-    if (lane < 2 * nb) {  // filter O for even positions, filter E for odd ones (the word index ignores the substituted residue)
-      const uint64_t hk = __ldg(P.a.hash + P.a_first + first + (lane >> 1));
-      if (lane & 1) b_hash[lane >> 1] = hk;
-      b_ws[lane] = filter_word(P, hk, lane & 1);
+    if (lane < 4 * nb) {  // the seed's own word in each class filter = the word of all its substitution slots of that class
+      const uint64_t hk = __ldg(P.a.hash + P.a_first + first + (lane >> 2));
+      if ((lane & 3) == 0) b_hash[lane >> 2] = hk;
+      b_ws[lane] = filter_word(P, hk, lane & 3);
     }
     {  // slot and item counts -> inclusive prefix sums over the WB seeds
       const bool live = my_len != LEN_SKIP;
@@ -303,17 +296,16 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
       if (sub) {
         cmp = b_res[k * ZP + pos];
         R.base2 = h ^ zT[cmp * ZP + pos];
-        R.word = b_ws[2 * k + (pos & 1)];
+        R.word = b_ws[4 * k + pos_class(pos)];
         R.var = pack_var(VK_SUBSTITUTION, pos, 0, 0, 0);
       } else {  // insertion before position pos: the new residue sits at position pos of the variant;
                 // not the residue before it, which would repeat a variant (variants.cc:341-353)
         cmp = pos ? b_res[k * ZP + pos - 1] : 31u;
         R.base2 = h ^ pre[k * ZP + L] ^ pre[k * ZP + pos] ^ sp[k * ZP + pos];
-        R.word = filter_word(P, R.base2, pos & 1);
+        R.word = filter_word(P, R.base2, pos_class(pos));
         R.var = pack_var(VK_INSERTION, pos, 0, 0, 0);
       }
       R.allowed = valid ? (ALL & ~(1u << cmp)) : 0u;
-      R.emask = (pos & 1) ? 0u : ~0u;
       R.zrow = zT + pos;
       R.seed = (uint32_t)first + k;
       return R;
@@ -343,13 +335,13 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
       const uint64_t h = b_hash[k];
       uint64_t hv = h;
       bool valid = in;
-      unsigned long long w = b_ws[2 * k + 1];  // identical: filter E, whose word for the seed's own hash is the odd one
-      if (is_del) {
+      unsigned long long w = b_ws[4 * k];  // identical: any filter will do; the seed's word in filter 0 is at hand
+      if (is_del) {  // no free residue: any filter, spread over the four
         hv = h ^ pre[k * ZP + L] ^ pre[k * ZP + t] ^ sm[k * ZP + t + 1];
         valid = in && L > 1 && (t == 0 || b_res[k * ZP + t] != b_res[k * ZP + t - 1]);
-        w = filter_word(P, hv, true);
+        w = filter_word(P, hv, pos_class(t));
       }
-      const bool pass = valid & pattern_hit(w, field_odd(hv));
+      const bool pass = valid & pattern_hit(w, pattern_field(hv));
       submit(P, c, pass, hv, [is_del, t] {
         return is_del ? pack_var(VK_DELETION, t, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0);
       }, (uint32_t)first + k);
@@ -411,7 +403,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_const
     __syncwarp();
 
     if (part == 0) {  // identical + single substitutions (the reference emits them with d = 2 too, variants.cc:410-427)
-      const unsigned long long ws = filter_word(P, h, lane & 1);  // lane parity = position parity
+      const unsigned long long ws = filter_word(P, h, lane & 3);  // class of the lane = class of its position (p0 is a multiple of 32)
       for (uint32_t p0 = 0; p0 < L; p0 += 32) {
         const uint32_t pos = p0 + lane;
         const bool valid = pos < L;
@@ -419,21 +411,19 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_const
         const uint32_t cmp = sres[pc];
         SlotRegs R;
         R.base2 = h ^ zT[cmp * ZP + pc];
-        R.word = ws;  // pos and lane have the same parity (p0 is a multiple of 32)
+        R.word = ws;
         R.allowed = valid ? (ALL & ~(1u << cmp)) : 0u;
-        R.emask = (lane & 1) ? 0u : ~0u;
         R.zrow = zT + pc;
         R.var = pack_var(VK_SUBSTITUTION, pc, 0, 0, 0);
         R.seed = slocal;
         residue_loop<SIGMA, ZP, 3>(P, c, R);
       }
-      const unsigned long long w1 = __shfl_sync(FULL, ws, 1);  // filter E word of the seed's own hash
-      submit(P, c, lane == 0 && pattern_hit(w1, field_odd(h)), h, [] { return pack_var(VK_IDENTICAL, 0, 0, 0, 0); }, slocal);
+      submit(P, c, lane == 0 && pattern_hit(ws, pattern_field(h)), h, [] { return pack_var(VK_IDENTICAL, 0, 0, 0, 0); }, slocal);
     }
 
     // double substitutions i < j (variants.cc:357-400): slots x = (pair e, first residue v), lanes
     // over x, the loop over the second residue w.  The second substitution cannot change the filter
-    // word: for odd j it is filter E's word of h ^ Z(i,s[i]) ^ Z(i,v), for even j filter O's.
+    // word: it is the word of h ^ Z(i,s[i]) ^ Z(i,v) in the filter of j's class.
     const uint32_t n_x = L * (L - 1) / 2 * S1;
     auto load_slot = [&](uint32_t x) {
       SlotRegs R;
@@ -446,9 +436,8 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_const
       const uint32_t v = sub_residue(vp, si);
       const uint64_t b2v = h ^ zT[si * ZP + i] ^ zT[v * ZP + i];
       R.base2 = b2v ^ zT[sj * ZP + j];
-      R.word = filter_word(P, b2v, j & 1);
+      R.word = filter_word(P, b2v, pos_class(j));
       R.allowed = valid ? (ALL & ~(1u << sj)) : 0u;
-      R.emask = (j & 1) ? 0u : ~0u;
       R.zrow = zT + j;
       R.var = pack_var(VK_SUB_SUB, i, v, j, 0);
       R.seed = slocal;
@@ -476,15 +465,14 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_const
 // =====================================================================================================
 
 __device__ __forceinline__ void filter_step(const ProbeParams& P, const uint64_t (&hv)[VK_U],
-                                            const bool (&odd)[VK_U], bool (&pass)[VK_U]) {
+                                            const uint32_t (&cls)[VK_U], bool (&pass)[VK_U]) {
   if (!P.use_bloom) return;
   unsigned long long w[VK_U];
 #pragma unroll
   for (int u = 0; u < VK_U; u++)  // unconditional: an inactive candidate's hash is a valid address too
-    w[u] = __ldg(P.bloom + pfilter_word(hv[u], P.bloom_blocks, odd[u]));
+    w[u] = __ldg(P.bloom + pfilter_word(hv[u], P.bloom_blocks, cls[u]));
 #pragma unroll
-  for (int u = 0; u < VK_U; u++)
-    pass[u] = pass[u] & pattern_hit(w[u], odd[u] ? field_odd(hv[u]) : field_even(hv[u]));
+  for (int u = 0; u < VK_U; u++) pass[u] = pass[u] & pattern_hit(w[u], pattern_field(hv[u]));
 }
 
 // Per-warp scratch of the generic kernel for one seed.
@@ -563,13 +551,14 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
   for (uint32_t base = 0; base < T; base += 32 * VK_U) {
     uint64_t hv[VK_U];
     uint32_t var[VK_U];
-    bool pass[VK_U], odd[VK_U];
+    bool pass[VK_U];
+    uint32_t cls[VK_U];
 #pragma unroll
     for (int u = 0; u < VK_U; u++) {
       const uint32_t idx = base + u * 32 + c.lane;
       pass[u] = idx < T;
       hv[u] = h;
-      odd[u] = true;
+      cls[u] = 0;
       var[u] = pack_var(VK_IDENTICAL, 0, 0, 0, 0);
       if (pass[u] && idx >= 1) {
         uint32_t t = idx - 1;
@@ -577,27 +566,27 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
           const uint32_t pos = t / S1, rp = t - pos * S1;
           const uint32_t r = sub_residue(rp, sres[pos]);
           hv[u] = h ^ s.zo[pos] ^ zval<ZG>(z, pos * SIGMA + r);
-          odd[u] = pos & 1;
+          cls[u] = pos_class(pos);
           var[u] = pack_var(VK_SUBSTITUTION, pos, r, 0, 0);
         } else if (INDELS) {
           t -= nsub;
           if (t < L) {  // deletion of residue t: only at the start of a run, only if L > 1
             pass[u] = (L > 1) && (t == 0 || sres[t] != sres[t - 1]);
             hv[u] = vjh ^ s.pre()[t] ^ s.sm()[t + 1];
-            odd[u] = t & 1;  // no free residue: either filter, alternate for balance
+            cls[u] = pos_class(t);  // no free residue: any filter, spread over the four
             var[u] = pack_var(VK_DELETION, t, 0, 0, 0);
           } else {  // insertion of residue r before seed position pos
             t -= L;
             const uint32_t pos = t / SIGMA, r = t - pos * SIGMA;
             pass[u] = (pos == 0) || (r != sres[pos - 1]);
             hv[u] = vjh ^ s.pre()[pos] ^ zval<ZG>(z, pos * SIGMA + r) ^ s.sp()[pos];
-            odd[u] = pos & 1;  // the inserted residue sits at position pos of the variant
+            cls[u] = pos_class(pos);  // the inserted residue sits at position pos of the variant
             var[u] = pack_var(VK_INSERTION, pos, r, 0, 0);
           }
         }
       }
     }
-    filter_step(P, hv, odd, pass);
+    filter_step(P, hv, cls, pass);
 #pragma unroll
     for (int u = 0; u < VK_U; u++) {
       const uint32_t v = var[u];
@@ -607,7 +596,7 @@ __device__ __forceinline__ void phase_a(const ProbeParams& P, WarpCtx& c, const 
 }
 
 // Phase B: double substitutions i < j (variants.cc:357-400).  Outer (i, v) warp-uniform, lanes over
-// the slots (j > i, r) of the second substitution, two filter words per outer iteration.
+// the slots (j > i, r) of the second substitution, one filter word per class of j per outer iteration.
 template <int SIGMA, bool ZG>
 __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const uint64_t* __restrict__ z,
                                         const uint8_t* sres, const SeedScratch& s,
@@ -618,7 +607,9 @@ __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const 
   for (uint32_t o = part; o < nouter; o += split) {
     const uint32_t i = o / S1, v = sub_residue(o - i * S1, sres[i]);
     const uint64_t b2 = h ^ s.zo[i] ^ zval<ZG>(z, i * SIGMA + v);
-    const unsigned long long we = filter_word(P, b2, true), wo = filter_word(P, b2, false);
+    unsigned long long wc[CB_CLASSES];
+#pragma unroll
+    for (uint32_t q = 0; q < CB_CLASSES; q++) wc[q] = filter_word(P, b2, q);
     const uint32_t ninner = SIGMA * (L - 1 - i);
     for (uint32_t tb = 0; tb < ninner; tb += 32) {
       const uint32_t t = tb + c.lane;
@@ -628,7 +619,9 @@ __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const 
       const uint32_t j = in ? i + 1 + jj : i;  // inactive lanes read a valid row
       const uint32_t cmp = sres[j];
       const uint64_t hv = b2 ^ s.zo[j] ^ zval<ZG>(z, j * SIGMA + r);
-      const bool pass = in & (r != cmp) & pattern_hit((j & 1) ? we : wo, (j & 1) ? field_odd(hv) : field_even(hv));
+      const uint32_t jc = pos_class(j);
+      const unsigned long long w = jc == 0 ? wc[0] : jc == 1 ? wc[1] : jc == 2 ? wc[2] : wc[3];
+      const bool pass = in & (r != cmp) & pattern_hit(w, pattern_field(hv));
       submit(P, c, pass, hv, [i, v, j, r] { return pack_var(VK_SUB_SUB, i, v, j, r); }, slocal);
     }
   }
@@ -814,6 +807,7 @@ static int launch_by_length(const ProbeParams& p_in, int sm_count, cudaStream_t 
     if (p_in.lmax >= lo) {
       p.len_lo = lo;
       p.len_hi = f96;
+      cudaMemsetAsync(p.counters + CTR_WORK, 0, sizeof(unsigned long long), st);  // every launch walks all seeds: its own dispenser
       if ((l = launch_fast<SIGMA, 96>(p, sm_count, st, err)) < 0) return l;
       launches += l;
       lo = f96 + 1;
@@ -822,6 +816,7 @@ static int launch_by_length(const ProbeParams& p_in, int sm_count, cudaStream_t 
   if (p_in.lmax >= lo) {
     p.len_lo = lo;
     p.len_hi = 0xffffffffu;
+    if (launches) cudaMemsetAsync(p.counters + CTR_WORK, 0, sizeof(unsigned long long), st);
     if ((l = launch_generic<SIGMA>(p, sm_count, st, err)) < 0) return l;
     launches += l;
   }

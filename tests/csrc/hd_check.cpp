@@ -3,16 +3,17 @@
 // tests/test_parity_fields.py; test infrastructure, not a product path.  No GPU involved.
 //
 // Checks, on random sequences:
-//   1. the Zobrist values are structured by position parity: a substitution at an odd position
-//      leaves field_even() of the hash unchanged, one at an even position leaves field_odd()
-//      unchanged — for insertions (everything behind the insertion shifts by one) and for the
-//      second substitution of a double substitution alike;
+//   1. the Zobrist values are structured by position class (p mod 4): a substitution at a position
+//      of class c leaves blind_field(h, c) unchanged — for insertions (everything behind the
+//      insertion shifts by one) and for the second substitution of a double substitution alike;
 //   2. therefore pfilter_word() is the same for every residue at a slot, in the filter the
-//      enumeration kernels pick for that slot (odd free position -> filter E, even -> filter O);
-//   3. the two filters never overlap (E words in [0, n), O words in [n, 2n));
-//   4. a key inserted into both filters is found by either lookup (no false negatives);
+//      enumeration kernels pick for that slot (free position of class c -> filter c);
+//   3. the four filters never overlap (filter c owns words [c n, (c + 1) n));
+//   4. a key inserted into all four filters is found by every lookup (no false negatives);
 //   5. probe_count() equals a literal enumeration count of the reference's rules
-//      (variants.cc:260-428) for small sequences.
+//      (variants.cc:260-428) for small sequences;
+//   6. the home-slot multiplier is invertible (the partitioned build sorts h * K and recovers h),
+//      table_home() stays in range and sees every class of positions.
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -57,31 +58,37 @@ int main() {
       for (auto& x : s) x = (uint8_t)(rnd() % sigma);
       const uint64_t vj = vj_hash(seed, (uint32_t)(rnd() % 60), (uint32_t)(rnd() % 13));
       const uint64_t h = hash_of(s, seed, vj);
-      std::vector<unsigned long long> filt(2 * (size_t)nblocks, 0);
-      // 4: insert h into both filters, look it up both ways
-      filt[pfilter_word(h, nblocks, true)] |= pfilter_pattern(h, true);
-      filt[pfilter_word(h, nblocks, false)] |= pfilter_pattern(h, false);
-      for (bool odd : {true, false}) {
-        const uint64_t w = pfilter_word(h, nblocks, odd);
-        CHECK(odd ? w < nblocks : (w >= nblocks && w < 2ull * nblocks));  // 3
-        CHECK((filt[w] & pfilter_pattern(h, odd)) == pfilter_pattern(h, odd));
+      std::vector<unsigned long long> filt(CB_CLASSES * (size_t)nblocks, 0);
+      // 4: insert h into all four filters, look it up in each
+      for (uint32_t c = 0; c < CB_CLASSES; c++) filt[pfilter_word(h, nblocks, c)] |= pfilter_pattern(h);
+      for (uint32_t c = 0; c < CB_CLASSES; c++) {
+        const uint64_t w = pfilter_word(h, nblocks, c);
+        CHECK(w >= (uint64_t)c * nblocks && w < (uint64_t)(c + 1) * nblocks);  // 3
+        CHECK(pattern_hit(filt[w], pattern_field(h)));
       }
+      // 6
+      CHECK(h * CB_HOME_MUL * CB_HOME_INV == h);
+      for (int bits : {3, 21, 28, 33}) CHECK(table_home(h, (1ull << bits) - 1) < (1ull << bits));
       // 1 + 2: substitutions
       for (uint32_t p = 0; p < L; p++) {
-        const bool odd = p & 1;
+        const uint32_t c = pos_class(p);
         for (int r = 0; r < sigma; r++) {
           std::vector<uint8_t> t = s;
           t[p] = (uint8_t)r;
           const uint64_t hv = hash_of(t, seed, vj);
           CHECK(hv == (h ^ zobrist_gen(seed, p, s[p]) ^ zobrist_gen(seed, p, (uint32_t)r)));
-          CHECK(odd ? field_even(hv) == field_even(h) : field_odd(hv) == field_odd(h));
-          CHECK(pfilter_word(hv, nblocks, odd) == pfilter_word(h, nblocks, odd));
-          // 1 for double substitutions: a second one at j > p of either parity
-          for (uint32_t j = p + 1; j < L && j < p + 4; j++) {
+          CHECK(blind_field(hv, c) == blind_field(h, c));
+          CHECK(pfilter_word(hv, nblocks, c) == pfilter_word(h, nblocks, c));
+          if (r != s[p]) {  // ... while the hash itself, its pattern field and (almost always) the home slot move
+            CHECK(hv != h);
+            CHECK(pattern_field(hv) != pattern_field(h));
+          }
+          // 1 for double substitutions: a second one at j > p of any class
+          for (uint32_t j = p + 1; j < L && j < p + 6; j++) {
             std::vector<uint8_t> u = t;
             u[j] = (uint8_t)((s[j] + 1) % sigma);
             const uint64_t h2 = hash_of(u, seed, vj);
-            CHECK(pfilter_word(h2, nblocks, j & 1) == pfilter_word(hv, nblocks, j & 1));
+            CHECK(pfilter_word(h2, nblocks, pos_class(j)) == pfilter_word(hv, nblocks, pos_class(j)));
           }
         }
       }
@@ -92,12 +99,28 @@ int main() {
           std::vector<uint8_t> t(s.begin(), s.begin() + p);
           t.push_back((uint8_t)r);
           t.insert(t.end(), s.begin() + p, s.end());
-          const uint64_t w = pfilter_word(hash_of(t, seed, vj), nblocks, p & 1);
+          const uint64_t w = pfilter_word(hash_of(t, seed, vj), nblocks, pos_class(p));
           if (r == 0) first = w;
           CHECK(w == first);
         }
       }
     }
+  }
+  // 6: the home slot depends on positions of every class (flip one residue per class, the slot
+  // moves in the large majority of cases)
+  {
+    int moved[CB_CLASSES] = {0, 0, 0, 0};
+    for (int it = 0; it < 400; it++) {
+      std::vector<uint8_t> s(16);
+      for (auto& x : s) x = (uint8_t)(rnd() % 20);
+      const uint64_t h = hash_of(s, seed, 0);
+      for (uint32_t p = 4; p < 8; p++) {
+        auto t = s;
+        t[p] = (uint8_t)((t[p] + 1) % 20);
+        moved[pos_class(p)] += table_home(hash_of(t, seed, 0), (1ull << 24) - 1) != table_home(h, (1ull << 24) - 1);
+      }
+    }
+    for (uint32_t c = 0; c < CB_CLASSES; c++) CHECK(moved[c] > 390);
   }
   // pattern_hit(w, f) is (w & bloom_pattern(f)) == bloom_pattern(f), for sparse and dense words
   for (int it = 0; it < 200000; it++) {
@@ -106,6 +129,7 @@ int main() {
     if (it % 3 == 0) w |= rnd() | rnd();
     if (it % 5 == 0) w |= bloom_pattern(f);
     CHECK(pattern_hit(w, f) == ((w & bloom_pattern(f)) == bloom_pattern(f)));
+    CHECK(__builtin_popcountll(bloom_pattern(f)) <= 2 * CB_PATTERN_HALF_BITS && bloom_pattern(f) != 0);
   }
   // 5: probe_count against a literal enumeration of distinct variant strings + the rules
   for (int it = 0; it < 200; it++) {

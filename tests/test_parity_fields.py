@@ -1,6 +1,6 @@
 """Host-side check of compairr_b200/csrc/common.cuh (the integer arithmetic shared by the kernels
-and the engine): the parity structure of the Zobrist values, the parity-filter addressing and the
-closed-form variant count.  Compiles tests/csrc/hd_check.cpp with g++; no GPU."""
+and the engine): the position-class structure of the Zobrist values, the class-filter addressing, the
+home-slot multiplier and the closed-form variant count.  Compiles tests/csrc/hd_check.cpp with g++; no GPU."""
 import os
 import subprocess
 

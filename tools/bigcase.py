@@ -21,7 +21,7 @@ def mk(seed, reps):
     return synth.make_set(seed, reps, 100000, pool=pool, indel_mutants=True, workers=14)
 b = cached("b", lambda: mk(3, 1000)); a = cached("a", lambda: mk(2, 100))
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
-bpk = float(sys.argv[2]) if len(sys.argv) > 2 else 16.0
+bpk = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0   # 0 = the engine's default
 for d, ind in [(1, True), (2, False)]:
     if which not in ("both", f"d{d}"): continue
     with Engine(OverlapOptions(differences=d, indels=ind, bloom_bits_per_key=bpk), n_reps_a=a.n_reps) as eng:
