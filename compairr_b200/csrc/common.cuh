@@ -117,9 +117,24 @@ CB_HD uint64_t splitmix64(uint64_t x) {
 // only); every hash match is verified on the residues anyway.
 constexpr uint32_t CB_CLASSES = 4;
 CB_HD uint32_t pos_class(uint32_t p) { return p & 3u; }
+// The 16-bit values of one position are non-zero and pairwise distinct (redrawn until they are), so
+// a substitution always changes the hash and its pattern field; used on the host to fill the table
+// (and by the tests), never per probe.
 CB_HD uint64_t zobrist_gen(uint64_t seed, uint32_t p, uint32_t r) {
-  const uint64_t x = splitmix64(splitmix64(seed ^ 0x5A0B1157ull) + ((uint64_t)p << 8) + r) >> 48;
-  return x << (16 * pos_class(p));
+  uint32_t vals[32];
+  const uint64_t base = splitmix64(seed ^ 0x5A0B1157ull) + ((uint64_t)p << 16);
+  for (uint32_t q = 0; q <= (r & 31u); q++) {
+    for (uint32_t attempt = 0;; attempt++) {
+      const uint32_t x = (uint32_t)(splitmix64(base + (attempt << 8) + q) >> 48);
+      bool fresh = x != 0;
+      for (uint32_t k = 0; k < q && fresh; k++) fresh = vals[k] != x;
+      if (fresh) {
+        vals[q] = x;
+        break;
+      }
+    }
+  }
+  return (uint64_t)vals[r & 31u] << (16 * pos_class(p));
 }
 // 32 bits of the hash that depend on every position, for the "possibly the same sequence" tag of
 // a table slot.
@@ -151,7 +166,7 @@ constexpr int CB_PARTITION_TOP_BIT = 64;  // partition keys are bits [64 - p, 64
 // Class filters (replace bloom_s, bloompat.h:26-58): FOUR blocked Bloom filters of `nblocks`
 // 64-bit words each, laid out back to back; every set-B key is in all four.
 //     filter c (words [c nblocks, (c + 1) nblocks)): word picked by the 48 bits of the hash that
-//     are blind to class c, 3 + 3 bits picked by the whole hash
+//     are blind to class c, 3 + 3 bits picked by field c
 // A variant may be looked up in any of them (no false negatives in all four).  The enumeration
 // kernels use filter c for a variant whose free residue sits at a position of class c: the 19 (or
 // 20) variants at that position — and those at every other position of that class — then read the
@@ -178,16 +193,23 @@ CB_HD uint32_t blind_field(uint64_t h, uint32_t c) {
 CB_HD uint64_t pfilter_word(uint64_t h, uint32_t nblocks, uint32_t c) {
   return (uint64_t)c * nblocks + mulhi32(blind_field(h, c), nblocks);
 }
-// The 32 bits the bit pattern is taken from: all four fields (two of them in each half).
-CB_HD uint32_t pattern_field(uint64_t h) { return (uint32_t)h ^ (uint32_t)(h >> 32); }
+// The 32 bits the bit pattern of h in filter c is cut from: field c — the one field the index of
+// that filter does NOT see, and the only one that differs between the candidates of a slot — spread
+// over 32 bits by a GF(2)-linear map.  Taken from that field alone, because a seed that is itself in
+// set B has its own key in the very word its substitution variants are looked up in: pattern bits
+// drawn from the other fields would be the same as the key's, i.e. set, and the test would be down
+// to the remaining ones (measured with such a pattern: 3 x the false positives).  Linear, so that
+// the pattern field of a variant is the XOR of a per-slot part and a per-(position, residue) part:
+// the enumeration loop reads the latter from a 32-bit table and never forms the 64-bit hash.
+CB_HD uint32_t class_field(uint64_t h, uint32_t c) { return (uint32_t)(h >> (16 * c)) & 0xFFFFu; }
+CB_HD uint32_t expand16(uint32_t x) { return x ^ (x << 3) ^ (x << 7) ^ (x << 11) ^ (x << 14) ^ (x << 16); }
+CB_HD uint32_t pattern_field(uint64_t h, uint32_t c) { return expand16(class_field(h, c)); }
 // Bits per key in each 32-bit half of a filter word: 3 (default) or 2 (compile-time knob for A/B
 // runs of the enumeration kernels: four fewer instructions per candidate, ~2.5x the false positives).
 #ifndef CB_PATTERN_HALF_BITS
 #define CB_PATTERN_HALF_BITS 3
 #endif
-// Six 5-bit windows of the pattern field; each half of the word takes windows from both halves of
-// the field, so that the candidates of one slot (whose fields differ in 16 bits only) differ in
-// bits of both halves of the word.
+// Six 5-bit windows of the pattern field.
 constexpr int CB_PAT_A0 = 0, CB_PAT_A1 = 16, CB_PAT_A2 = 5;     // low half of the word
 constexpr int CB_PAT_B0 = 21, CB_PAT_B1 = 10, CB_PAT_B2 = 26;   // high half
 CB_HD uint32_t bloom_pat_lo(uint32_t f) {
@@ -226,8 +248,8 @@ CB_HD bool pattern_hit_halves(uint32_t lo, uint32_t hi, uint32_t f) {
 CB_HD bool pattern_hit(unsigned long long w, uint32_t f) {
   return pattern_hit_halves((uint32_t)w, (uint32_t)(w >> 32), f);
 }
-// bit pattern of h (the same in all four filters)
-CB_HD uint64_t pfilter_pattern(uint64_t h) { return bloom_pattern(pattern_field(h)); }
+// bit pattern of h in filter c
+CB_HD uint64_t pfilter_pattern(uint64_t h, uint32_t c) { return bloom_pattern(pattern_field(h, c)); }
 
 // ---- score summand (overlap.cc:144-166) ---------------------------------------------------------
 

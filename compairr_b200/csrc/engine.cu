@@ -396,8 +396,14 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
       part_idx = nullptr;
     }
   }
+  // a sorted (large) batch: filters in their own L2-blocked passes, the build kernel sweeps the table only
+  unsigned long long* bloom_in_build = t.bloom;
+  if (part_hash && !(c->cfg.flags & CB_FLAG_FILTERS_IN_BUILD)) {
+    c->insert_launches += launch_filters(s->d_hash + first, n, t.bloom, t.blocks, c->sm_count, c->stream);
+    bloom_in_build = nullptr;
+  }
   launch_build(s->d_meta, s->d_res, s->d_hash, part_hash, part_idx, first, n, c->cfg.ignore_genes != 0, t.table,
-               t.slots - 1, t.bloom, t.blocks, c->stream);
+               t.slots - 1, bloom_in_build, t.blocks, c->stream);
   cb_dfree(key_in);
   cb_dfree(part_hash);
   cb_dfree(iota);
@@ -753,9 +759,10 @@ extern "C" int cb_run(cb_ctx* c, const cb_dset* a, uint64_t first, uint64_t coun
     p.counters = c->d_counters;
     p.lmax = a->longest;
     p.force_generic = (c->cfg.flags & CB_FLAG_GENERIC_KERNEL) ? 1u : 0u;
-    // one matrix row in shared memory per CTA (d=1 kernel) when it is small enough
-    p.tile_cols = (!existence && !c->cfg.no_matrix && !(c->cfg.flags & CB_FLAG_NO_SMEM_TILE) && cols <= 4096)
-                      ? (uint32_t)cols : 0;
+    // a small matrix is accumulated in CTA-private shared-memory tiles with warp-aggregated atomics
+    p.tile_cells = (!existence && !c->cfg.no_matrix && !(c->cfg.flags & CB_FLAG_NO_SMEM_TILE) &&
+                    c->rows * cols <= MATRIX_TILE_MAX_CELLS)
+                       ? (uint32_t)(c->rows * cols) : 0;
     p.score = c->cfg.score;
     p.ignore_counts = c->cfg.ignore_counts != 0;
     p.ignore_genes = c->cfg.ignore_genes != 0;

@@ -201,9 +201,11 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
           cur = atomicCAS(idxp, SLOT_EMPTY, tagged);
           if (cur == SLOT_EMPTY) {  // we own the slot
             table[slot].hash = h;  // SeqRec.next is SEQ_NIL already (pack kernel / reset_next_kernel)
-            const unsigned long long pat = pfilter_pattern(h);
+            if (bloom) {  // direct (pipelined-upload) path: the key's bits in the four class filters
 #pragma unroll
-            for (uint32_t cls = 0; cls < CB_CLASSES; cls++) atomicOr(bloom + pfilter_word(h, bloom_blocks, cls), pat);
+              for (uint32_t cls = 0; cls < CB_CLASSES; cls++)
+                atomicOr(bloom + pfilter_word(h, bloom_blocks, cls), pfilter_pattern(h, cls));
+            }
             walking = false;
           }
         }
@@ -246,6 +248,40 @@ void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const 
   const uint64_t blocks = (n + 255) / 256;
   build_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
       meta, res, hash, part_hash, part_idx, first, n, ignore_genes, table, mask, bloom, bloom_blocks);
+}
+
+// The class filters of a large set, built apart from the table: one launch per (filter, range of its
+// words), every launch a streaming pass over all hashes that sets the bits of the keys whose word
+// falls into the range.  Random 8-byte REDs into a range that fits L2 run at L2 speed; the same
+// REDs spread over four filters of 190 MiB each, interleaved with the table sweep, were DRAM
+// sector read-modify-writes (measured inside build_kernel: +4 ms per filter at 10^8 keys).
+// Duplicate keys set the same bits again: harmless.
+__global__ void __launch_bounds__(256)
+filter_kernel(const uint64_t* __restrict__ hash, uint64_t n, unsigned long long* bloom, uint32_t bloom_blocks,
+              uint32_t cls, uint32_t w_lo, uint32_t w_hi) {
+  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+    const uint64_t h = hash[i];
+    const uint32_t w = mulhi32(blind_field(h, cls), bloom_blocks);
+    if (w >= w_lo && w < w_hi) atomicOr(bloom + (uint64_t)cls * bloom_blocks + w, pfilter_pattern(h, cls));
+  }
+}
+
+int launch_filters(const uint64_t* hash, uint64_t n, unsigned long long* bloom, uint32_t bloom_blocks, int sm_count,
+                   cudaStream_t st) {
+  if (n == 0) return 0;
+  // word ranges of at most ~48 MiB: resident in L2 beside the streamed hashes
+  const uint64_t bytes = (uint64_t)bloom_blocks * 8;
+  uint32_t parts = (uint32_t)((bytes + (48ull << 20) - 1) / (48ull << 20));
+  if (parts < 1) parts = 1;
+  if (parts > 16) parts = 16;
+  const uint64_t blocks = (n + 255) / 256;
+  const unsigned grid = (unsigned)(blocks < (uint64_t)sm_count * 8 ? blocks : (uint64_t)sm_count * 8);
+  for (uint32_t cls = 0; cls < CB_CLASSES; cls++)
+    for (uint32_t k = 0; k < parts; k++) {
+      const uint32_t lo = (uint32_t)((uint64_t)bloom_blocks * k / parts), hi = (uint32_t)((uint64_t)bloom_blocks * (k + 1) / parts);
+      filter_kernel<<<grid, 256, 0, st>>>(hash, n, bloom, bloom_blocks, cls, lo, hi);
+    }
+  return (int)(CB_CLASSES * parts);
 }
 
 __global__ void __launch_bounds__(256) iota_kernel(uint32_t* p, uint64_t n) {
@@ -387,7 +423,9 @@ void launch_count_probes(DeviceSetView a, uint64_t first, uint64_t count, uint32
 // K3/K4, d = 0: one thread per seed (one probe per seed: a hash join).
 // ---------------------------------------------------------------------------------------------
 
-__global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ ProbeParams P) {
+__global__ void __launch_bounds__(256, 4) identical_kernel(const __grid_constant__ ProbeParams P) {
+  extern __shared__ __align__(16) unsigned char tile_raw[];
+  double* const tile = matrix_tile_begin(P, tile_raw);
   uint32_t nmatch = 0, npass = 0;
   const uint32_t lane = threadIdx.x & 31;
   // warp-uniform trip count: probe_chains() re-converges with warp-wide votes
@@ -403,9 +441,9 @@ __global__ void __launch_bounds__(256) identical_kernel(const __grid_constant__ 
       walking = pfilter_test(P.bloom, P.bloom_blocks, h, 0);
     }
     npass += walking;
-    nmatch += probe_chains(&P, walking, h, pack_var(VK_IDENTICAL, 0, 0, 0, 0), sidx, (uint32_t)i,
-                           nullptr, 0);
+    nmatch += probe_chains(&P, walking, h, pack_var(VK_IDENTICAL, 0, 0, 0, 0), sidx, (uint32_t)i, tile);
   }
+  matrix_tile_flush(P, tile);
   flush_counters(P, nmatch, P.count_bloom ? npass : 0);
 }
 
@@ -415,8 +453,10 @@ int launch_probe(const ProbeParams& p, int sm_count, cudaStream_t st, const char
   if (p.w_count == 0) return 0;
   if (p.differences == 0) {
     const uint64_t blocks = (p.w_count + 255) / 256;
-    const uint64_t cap = (uint64_t)sm_count * 8;
-    identical_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, 0, st>>>(p);
+    const size_t smem = (size_t)p.tile_cells * sizeof(double);
+    if (smem > 48 * 1024) cudaFuncSetAttribute(identical_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const uint64_t cap = (uint64_t)sm_count * (smem ? (smem > 48 * 1024 ? 2 : 4) : 8);
+    identical_kernel<<<(unsigned)(blocks < cap ? blocks : cap), 256, smem, st>>>(p);
     return 1;
   }
   return launch_variant_kernels(p, sm_count, st, err);

@@ -34,6 +34,8 @@ struct DeviceSetView {
   uint64_t index_base;
 };
 
+constexpr uint32_t MATRIX_TILE_MAX_CELLS = 10240;  // shared-memory matrix tile: 80 KB, 100 x 100 repertoires (C2) fit
+
 struct ProbeParams {
   DeviceSetView a;
   DeviceSetView b;
@@ -62,7 +64,8 @@ struct ProbeParams {
   uint32_t lmax;   // longest seed of the set (decides which enumeration kernels are launched)
   uint32_t len_lo, len_hi;  // an enumeration launch handles the seeds with len_lo <= length <= len_hi
   uint32_t force_generic;   // A/B and tests: every seed through the generic (any-length) kernel
-  uint32_t tile_cols;  // > 0: CTAs keep one matrix row (n_cols doubles) in shared memory
+  uint32_t tile_cells;  // > 0: the matrix (rows x n_cols = tile_cells doubles) is small: CTAs of the table stage
+                        // accumulate into a private copy in shared memory (device_utils.cuh accumulate_warp)
   uint32_t split;  // d=2: work items per seed
   int32_t score;
   uint8_t ignore_counts, ignore_genes, existence, no_matrix;
@@ -97,12 +100,15 @@ void launch_hash(const SeqRec* meta, const uint8_t* res, uint64_t n, const uint6
 void launch_table_clear(Slot* table, uint64_t slots, cudaStream_t st);
 void launch_reset_next(SeqRec* meta, uint64_t n, cudaStream_t st);
 // Inserts sequences [first, first + n) of the set; writes their SeqRec.next links (which must be
-// SEQ_NIL on entry).
+// SEQ_NIL on entry).  bloom == nullptr: table only (the filters are built by launch_filters).
 // part_hash/part_idx (both or neither): the keys h * CB_HOME_MUL sorted by their top bits (= by home
 // slot), position t = sequence first + part_idx[t].
 void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const uint64_t* part_hash,
                   const uint32_t* part_idx, uint64_t first, uint64_t n, bool ignore_genes, Slot* table,
                   uint64_t mask, unsigned long long* bloom, uint32_t bloom_blocks, cudaStream_t st);
+// the four class filters of hashes [0, n), L2-sized word ranges at a time; returns the launches made
+int launch_filters(const uint64_t* hash, uint64_t n, unsigned long long* bloom, uint32_t bloom_blocks, int sm_count,
+                   cudaStream_t st);
 void launch_iota(uint32_t* p, uint64_t n, cudaStream_t st);
 void launch_partition_keys(const uint64_t* hash, uint64_t n, uint64_t* key, uint32_t* idx, cudaStream_t st);
 void launch_count_dups(DeviceSetView s, unsigned long long* counters, cudaStream_t st);

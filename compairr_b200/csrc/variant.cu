@@ -112,7 +112,9 @@ __device__ __forceinline__ void finish(const ProbeParams& P, WarpCtx& c) {
 struct SlotRegs {
   uint64_t base2;
   unsigned long long word;
-  const uint64_t* zrow;  // &zT[pos]; residue r's value is zrow[r * ZP]
+  const uint64_t* zrow;  // &zT[pos]; residue r's value is zrow[r * ZP] (survivors only)
+  const uint32_t* erow;  // &zE[pos]; residue r's part of the pattern field is erow[r * ZP]
+  uint32_t fbase;        // the slot's part of the pattern field: pattern_field(base2, class of pos)
   uint32_t allowed;      // bit r: residue r is a candidate here (0: idle lane)
   uint32_t var;          // variant descriptor without the free residue
   uint32_t seed;         // seed number relative to a_first
@@ -126,8 +128,8 @@ __device__ __forceinline__ void residue_loop(const ProbeParams& P, WarpCtx& c, c
   uint32_t hits = 0;
 #pragma unroll
   for (int r = 0; r < SIGMA; r++) {
-    const uint64_t hv = R.base2 ^ R.zrow[r * ZP];
-    if (pattern_hit_halves(wlo, whi, pattern_field(hv))) hits |= 1u << r;
+    // the pattern field is linear in the hash: slot part ^ (position, residue) part (common.cuh)
+    if (pattern_hit_halves(wlo, whi, R.fbase ^ R.erow[r * ZP])) hits |= 1u << r;
   }
   hits &= R.allowed;
   // survivors: a fraction of a percent of the candidates (false positives + true matches)
@@ -147,14 +149,19 @@ __device__ __forceinline__ unsigned long long filter_word(const ProbeParams& P, 
   return P.use_bloom ? __ldg(P.bloom + pfilter_word(h, P.bloom_blocks, cls)) : ~0ull;
 }
 
-// Transposed Zobrist table into shared memory: zT[r * ZP + p] = Z(p, r), rows beyond the table 0.
+// Transposed Zobrist table into shared memory: zT[r * ZP + p] = Z(p, r), rows beyond the table 0,
+// and beside it zE[r * ZP + p] = the pattern-field part of Z(p, r) in the filter of p's class.
 template <int SIGMA, int ZP>
-__device__ __forceinline__ void stage_zt(const ProbeParams& P, uint64_t* zT) {
+__device__ __forceinline__ void stage_zt(const ProbeParams& P, uint64_t* zT, uint32_t* zE) {
   for (uint32_t i = threadIdx.x; i < SIGMA * ZP; i += VK_THREADS) {
     const uint32_t r = i / ZP, p = i - r * ZP;
-    zT[i] = p < P.zrows ? P.ztab[p * SIGMA + r] : 0ull;
+    const uint64_t z = p < P.zrows ? P.ztab[p * SIGMA + r] : 0ull;
+    zT[i] = z;
+    zE[i] = pattern_field(z, pos_class(p));
   }
 }
+template <int SIGMA, int ZP>
+constexpr size_t zt_bytes() { return (size_t)SIGMA * ZP * 12; }
 
 // ---- d = 1 -------------------------------------------------------------------------------------------
 
@@ -179,7 +186,7 @@ struct E1Layout {
   static constexpr size_t off_dcum = off_cum + (WB + 1) * 4;            // [WB + 1] u32, deletion + identical items
   static constexpr size_t off_res = (off_dcum + (WB + 1) * 4 + 15) & ~(size_t)15;  // [WB][ZP] u8
   static constexpr size_t warp_bytes = (off_res + (size_t)WB * ZP + 15) & ~(size_t)15;
-  static constexpr size_t total(int sigma) { return (size_t)sigma * ZP * 8 + VK_WARPS * warp_bytes; }
+  static constexpr size_t total(int sigma) { return (size_t)sigma * ZP * 12 + VK_WARPS * warp_bytes; }
 };
 
 template <int SIGMA, bool INDELS, int ZP>
@@ -189,8 +196,9 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* const zT = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* const zE = reinterpret_cast<uint32_t*>(smem_raw + (size_t)SIGMA * ZP * 8);
   WarpCtx c;
-  c.wb = smem_raw + (size_t)SIGMA * ZP * 8 + warp * Lay::warp_bytes;
+  c.wb = smem_raw + zt_bytes<SIGMA, ZP>() + warp * Lay::warp_bytes;
   c.head = c.count = 0;
   c.lane = lane;
   uint64_t* const scan = reinterpret_cast<uint64_t*>(c.wb + Lay::off_scan);
@@ -204,7 +212,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
   uint32_t* const b_dcum = reinterpret_cast<uint32_t*>(c.wb + Lay::off_dcum);
   uint8_t* const b_res = c.wb + Lay::off_res;
 
-  stage_zt<SIGMA, ZP>(P, zT);
+  stage_zt<SIGMA, ZP>(P, zT, zE);
   __syncthreads();
   const uint64_t n_batches = (P.w_count + WB - 1) / WB;
   constexpr uint32_t ALL = (SIGMA >= 32) ? 0xffffffffu : ((1u << SIGMA) - 1u);
@@ -307,6 +315,8 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
       }
       R.allowed = valid ? (ALL & ~(1u << cmp)) : 0u;
       R.zrow = zT + pos;
+      R.erow = zE + pos;
+      R.fbase = pattern_field(R.base2, pos_class(pos));
       R.seed = (uint32_t)first + k;
       return R;
     };
@@ -336,12 +346,14 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
       uint64_t hv = h;
       bool valid = in;
       unsigned long long w = b_ws[4 * k];  // identical: any filter will do; the seed's word in filter 0 is at hand
+      uint32_t cls = 0;
       if (is_del) {  // no free residue: any filter, spread over the four
         hv = h ^ pre[k * ZP + L] ^ pre[k * ZP + t] ^ sm[k * ZP + t + 1];
         valid = in && L > 1 && (t == 0 || b_res[k * ZP + t] != b_res[k * ZP + t - 1]);
-        w = filter_word(P, hv, pos_class(t));
+        cls = pos_class(t);
+        w = filter_word(P, hv, cls);
       }
-      const bool pass = valid & pattern_hit(w, pattern_field(hv));
+      const bool pass = valid & pattern_hit(w, pattern_field(hv, cls));
       submit(P, c, pass, hv, [is_del, t] {
         return is_del ? pack_var(VK_DELETION, t, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0);
       }, (uint32_t)first + k);
@@ -359,7 +371,7 @@ struct E2Layout {
   static constexpr size_t off_res = VK_Q_BYTES;                  // [ZP] u8 per warp
   static constexpr size_t warp_bytes = (off_res + ZP + 15) & ~(size_t)15;
   static constexpr size_t pair_bytes = ((size_t)NPAIR * 2 + 15) & ~(size_t)15;
-  static constexpr size_t total(int sigma) { return (size_t)sigma * ZP * 8 + pair_bytes + VK_WARPS * warp_bytes; }
+  static constexpr size_t total(int sigma) { return (size_t)sigma * ZP * 12 + pair_bytes + VK_WARPS * warp_bytes; }
 };
 
 template <int SIGMA, int ZP>
@@ -370,15 +382,16 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_const
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   uint64_t* const zT = reinterpret_cast<uint64_t*>(smem_raw);
+  uint32_t* const zE = reinterpret_cast<uint32_t*>(smem_raw + (size_t)SIGMA * ZP * 8);
   // pair e = j (j - 1) / 2 + i  (i < j): independent of the seed's length, a seed of length L owns e < L (L - 1) / 2
-  uint16_t* const pairtab = reinterpret_cast<uint16_t*>(smem_raw + (size_t)SIGMA * ZP * 8);
+  uint16_t* const pairtab = reinterpret_cast<uint16_t*>(smem_raw + zt_bytes<SIGMA, ZP>());
   WarpCtx c;
-  c.wb = smem_raw + (size_t)SIGMA * ZP * 8 + Lay::pair_bytes + warp * Lay::warp_bytes;
+  c.wb = smem_raw + zt_bytes<SIGMA, ZP>() + Lay::pair_bytes + warp * Lay::warp_bytes;
   c.head = c.count = 0;
   c.lane = lane;
   uint8_t* const sres = c.wb + Lay::off_res;
 
-  stage_zt<SIGMA, ZP>(P, zT);
+  stage_zt<SIGMA, ZP>(P, zT, zE);
   for (uint32_t j = 1 + threadIdx.x; j < Lay::LMAX; j += VK_THREADS)
     for (uint32_t i = 0; i < j; i++) pairtab[j * (j - 1) / 2 + i] = (uint16_t)(i | (j << 8));
   __syncthreads();
@@ -414,11 +427,13 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_const
         R.word = ws;
         R.allowed = valid ? (ALL & ~(1u << cmp)) : 0u;
         R.zrow = zT + pc;
+        R.erow = zE + pc;
+        R.fbase = pattern_field(R.base2, lane & 3);
         R.var = pack_var(VK_SUBSTITUTION, pc, 0, 0, 0);
         R.seed = slocal;
         residue_loop<SIGMA, ZP, 3>(P, c, R);
       }
-      submit(P, c, lane == 0 && pattern_hit(ws, pattern_field(h)), h, [] { return pack_var(VK_IDENTICAL, 0, 0, 0, 0); }, slocal);
+      submit(P, c, lane == 0 && pattern_hit(ws, pattern_field(h, 0)), h, [] { return pack_var(VK_IDENTICAL, 0, 0, 0, 0); }, slocal);
     }
 
     // double substitutions i < j (variants.cc:357-400): slots x = (pair e, first residue v), lanes
@@ -439,6 +454,8 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_const
       R.word = filter_word(P, b2v, pos_class(j));
       R.allowed = valid ? (ALL & ~(1u << sj)) : 0u;
       R.zrow = zT + j;
+      R.erow = zE + j;
+      R.fbase = pattern_field(R.base2, pos_class(j));
       R.var = pack_var(VK_SUB_SUB, i, v, j, 0);
       R.seed = slocal;
       return R;
@@ -472,7 +489,7 @@ __device__ __forceinline__ void filter_step(const ProbeParams& P, const uint64_t
   for (int u = 0; u < VK_U; u++)  // unconditional: an inactive candidate's hash is a valid address too
     w[u] = __ldg(P.bloom + pfilter_word(hv[u], P.bloom_blocks, cls[u]));
 #pragma unroll
-  for (int u = 0; u < VK_U; u++) pass[u] = pass[u] & pattern_hit(w[u], pattern_field(hv[u]));
+  for (int u = 0; u < VK_U; u++) pass[u] = pass[u] & pattern_hit(w[u], pattern_field(hv[u], cls[u]));
 }
 
 // Per-warp scratch of the generic kernel for one seed.
@@ -621,7 +638,7 @@ __device__ __forceinline__ void phase_b(const ProbeParams& P, WarpCtx& c, const 
       const uint64_t hv = b2 ^ s.zo[j] ^ zval<ZG>(z, j * SIGMA + r);
       const uint32_t jc = pos_class(j);
       const unsigned long long w = jc == 0 ? wc[0] : jc == 1 ? wc[1] : jc == 2 ? wc[2] : wc[3];
-      const bool pass = in & (r != cmp) & pattern_hit(w, pattern_field(hv));
+      const bool pass = in & (r != cmp) & pattern_hit(w, pattern_field(hv, jc));
       submit(P, c, pass, hv, [i, v, j, r] { return pack_var(VK_SUB_SUB, i, v, j, r); }, slocal);
     }
   }
@@ -695,6 +712,7 @@ __global__ void __launch_bounds__(VK_THREADS, 2) generic_kernel(const __grid_con
 // of the occurrence list, score + matrix atomics + pair append per occurrence.  A queue that
 // overflowed is not touched at all: the chunk is recorded and redone by the host.
 __global__ void __launch_bounds__(256) table_kernel(const __grid_constant__ ProbeParams P, uint32_t chunk_id) {
+  extern __shared__ __align__(16) unsigned char tile_raw[];
   const unsigned long long filled = P.counters[CTR_GQ];
   if (filled > P.gq_cap) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -706,6 +724,7 @@ __global__ void __launch_bounds__(256) table_kernel(const __grid_constant__ Prob
   // candidates that passed the filter stage = entries of a queue that is consumed (a chunk that
   // overflowed is redone and counted then)
   if (P.count_bloom && blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(P.counters + CTR_BLOOM_PASS, filled);
+  double* const tile = matrix_tile_begin(P, tile_raw);
   uint32_t nmatch = 0;
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   for (uint64_t i0 = blockIdx.x * (uint64_t)blockDim.x + (threadIdx.x & ~31u); i0 < filled; i0 += stride) {
@@ -717,13 +736,18 @@ __global__ void __launch_bounds__(256) table_kernel(const __grid_constant__ Prob
       hv = P.gq_hv[i];
       vs = P.gq_vs[i];
     }
-    nmatch += probe_chains(&P, act, hv, vs.x, P.a_first + vs.y, vs.y, nullptr, 0);
+    nmatch += probe_chains(&P, act, hv, vs.x, P.a_first + vs.y, vs.y, tile);
   }
+  matrix_tile_flush(P, tile);
   flush_counters(P, nmatch, 0);
 }
 
 void launch_table_stage(const ProbeParams& p, int sm_count, uint32_t chunk_id, cudaStream_t st) {
-  table_kernel<<<sm_count * 8, 256, 0, st>>>(p, chunk_id);
+  const size_t smem = (size_t)p.tile_cells * sizeof(double);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  // with a tile fewer, longer-lived CTAs: every CTA flushes its whole tile once
+  const int per_sm = smem ? (smem > 48 * 1024 ? 2 : 4) : 8;
+  table_kernel<<<sm_count * per_sm, 256, smem, st>>>(p, chunk_id);
 }
 
 // ---- launch ------------------------------------------------------------------------------------------

@@ -76,8 +76,8 @@ typedef struct cb_config {
   uint32_t n_reps_a;       /* repertoires in set A (rows in matrix mode); 1 in existence mode     */
   uint64_t seed;           /* PRNG seed for the Zobrist table; results do not depend on it        */
   /* tuning; 0 selects the default.  Results do not depend on these either. */
-  uint32_t bloom_bits_per_key_x16;  /* bits per set-B sequence in EACH of the two parity filters, */
-                                    /* fixed point 1/16 bit (default 24 bits)                     */
+  uint32_t bloom_bits_per_key_x16;  /* bits per set-B sequence in EACH of the four class filters, */
+                                    /* fixed point 1/16 bit (default 16 bits)                     */
   uint32_t table_load_pct;          /* max hash-table load in percent (default 50)               */
   uint64_t pairs_capacity;          /* device pair-buffer capacity per launch, in pairs          */
   uint32_t flags;                   /* CB_FLAG_*                                                  */
@@ -87,10 +87,13 @@ typedef struct cb_config {
                                     /* costs time: the chunk of seeds is redone in smaller pieces */
 } cb_config;
 
-#define CB_FLAG_NO_SMEM_TILE 1u   /* accumulate straight into the global matrix (A/B testing)    */
+#define CB_FLAG_NO_SMEM_TILE 1u   /* small matrices too: accumulate straight into the global     */
+                                  /* matrix, no shared-memory tile (A/B testing)                 */
 #define CB_FLAG_NO_BLOOM 2u       /* probe the hash table for every variant (A/B testing)        */
 #define CB_FLAG_NO_TENSOR 4u      /* d >= 3: CUDA-core kernel only, no tcgen05 GEMM (A/B testing) */
 #define CB_FLAG_NO_PARTITION 8u   /* table build in input order, no radix sort by home slot (A/B testing) */
+#define CB_FLAG_FILTERS_IN_BUILD 32u /* large builds: filter bits set by the table-build kernel instead of */
+                                    /* the L2-blocked filter passes (A/B testing)                          */
 #define CB_FLAG_GENERIC_KERNEL 16u /* d = 1, 2: every seed through the any-length enumeration kernel  */
                                    /* (otherwise only seeds longer than 94 residues; A/B testing)     */
 
@@ -163,8 +166,8 @@ typedef struct cb_stats {
   uint64_t matches;         /* verified (seed, hit) matches (reference all_matches, overlap.cc:230) */
   uint64_t pairs;           /* pairs stored for cb_drain_pairs                                    */
   uint64_t table_slots;     /* hash-table slots                                                   */
-  uint64_t bloom_bytes;     /* bytes of parity filter E (word picked by the even-position field) */
-  uint64_t bloom2_bytes;    /* bytes of parity filter O (word picked by the odd-position field)  */
+  uint64_t bloom_bytes;     /* bytes of ONE of the four class filters                             */
+  uint64_t bloom2_bytes;    /* bytes of the other three together                                  */
   float ms_hash_b;          /* device time, CUDA events on the engine's stream                    */
   float ms_build_b;
   float ms_dups_b;

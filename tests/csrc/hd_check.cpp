@@ -60,11 +60,11 @@ int main() {
       const uint64_t h = hash_of(s, seed, vj);
       std::vector<unsigned long long> filt(CB_CLASSES * (size_t)nblocks, 0);
       // 4: insert h into all four filters, look it up in each
-      for (uint32_t c = 0; c < CB_CLASSES; c++) filt[pfilter_word(h, nblocks, c)] |= pfilter_pattern(h);
+      for (uint32_t c = 0; c < CB_CLASSES; c++) filt[pfilter_word(h, nblocks, c)] |= pfilter_pattern(h, c);
       for (uint32_t c = 0; c < CB_CLASSES; c++) {
         const uint64_t w = pfilter_word(h, nblocks, c);
         CHECK(w >= (uint64_t)c * nblocks && w < (uint64_t)(c + 1) * nblocks);  // 3
-        CHECK(pattern_hit(filt[w], pattern_field(h)));
+        CHECK(pattern_hit(filt[w], pattern_field(h, c)));
       }
       // 6
       CHECK(h * CB_HOME_MUL * CB_HOME_INV == h);
@@ -81,7 +81,11 @@ int main() {
           CHECK(pfilter_word(hv, nblocks, c) == pfilter_word(h, nblocks, c));
           if (r != s[p]) {  // ... while the hash itself, its pattern field and (almost always) the home slot move
             CHECK(hv != h);
-            CHECK(pattern_field(hv) != pattern_field(h));
+            CHECK(pattern_field(hv, c) != pattern_field(h, c));
+            // the pattern field is linear: per-slot part ^ per-(position, residue) part
+            CHECK(pattern_field(hv, c) == (pattern_field(h ^ zobrist_gen(seed, p, s[p]), c) ^ pattern_field(zobrist_gen(seed, p, (uint32_t)r), c)));
+            for (uint32_t o = 0; o < CB_CLASSES; o++)
+              if (o != c) CHECK(pattern_field(hv, o) == pattern_field(h, o));
           }
           // 1 for double substitutions: a second one at j > p of any class
           for (uint32_t j = p + 1; j < L && j < p + 6; j++) {

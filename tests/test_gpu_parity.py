@@ -89,7 +89,7 @@ def test_dups():
 @pytest.mark.parametrize("bpk", [24.0, 16.0, 4.0, 1.0])
 @pytest.mark.parametrize("d,indels", [(0, False), (1, True), (2, False)])
 def test_filter_geometries(bpk, d, indels):
-    """Results must not depend on the filter geometry: from generous (16 bits per key in each parity
+    """Results must not depend on the filter geometry: from generous (24 bits per key in each class
     filter) down to saturated filters (1 bit per key: nearly every candidate reaches the table)."""
     pool = synth.make_pool(31, 2000)
     a = synth.make_set(32, 4, 1200, pool=pool, indel_mutants=True)
@@ -98,7 +98,7 @@ def test_filter_geometries(bpk, d, indels):
                                               bloom_bits_per_key=bpk))
     mo, po, io = orc.overlap(a, b, differences=d, indels=indels, want_pairs=True)
     assert np.array_equal(m, mo) and _pairs(p) == _pairs(po)
-    assert info["build"]["bloom_bytes"] == info["build"]["bloom2_bytes"] > 0   # filter E, filter O
+    assert 3 * info["build"]["bloom_bytes"] == info["build"]["bloom2_bytes"] > 0   # one class filter, the other three
     if d > 0 and bpk >= 16:
         assert info["run"]["bloom_pass"] < 0.05 * info["run"]["probes"]
 

@@ -14,7 +14,7 @@ the CPU oracle finishes in seconds (reference semantics: src/overlap.cc:168-251 
 import numpy as np
 import pytest
 
-from compairr_b200 import Engine, OverlapOptions, cluster, overlap, synth
+from compairr_b200 import Engine, OverlapOptions, SeqSet, cluster, overlap, synth
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -196,3 +196,67 @@ def test_d3_tensor_core_with_vj_buckets(nucleotides):
     assert np.array_equal(m2, mo) and _pairs(p2) == _pairs(po)
     # the two runs really took different kernels
     assert info["run"]["kernel_launches"] != info2["run"]["kernel_launches"]
+
+
+@pytest.mark.parametrize("score", ["product", "ratio", "min"])
+@pytest.mark.parametrize("d,indels", [(0, False), (1, True), (2, False)])
+def test_matrix_tile_equals_global_atomics(d, indels, score):
+    """Small matrices are accumulated in CTA-private shared-memory tiles with warp-aggregated
+    atomics (device_utils.cuh accumulate_warp); CB_FLAG_NO_SMEM_TILE sends every match straight to
+    the global matrix.  Low-complexity sets: many matches per cell, many lanes on the same cell."""
+    a = synth.small_dense_set(301, 3, 4000, max_len=6)
+    b = synth.small_dense_set(302, 2, 5000, max_len=6)
+    kw = dict(differences=d, indels=indels, score=score)
+    mo, _, io = orc.overlap(a, b, threads=8, **kw)
+    assert io["matches"] > 20 * a.n                      # dense: tens to hundreds of matches per seed
+    for flags in (0, 1):
+        m, _, info = overlap(a, b, OverlapOptions(flags=flags, **kw))
+        if score == "ratio":
+            np.testing.assert_allclose(m, mo, rtol=1e-12, atol=0)
+        else:
+            assert np.array_equal(m, mo)
+        assert info["run"]["matches"] == io["matches"]
+
+
+def test_matrix_too_large_for_a_tile():
+    """More cells than the tile holds (> 10240): the global-atomics path, same answer."""
+    a = synth.small_dense_set(311, 120, 40, max_len=5)
+    b = synth.small_dense_set(312, 110, 40, max_len=5)
+    m, _, info = overlap(a, b, OverlapOptions(differences=1, indels=True))
+    mo, _, io = orc.overlap(a, b, differences=1, indels=True, threads=4)
+    assert m.shape == (120, 110) and np.array_equal(m, mo) and info["run"]["matches"] == io["matches"]
+
+
+def test_degenerate_family_saturates_one_filter_word_only():
+    """20 000 keys that differ ONLY at positions of one class (p = 0 mod 4) share their word in
+    class filter 0 (its index is blind to exactly those positions): that word saturates and every
+    candidate looked up there reaches the table stage.  Results must stay exact, and the damage
+    bounded: the other three filters are unaffected, so at most the slots of one class in four
+    lose their filter."""
+    rng = np.random.default_rng(77)
+    L, n = 16, 20_000
+    base = rng.integers(0, 20, L).astype(np.uint8)
+    fam = np.tile(base, (n, 1))
+    fam[:, [0, 4, 8, 12]] = rng.integers(0, 20, (n, 4))
+    fam = np.unique(fam, axis=0)
+    n = fam.shape[0]
+
+    def mk(rows, reps, seed):
+        r = np.random.default_rng(seed)
+        m = rows.shape[0]
+        off = np.arange(m + 1, dtype=np.uint64) * np.uint64(L)
+        return SeqSet(rows.reshape(-1), off, np.zeros(m, np.uint32), np.zeros(m, np.uint32),
+                      r.integers(0, reps, m).astype(np.uint32), r.integers(1, 4, m).astype(np.uint64), reps)
+    b = mk(fam, 3, 1)
+    a = mk(fam[rng.permutation(n)[:4000]], 2, 2)
+    healthy = rng.integers(0, 20, (n, L)).astype(np.uint8)
+    b_h, a_h = mk(healthy, 3, 1), mk(healthy[:4000], 2, 2)
+    for kw in (dict(differences=1, indels=True), dict(differences=2)):
+        mo, _, io = orc.overlap(a, b, threads=8, **kw)
+        m, _, info = overlap(a, b, OverlapOptions(**kw))
+        assert np.array_equal(m, mo) and info["run"]["matches"] == io["matches"]
+        _, _, info_h = overlap(a_h, b_h, OverlapOptions(**kw))
+        frac = info["run"]["bloom_pass"] / info["run"]["probes"]
+        # only slots of class 0 can be hit by the saturated word; the family's true neighbours pass anyway
+        assert frac < 0.30, frac
+        assert info_h["run"]["bloom_pass"] / info_h["run"]["probes"] < 0.02
