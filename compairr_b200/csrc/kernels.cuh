@@ -34,7 +34,12 @@ struct DeviceSetView {
   uint64_t index_base;
 };
 
-constexpr uint32_t MATRIX_TILE_MAX_CELLS = 10240;  // shared-memory matrix tile: 80 KB, 100 x 100 repertoires (C2) fit
+// Shared-memory matrix tile: up to 4096 cells (32 KB, 64 x 64 repertoires) — the table kernel keeps
+// its 4 CTAs per SM.  Measured on 2 * 10^6 low-complexity sequences, self-comparison, d = 1 -i
+// (5.4e10 matches): 2 repertoires 2.9 s with the tile vs 52 s without (18 x; every match lands on
+// one of 4 cells), 8 repertoires 1.5 vs 8.2 s; at 100 x 100 repertoires an 80 KB tile (2 CTAs per
+// SM) LOST 2.6 x against plain global REDs, which by then spread over 10^4 cells.
+constexpr uint32_t MATRIX_TILE_MAX_CELLS = 4096;
 
 struct ProbeParams {
   DeviceSetView a;

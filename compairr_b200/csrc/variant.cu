@@ -182,8 +182,9 @@ struct E1Layout {
   static constexpr size_t off_hash = off_scan + scan_u64 * 8;           // [WB] u64
   static constexpr size_t off_ws = off_hash + WB * 8;                   // [WB][4] u64: the seed's word in each class filter
   static constexpr size_t off_len = off_ws + WB * 32;                   // [WB] u32
-  static constexpr size_t off_cum = off_len + WB * 4;                   // [WB + 1] u32, residue slots
-  static constexpr size_t off_dcum = off_cum + (WB + 1) * 4;            // [WB + 1] u32, deletion + identical items
+  static constexpr size_t off_cum = off_len + WB * 4;                   // [WB + 1] u32, substitution slots
+  static constexpr size_t off_icum = off_cum + (WB + 1) * 4;            // [WB + 1] u32, insertion slots
+  static constexpr size_t off_dcum = off_icum + (WB + 1) * 4;           // [WB + 1] u32, deletion + identical items
   static constexpr size_t off_res = (off_dcum + (WB + 1) * 4 + 15) & ~(size_t)15;  // [WB][ZP] u8
   static constexpr size_t warp_bytes = (off_res + (size_t)WB * ZP + 15) & ~(size_t)15;
   static constexpr size_t total(int sigma) { return (size_t)sigma * ZP * 12 + VK_WARPS * warp_bytes; }
@@ -209,6 +210,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
   unsigned long long* const b_ws = reinterpret_cast<unsigned long long*>(c.wb + Lay::off_ws);
   uint32_t* const b_len = reinterpret_cast<uint32_t*>(c.wb + Lay::off_len);
   uint32_t* const b_cum = reinterpret_cast<uint32_t*>(c.wb + Lay::off_cum);
+  uint32_t* const b_icum = reinterpret_cast<uint32_t*>(c.wb + Lay::off_icum);
   uint32_t* const b_dcum = reinterpret_cast<uint32_t*>(c.wb + Lay::off_dcum);
   uint8_t* const b_res = c.wb + Lay::off_res;
 
@@ -242,22 +244,24 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
     }
     {  // slot and item counts -> inclusive prefix sums over the WB seeds
       const bool live = my_len != LEN_SKIP;
-      uint32_t ns = live ? (INDELS ? 2 * my_len + 1 : my_len) : 0;
-      uint32_t nd = live ? (INDELS ? my_len + 1 : 1) : 0;
+      // L substitution slots, L + 1 insertion slots, L deletion candidates + the identical one: the
+      // three lists differ by the number of live seeds before this one only
+      uint32_t ns = live ? my_len : 0, nl = live ? 1 : 0;
 #pragma unroll
       for (int o = 1; o < WB; o <<= 1) {
-        const uint32_t xs = __shfl_up_sync(FULL, ns, o), xd = __shfl_up_sync(FULL, nd, o);
+        const uint32_t xs = __shfl_up_sync(FULL, ns, o), xl = __shfl_up_sync(FULL, nl, o);
         if ((int)lane >= o) {
           ns += xs;
-          nd += xd;
+          nl += xl;
         }
       }
       if (lane < WB) {
         b_len[lane] = my_len;
         b_cum[lane + 1] = ns;
-        b_dcum[lane + 1] = nd;
+        b_icum[lane + 1] = INDELS ? ns + nl : 0;
+        b_dcum[lane + 1] = INDELS ? ns + nl : nl;
       }
-      if (lane == 0) b_cum[0] = b_dcum[0] = 0;
+      if (lane == 0) b_cum[0] = b_icum[0] = b_dcum[0] = 0;
     }
 #pragma unroll
     for (int k = 0; k < WB; k++) {  // residues: one row of ZP bytes per seed
@@ -287,32 +291,23 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
       __syncwarp();
     }
 
-    // ---- residue slots of the batch, 32 at a time ---------------------------------------------------------
-    const uint32_t n_slots = b_cum[WB];
-    auto load_slot = [&](uint32_t g) {
-      SlotRegs R;
-      const bool valid = g < n_slots;
-      if (!valid) g = 0;
+    // ---- residue slots of the batch, 32 at a time: first all substitution slots, then all insertion
+    // slots (two flat lists, so that a pass loads its slots through one code path) ----------------------------
+    auto seed_of = [&](const uint32_t* cum, uint32_t g) {
       uint32_t k = 0;
 #pragma unroll
-      for (int j = 1; j < WB; j++) k += g >= b_cum[j];
-      const uint32_t L = b_len[k], pp = g - b_cum[k];
-      const bool sub = !INDELS || pp < L;
-      const uint32_t pos = sub ? pp : pp - L;
-      const uint64_t h = b_hash[k];
-      uint32_t cmp;
-      if (sub) {
-        cmp = b_res[k * ZP + pos];
-        R.base2 = h ^ zT[cmp * ZP + pos];
-        R.word = b_ws[4 * k + pos_class(pos)];
-        R.var = pack_var(VK_SUBSTITUTION, pos, 0, 0, 0);
-      } else {  // insertion before position pos: the new residue sits at position pos of the variant;
-                // not the residue before it, which would repeat a variant (variants.cc:341-353)
-        cmp = pos ? b_res[k * ZP + pos - 1] : 31u;
-        R.base2 = h ^ pre[k * ZP + L] ^ pre[k * ZP + pos] ^ sp[k * ZP + pos];
-        R.word = filter_word(P, R.base2, pos_class(pos));
-        R.var = pack_var(VK_INSERTION, pos, 0, 0, 0);
-      }
+      for (int j = 1; j < WB; j++) k += g >= cum[j];
+      return k;
+    };
+    auto load_sub = [&](uint32_t g, uint32_t n) {
+      SlotRegs R;
+      const bool valid = g < n;
+      if (!valid) g = 0;
+      const uint32_t k = seed_of(b_cum, g), pos = g - b_cum[k];
+      const uint32_t cmp = b_res[k * ZP + pos];
+      R.base2 = b_hash[k] ^ zT[cmp * ZP + pos];
+      R.word = b_ws[4 * k + pos_class(pos)];
+      R.var = pack_var(VK_SUBSTITUTION, pos, 0, 0, 0);
       R.allowed = valid ? (ALL & ~(1u << cmp)) : 0u;
       R.zrow = zT + pos;
       R.erow = zE + pos;
@@ -320,43 +315,74 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
       R.seed = (uint32_t)first + k;
       return R;
     };
-    if (n_slots) {
-      SlotRegs cur = load_slot(lane);
-      for (uint32_t g0 = 0; g0 < n_slots; g0 += 32) {
+    auto load_ins = [&](uint32_t g, uint32_t n) {  // insertion before position pos: the new residue sits at position
+      SlotRegs R;                                  // pos of the variant; not the residue before it, which would
+      const bool valid = g < n;                    // repeat a variant (variants.cc:341-353)
+      if (!valid) g = 0;
+      const uint32_t k = seed_of(b_icum, g), pos = g - b_icum[k], L = b_len[k];
+      const uint32_t cmp = pos ? b_res[k * ZP + pos - 1] : 31u;
+      R.base2 = b_hash[k] ^ pre[k * ZP + L] ^ pre[k * ZP + pos] ^ sp[k * ZP + pos];
+      R.word = filter_word(P, R.base2, pos_class(pos));
+      R.var = pack_var(VK_INSERTION, pos, 0, 0, 0);
+      R.allowed = valid ? (ALL & ~(1u << cmp)) : 0u;
+      R.zrow = zT + pos;
+      R.erow = zE + pos;
+      R.fbase = pattern_field(R.base2, pos_class(pos));
+      R.seed = (uint32_t)first + k;
+      return R;
+    };
+    auto passes = [&](uint32_t n, auto load) {
+      if (n == 0) return;
+      SlotRegs cur = load(lane, n);
+      for (uint32_t g0 = 0; g0 < n; g0 += 32) {
         SlotRegs nxt = cur;
-        if (g0 + 32 < n_slots) nxt = load_slot(g0 + 32 + lane);  // the next pass's words are in flight during this one
+        if (g0 + 32 < n) nxt = load(g0 + 32 + lane, n);  // the next pass's words are in flight during this one
         residue_loop<SIGMA, ZP, 3>(P, c, cur);
         cur = nxt;
       }
-    }
+    };
+    passes(b_cum[WB], load_sub);
+    if (INDELS) passes(b_icum[WB], load_ins);
 
     // ---- deletions (one per run of equal residues, only if L > 1, variants.cc:301-325) and the
     // identical candidate of every seed: one candidate per item ---------------------------------------------
     const uint32_t n_items = b_dcum[WB];
-    for (uint32_t g0 = 0; g0 < n_items; g0 += 32) {
-      uint32_t g = g0 + lane;
-      const bool in = g < n_items;
-      if (!in) g = 0;
-      uint32_t k = 0;
+    constexpr int DU = 4;  // item passes in flight: their filter-word loads are issued together
+    for (uint32_t g0 = 0; g0 < n_items; g0 += 32 * DU) {
+      uint64_t hv[DU];
+      unsigned long long w[DU];
+      uint32_t desc[DU], ks[DU];  // descriptor | filter class << 29 | valid << 31
 #pragma unroll
-      for (int j = 1; j < WB; j++) k += g >= b_dcum[j];
-      const uint32_t L = b_len[k], t = g - b_dcum[k];
-      const bool is_del = INDELS && t < L;
-      const uint64_t h = b_hash[k];
-      uint64_t hv = h;
-      bool valid = in;
-      unsigned long long w = b_ws[4 * k];  // identical: any filter will do; the seed's word in filter 0 is at hand
-      uint32_t cls = 0;
-      if (is_del) {  // no free residue: any filter, spread over the four
-        hv = h ^ pre[k * ZP + L] ^ pre[k * ZP + t] ^ sm[k * ZP + t + 1];
-        valid = in && L > 1 && (t == 0 || b_res[k * ZP + t] != b_res[k * ZP + t - 1]);
-        cls = pos_class(t);
-        w = filter_word(P, hv, cls);
+      for (int u = 0; u < DU; u++) {
+        uint32_t g = g0 + u * 32 + lane;
+        const bool in = g < n_items;
+        if (!in) g = 0;
+        uint32_t k = 0;
+#pragma unroll
+        for (int j = 1; j < WB; j++) k += g >= b_dcum[j];
+        const uint32_t L = b_len[k], t = g - b_dcum[k];
+        const bool is_del = INDELS && t < L;
+        const uint64_t h = b_hash[k];
+        hv[u] = h;
+        bool valid = in;
+        uint32_t cls = 0;
+        w[u] = b_ws[4 * k];  // identical: any filter will do; the seed's word in filter 0 is at hand
+        if (is_del) {        // no free residue: any filter, spread over the four
+          hv[u] = h ^ pre[k * ZP + L] ^ pre[k * ZP + t] ^ sm[k * ZP + t + 1];
+          valid = in && L > 1 && (t == 0 || b_res[k * ZP + t] != b_res[k * ZP + t - 1]);
+          cls = pos_class(t);
+          w[u] = filter_word(P, hv[u], cls);
+        }
+        desc[u] = (is_del ? pack_var(VK_DELETION, t, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0)) | (cls << 29) | ((uint32_t)valid << 31);
+        ks[u] = (uint32_t)first + k;
       }
-      const bool pass = valid & pattern_hit(w, pattern_field(hv, cls));
-      submit(P, c, pass, hv, [is_del, t] {
-        return is_del ? pack_var(VK_DELETION, t, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0);
-      }, (uint32_t)first + k);
+#pragma unroll
+      for (int u = 0; u < DU; u++) {
+        if (g0 + u * 32 >= n_items) break;  // warp-uniform
+        const bool pass = (desc[u] >> 31) & pattern_hit(w[u], pattern_field(hv[u], (desc[u] >> 29) & 3u));
+        const uint32_t var = desc[u] & 0x1fffffffu;  // deletion / identical descriptors use bits 0..21 only
+        submit(P, c, pass, hv[u], [var] { return var; }, ks[u]);
+      }
     }
   }
   finish(P, c);

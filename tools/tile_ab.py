@@ -3,8 +3,8 @@ workload: self-comparison of a low-complexity set in few repertoires.  usage: ti
 import sys, json
 sys.path.insert(0, ".")
 from compairr_b200 import Engine, OverlapOptions, synth
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 1_000_000
-for reps, d, indels in ((2, 1, True), (2, 0, False), (8, 1, False), (100, 1, True)):
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 500_000
+for reps, d, indels in ((2, 1, True), (8, 1, False), (32, 1, True), (64, 1, True), (100, 1, True)):
     s = synth.small_dense_set(7, reps, n * 2 // reps, max_len=7)
     for flags in (0, 1):
         with Engine(OverlapOptions(differences=d, indels=indels, flags=flags), n_reps_a=s.n_reps) as eng:
