@@ -21,6 +21,9 @@ verify + accumulate, and (N > 1) the all-reduce of the matrix (NCCL inside the l
             CUDA-event duration, against the measured HBM peak (MEASURED_PEAKS.json)
   d2        C4 geometry: `-m -d 2 -g`, same set B, 2*10^5 seeds per GPU, kernel + whole-step rates
   strong    the FIXED C3 problem (set A = 1000 x 100 000 in total) split over the N GPUs
+  c5        C5 geometry at a bounded size: nucleotide queries (one repertoire) against a nucleotide
+            set, `-x -n -d 2 -p --no-matrix` (hash path, pairs drained to the host) and `-x -n -g -d 3`
+            (length-bucketed one-hot int8 GEMM on tcgen05), probes/s and pair tests/s
   parity_checked  the engine at this N (sharded B, sharded A, all-reduce) against the UNMODIFIED
             reference binary on a sample of the same generator: matrices byte-identical
   cpu_baseline / cli_wall (N=1, rank 0)  oracle/_ref/compairr -t <all cores> on A = 10 repertoires
@@ -67,6 +70,9 @@ def parse():
     ap.add_argument("--skip-d2", action="store_true")
     ap.add_argument("--skip-strong", action="store_true")
     ap.add_argument("--skip-parity", action="store_true")
+    ap.add_argument("--skip-c5", action="store_true")
+    ap.add_argument("--c5-reps-b", type=int, default=100, help="C5 section: nucleotide set-B repertoires (x per-rep sequences)")
+    ap.add_argument("--c5-queries", type=int, default=1_000_000, help="C5 section: nucleotide query sequences per GPU")
     ap.add_argument("--d2-seeds", type=int, default=200_000, help="d=2 section: seeds per GPU")
     ap.add_argument("--strong-reps-a", type=int, default=0, help="strong-scaling section: set-A repertoires in total (0 = reps-b)")
     ap.add_argument("--sample-reps-a", type=int, default=10, help="reference run: set-A repertoires (set B is complete)")
@@ -508,6 +514,11 @@ def run_ours(a):
         db2.free()
         e2.close()
 
+    # ---- C5 geometry, bounded: nucleotide queries in one repertoire vs a nucleotide set ----------------------
+    c5 = None
+    if not a.skip_c5:
+        c5 = c5_section(a, rank, world, local, pool, stream, reduce_over_ranks, sync_all)
+
     # ---- reduce timings over ranks ------------------------------------------------------------------------
     (ms_dev, ms_e2e, kern), (probes_total, h2d_total) = reduce_over_ranks(
         [main["ms_dev"], ms_e2e, main["kernel_ms"]], [float(probes_rank), float(h2d_rank)])
@@ -558,7 +569,7 @@ def run_ours(a):
         "clocks": main["clocks"],
         "wall_ms_per_step": main["wall_ms"] / a.steps,
         "matches_per_step_rank0": run_stats["matches"], "bloom_pass_frac": run_stats["bloom_pass"] / max(run_stats["probes"], 1),
-        "d2": d2, "strong": strong, "parity_checked": parity,
+        "d2": d2, "strong": strong, "c5": c5, "parity_checked": parity,
     }
     if world == 1 and not a.skip_cpu_baseline:
         tmp = shm_tmp()
@@ -580,6 +591,59 @@ def run_ours(a):
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def c5_section(a, rank, world, local, pool, stream, reduce_over_ranks, sync_all):
+    """BASELINE config 5 at a size that fits the time box: Q nucleotide queries per GPU (one
+    repertoire, rank r takes its own block of the generator) against c5_reps_b x per_rep nucleotide
+    sequences.  (1) -x -n -d 2 -p --no-matrix: the hash path on ~43-nt sequences (ZP = 96 kernels),
+    pairs drained to the host every run; (2) -x -n -g -d 3 -p --no-matrix: the brute-force path, dense
+    length buckets on the tcgen05 one-hot int8 GEMM."""
+    import torch
+    from compairr_b200 import Engine, OverlapOptions, synth
+    t0 = time.perf_counter()
+    reps_q = (-(-a.c5_queries // a.per_rep) + 7) // 8 * 8      # whole generator blocks of 8 repertoires
+    b = synth.make_set(SEED_B, a.c5_reps_b, a.per_rep, pool=pool, nucleotides=True, workers=n_workers(a))
+    q = synth.make_set(SEED_A, reps_q, a.per_rep, pool=pool, nucleotides=True, single_repertoire=True,
+                       workers=max(1, n_workers(a) // world), first_rep=rank * reps_q)
+    q = q.slice(0, min(a.c5_queries, q.n))
+    t_gen = time.perf_counter() - t0
+    out = {"workload": f"C5 geometry, bounded: {q.n} nucleotide queries per GPU (one repertoire) vs B={a.c5_reps_b}x{a.per_rep} "
+                       f"nucleotide sequences (mean length {b.residues.size / max(b.n, 1):.0f}); pairs collected and drained to the host",
+           "generate_s": round(t_gen, 1)}
+    Lq, Lb = np.diff(q.offsets).astype(np.int64), np.diff(b.offsets).astype(np.int64)
+    pair_tests = float((np.bincount(Lq, minlength=512).astype(np.float64) * np.bincount(Lb, minlength=512)).sum())
+    for name, kw, steps in (("d2_hash", dict(differences=2), max(1, min(a.steps, 3))),
+                            ("d3_gemm", dict(differences=3, ignore_genes=True), max(1, min(a.steps, 3)))):
+        eng = Engine(OverlapOptions(existence=True, nucleotides=True, no_matrix=True, want_pairs=True, device=local, **kw), n_reps_a=1)
+        eng.set_stream(stream.cuda_stream)
+        db, dq = eng.upload(b), eng.upload(q)
+        eng.build_b(db)
+        ms, kern, pairs = [], [], 0
+        for it in range(1 + steps):                       # one warm-up run (sizes the pair buffer and the queue)
+            sync_all()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record(stream)
+            eng.run(dq)
+            st = eng.stats()
+            p = eng.drain_pairs()
+            ev1.record(stream)
+            sync_all()
+            if it:
+                ms.append(ev0.elapsed_time(ev1))
+                kern.append(st["ms_probe"])
+                pairs = len(p)
+        work = float(sum_probes(q, 2, False)) if name == "d2_hash" else pair_tests
+        (ms_max, kern_max), (work_all,) = reduce_over_ranks([statistics.mean(ms), statistics.mean(kern)], [work])
+        out[name] = {"value": work_all / (ms_max * 1e-3), "unit": "probes/s" if name == "d2_hash" else "pair tests/s",
+                     "kernel_value_rank0": work / (statistics.mean(kern) * 1e-3), "ms_per_step": ms_max, "kernel_ms": kern_max,
+                     "steps": steps, "warmup": 1, "pairs_rank0": pairs, "matches_rank0": st["matches"],
+                     "args": "-x -n -d 2 -p --no-matrix" if name == "d2_hash" else "-x -n -g -d 3 -p --no-matrix",
+                     "note": "value = run + drain of the pairs to host memory (device span); kernel_value = the kernels alone"}
+        dq.free()
+        db.free()
+        eng.close()
+    return out
 
 
 def peak_hbm():

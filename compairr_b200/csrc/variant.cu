@@ -122,24 +122,31 @@ struct SlotRegs {
 
 // The inner loop: all SIGMA residues of every lane's slot.  RSHIFT: where the free residue goes in
 // the descriptor (3 = res1: substitution / insertion, 8 = res2: second substitution).
+//
+// Two stages.  The loop tests only the three bits of the LOW half of the word (3 variable shifts
+// and a 3-input AND per candidate: the ALU pipe, which issues every other cycle, is what bounds
+// this kernel); ~3 % of the candidates pass it (0.3^3 at 16 bits per key).  Those are looked at
+// again — high half, exact survivors into the ring — in a short loop over the set bits, a couple of
+// iterations per pass.  Residues are walked downwards so that `ha = 2 ha + bit` (an IMAD, FMA pipe)
+// leaves bit r for residue r.
 template <int SIGMA, int ZP, int RSHIFT>
 __device__ __forceinline__ void residue_loop(const ProbeParams& P, WarpCtx& c, const SlotRegs& R) {
   const uint32_t wlo = (uint32_t)R.word, whi = (uint32_t)(R.word >> 32);
-  uint32_t hits = 0;
+  uint32_t ha = 0;
 #pragma unroll
-  for (int r = 0; r < SIGMA; r++) {
+  for (int r = SIGMA - 1; r >= 0; r--) {
     // the pattern field is linear in the hash: slot part ^ (position, residue) part (common.cuh)
-    if (pattern_hit_halves(wlo, whi, R.fbase ^ R.erow[r * ZP])) hits |= 1u << r;
+    ha = ha * 2u + (pattern_half_lo(wlo, R.fbase ^ R.erow[r * ZP]) & 1u);
   }
-  hits &= R.allowed;
-  // survivors: a fraction of a percent of the candidates (false positives + true matches)
-  while (__any_sync(FULL, hits != 0)) {
-    const bool pass = hits != 0;
-    const uint32_t r = pass ? (uint32_t)__ffs((int)hits) - 1u : 0u;
+  ha &= R.allowed;
+  while (__any_sync(FULL, ha != 0)) {
+    const bool live = ha != 0;
+    const uint32_t r = live ? (uint32_t)__ffs((int)ha) - 1u : 0u;
+    const bool pass = live && (pattern_half_hi(whi, R.fbase ^ R.erow[r * ZP]) & 1u);
     const uint64_t hv = R.base2 ^ R.zrow[r * ZP];
     const uint32_t var = R.var | (r << RSHIFT);
-    submit(P, c, pass, hv, [var] { return var; }, R.seed);
-    hits &= hits - 1;
+    submit(P, c, pass, hv, [var] { return var; }, R.seed);  // survivors: false positives + true matches
+    ha &= ha - 1;
   }
 }
 

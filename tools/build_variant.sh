@@ -9,12 +9,12 @@ set -e
 name=$1; shift
 cd "$(dirname "$0")/../compairr_b200/csrc"
 mkdir -p ../../_scratch/obj_$name
-for f in kernels variant engine upload brute hamming_tc cluster; do
+for f in kernels variant engine upload brute hamming_tc cluster comm; do
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC \
     -ccbin /usr/bin/g++ --expt-relaxed-constexpr "$@" -c -o ../../_scratch/obj_$name/$f.o $f.cu &
 done
 wait
 /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -shared -o ../../_scratch/lib_$name.so \
-  ../../_scratch/obj_$name/*.o -ccbin /usr/bin/g++ -cudart shared -lpthread
+  ../../_scratch/obj_$name/*.o -ccbin /usr/bin/g++ -cudart shared -lnccl -lpthread
 rm -rf ../../_scratch/obj_$name
 echo "built _scratch/lib_$name.so"
