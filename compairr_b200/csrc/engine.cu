@@ -235,6 +235,8 @@ extern "C" void cb_destroy(cb_ctx* c) {
   cb_dfree(c->d_ztab);
   cb_dfree(c->d_counters);
   if (c->h_counters) cudaFreeHost(c->h_counters);
+  for (auto& q : c->pin)
+    if (q) cudaFreeHost(q);
   cb_dfree(c->d_table);
   cb_dfree(c->d_bloom);
   if (!c->matrix_external) cb_dfree(c->d_matrix);

@@ -57,6 +57,8 @@ struct cb_ctx {
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D side of the pipelined upload
   cudaMemPool_t pool = nullptr;        // the context's own stream-ordered memory pool
+  void* pin[2] = {nullptr, nullptr};   // pinned pass-through buffers of the upload pipeline (pageable callers)
+  size_t pin_bytes[2] = {0, 0};
   cudaEvent_t ev[8]{};
   std::string err;
 

@@ -1,21 +1,26 @@
 // hamming_tc.cu — K5 on the 5th-generation tensor cores: d >= 3 Hamming comparison of one length
-// bucket as a one-hot int8 GEMM (replaces process_trad + seq_diff, overlap.cc:286-359,
-// util.cc:172-184, for buckets where it really is a dense contraction).
+// bucket as an int8 GEMM (replaces process_trad + seq_diff, overlap.cc:286-359, util.cc:172-184,
+// for buckets where it really is a dense contraction).
 //
-//   A (set-A tile)  128 sequences x K one-hot bytes, K = sigma * L rounded up to 32
-//   B (set-B tile)  256 sequences x K one-hot bytes
-//   D = A * B^T     128 x 256 int32 in TMEM = number of EQUAL positions of every pair
-//   epilogue        tcgen05.ld -> registers, match <=> D >= L - d; rare matches -> score,
-//                   matrix atomics, pair append.  D never leaves the SM.
-//
-// tcgen05.mma.cta_group::1.kind::i8, M = 128, N = 256, K = 32 per instruction, operands in shared
-// memory in the canonical K-major no-swizzle ("interleave") layout: 8-row x 16-byte core matrices,
-// row groups SBO = 128 B apart, 16-byte K chunks LBO = (rows / 8) * 128 B apart.  The one-hot
-// tiles are written by the CTA's threads (generic proxy), so a fence.proxy.async precedes the MMAs.
-// One thread issues the MMAs and commits them to an mbarrier; all four warps wait on it and read
-// their own 32-lane quarter of the accumulator.  Double-buffered: while the MMAs of B tile t run,
-// the warps build the one-hot image of tile t+1 — 2 x 256 TMEM columns, two B buffers in shared
-// memory.
+//   row image        NT: 4 one-hot bytes per position (D = number of equal positions, exact);
+//                    AA: an 8-byte weighted code per position (equal residues contribute 8,
+//                    different ones at most 6): D >= 8 (L - d) is NECESSARY for distance <= d, the
+//                    few candidates are verified exactly.  2.5 x fewer MACs and bytes than one-hot.
+//   work item        256 set-A rows (two 128-row A tiles, built once) x a run of 128-row set-B tiles
+//   D = A * B^T      tcgen05.mma.cta_group::1.kind::i8, M = 128, N = 128, K = 32 per instruction,
+//                    S32 accumulators in TMEM: 2 stages x 2 A tiles x 128 columns = all 512 columns
+//   operands         shared memory, canonical K-major no-swizzle layout (8-row x 16-byte core
+//                    matrices, row groups SBO = 128 B apart, 16-byte K chunks LBO = (rows / 8) * 128 B
+//                    apart), written by the CTA's own threads from packed residues through a
+//                    residue-pair LUT (no TMA: the tiles do not exist in memory); fence.proxy.async
+//                    before the MMAs
+//   warps (13)       0-7 epilogue (TMEM lane quarter x column half: tcgen05.ld, threshold test by a
+//                    tree of 3-input maxima, rare candidates -> per-warp queue -> exact verify,
+//                    score, matrix atomics, pair append; D never leaves the SM), 8-11 tile builders
+//                    (thread = set-B row, next tile's words prefetched), 12 MMA issue
+//   pipeline         mbarriers only, no CTA barrier inside an item: FULL_B[s] (128 builder
+//                    arrivals) -> MMA; tcgen05.commit -> ACC_FULL[a] and B_FREE[s]; ACC_FREE[a]
+//                    as soon as an accumulator stage is in registers; up to 4 B stages
 #include <cuda_runtime.h>
 
 #include "device_utils.cuh"

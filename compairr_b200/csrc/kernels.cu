@@ -2,17 +2,18 @@
 //
 //   pack_meta_kernel   SoA upload -> 32-byte SeqMeta records (+ longest length)
 //   hash_kernel        K1  batched Zobrist hashing                    (replaces zobrist.cc:74-88, db.cc:903-916)
-//   build_kernel       K2  open-addressing insert + Bloom set         (replaces overlap.cc:63-128 insert part,
+//   build_kernel       K2  open-addressing insert (+ filter bits)     (replaces overlap.cc:63-128 insert part,
 //                                                                      hashtable.h:48-77, bloompat.h:50-53)
 //   dups_kernel        K2b exact-duplicate count                      (replaces overlap.cc:63-128 dup part, :579-605)
+//   filter_kernel      K2  the four class filters of a large set, L2-sized word ranges at a time
 //   identical_kernel   K3/K4 for d = 0: one thread per seed           (replaces overlap.cc:253-284 with variants.cc:260-268)
-//   variant_kernel     K3/K4 for d = 1,2: one warp per seed (part): on-the-fly variant hashes by
-//                      incremental XOR, Bloom prefilter, table probe, exact verify, score,
-//                      matrix accumulation, pair append               (replaces variants.cc:270-428, overlap.cc:168-284)
+//   (d = 1, 2: the enumeration kernels and the table stage are in variant.cu; d >= 3: brute.cu, hamming_tc.cu)
 //
-// All of this is integer/byte work bound by random 8-byte Bloom reads (one 32-byte sector per
-// probe); nothing here is a GEMM, so no tensor cores (see DESIGN.md for the roofline).
+// Integer and byte work: streaming passes (pack, hash), random read-modify-writes (table, filters)
+// and dependent random loads (probe chains); nothing here is a GEMM, so no tensor cores (DESIGN.md
+// has each kernel's bound).
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "kernels.cuh"
 #include "device_utils.cuh"
@@ -270,8 +271,14 @@ int launch_filters(const uint64_t* hash, uint64_t n, unsigned long long* bloom, 
                    cudaStream_t st) {
   if (n == 0) return 0;
   // word ranges of at most ~48 MiB: resident in L2 beside the streamed hashes
+  // (COMPAIRR_B200_FILTER_PART_MIB: tuning knob for measurements)
+  static const uint64_t part_mib = [] {
+    const char* e = getenv("COMPAIRR_B200_FILTER_PART_MIB");
+    const long v = e ? strtol(e, nullptr, 10) : 0;
+    return (uint64_t)(v > 0 ? v : 48);
+  }();
   const uint64_t bytes = (uint64_t)bloom_blocks * 8;
-  uint32_t parts = (uint32_t)((bytes + (48ull << 20) - 1) / (48ull << 20));
+  uint32_t parts = (uint32_t)((bytes + (part_mib << 20) - 1) / (part_mib << 20));
   if (parts < 1) parts = 1;
   if (parts > 16) parts = 16;
   const uint64_t blocks = (n + 255) / 256;

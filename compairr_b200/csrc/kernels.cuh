@@ -34,12 +34,13 @@ struct DeviceSetView {
   uint64_t index_base;
 };
 
-// Shared-memory matrix tile: up to 4096 cells (32 KB, 64 x 64 repertoires) — the table kernel keeps
-// its 4 CTAs per SM.  Measured on 2 * 10^6 low-complexity sequences, self-comparison, d = 1 -i
-// (5.4e10 matches): 2 repertoires 2.9 s with the tile vs 52 s without (18 x; every match lands on
-// one of 4 cells), 8 repertoires 1.5 vs 8.2 s; at 100 x 100 repertoires an 80 KB tile (2 CTAs per
-// SM) LOST 2.6 x against plain global REDs, which by then spread over 10^4 cells.
-constexpr uint32_t MATRIX_TILE_MAX_CELLS = 4096;
+// Shared-memory matrix tile: up to 1024 cells (8 KB, 32 x 32 repertoires).  Measured on 10^6
+// low-complexity sequences, self-comparison, d = 1 -i (1.35e10 matches; tools/tile_ab.py): with the
+// tile vs plain global REDs — 2 repertoires (every match on one of 4 cells) 0.74 s vs 12.8 s, 8
+// repertoires 0.42 vs 2.04 s, 32 x 32 repertoires 0.68 vs 0.68 s, 64 x 64 0.68 vs 0.44 s: beyond
+// ~10^3 cells the global REDs are spread thinly enough and shared-memory f64 atomics (CAS loops)
+// lose.
+constexpr uint32_t MATRIX_TILE_MAX_CELLS = 1024;
 
 struct ProbeParams {
   DeviceSetView a;

@@ -122,31 +122,28 @@ struct SlotRegs {
 
 // The inner loop: all SIGMA residues of every lane's slot.  RSHIFT: where the free residue goes in
 // the descriptor (3 = res1: substitution / insertion, 8 = res2: second substitution).
-//
-// Two stages.  The loop tests only the three bits of the LOW half of the word (3 variable shifts
-// and a 3-input AND per candidate: the ALU pipe, which issues every other cycle, is what bounds
-// this kernel); ~3 % of the candidates pass it (0.3^3 at 16 bits per key).  Those are looked at
-// again — high half, exact survivors into the ring — in a short loop over the set bits, a couple of
-// iterations per pass.  Residues are walked downwards so that `ha = 2 ha + bit` (an IMAD, FMA pipe)
-// leaves bit r for residue r.
+// (Tried and dropped: a two-stage test — low half of the word for every candidate, high half only
+// for the 3 % that pass it.  The second stage is a loop over each lane's set bits, ~4 iterations per
+// pass at 5 of 32 lanes active; it cost what the first stage saved, and its branchy body pushed the
+// kernel into instruction-cache misses: 23 % of stall samples "no instruction", d = 1 -i 10 % slower.)
 template <int SIGMA, int ZP, int RSHIFT>
 __device__ __forceinline__ void residue_loop(const ProbeParams& P, WarpCtx& c, const SlotRegs& R) {
   const uint32_t wlo = (uint32_t)R.word, whi = (uint32_t)(R.word >> 32);
-  uint32_t ha = 0;
+  uint32_t hits = 0;
 #pragma unroll
-  for (int r = SIGMA - 1; r >= 0; r--) {
+  for (int r = 0; r < SIGMA; r++) {
     // the pattern field is linear in the hash: slot part ^ (position, residue) part (common.cuh)
-    ha = ha * 2u + (pattern_half_lo(wlo, R.fbase ^ R.erow[r * ZP]) & 1u);
+    if (pattern_hit_halves(wlo, whi, R.fbase ^ R.erow[r * ZP])) hits |= 1u << r;
   }
-  ha &= R.allowed;
-  while (__any_sync(FULL, ha != 0)) {
-    const bool live = ha != 0;
-    const uint32_t r = live ? (uint32_t)__ffs((int)ha) - 1u : 0u;
-    const bool pass = live && (pattern_half_hi(whi, R.fbase ^ R.erow[r * ZP]) & 1u);
+  hits &= R.allowed;
+  // survivors: a fraction of a percent of the candidates (false positives + true matches)
+  while (__any_sync(FULL, hits != 0)) {
+    const bool pass = hits != 0;
+    const uint32_t r = pass ? (uint32_t)__ffs((int)hits) - 1u : 0u;
     const uint64_t hv = R.base2 ^ R.zrow[r * ZP];
     const uint32_t var = R.var | (r << RSHIFT);
-    submit(P, c, pass, hv, [var] { return var; }, R.seed);  // survivors: false positives + true matches
-    ha &= ha - 1;
+    submit(P, c, pass, hv, [var] { return var; }, R.seed);
+    hits &= hits - 1;
   }
 }
 
@@ -338,23 +335,26 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
       R.seed = (uint32_t)first + k;
       return R;
     };
-    auto passes = [&](uint32_t n, auto load) {
-      if (n == 0) return;
-      SlotRegs cur = load(lane, n);
-      for (uint32_t g0 = 0; g0 < n; g0 += 32) {
+    // one loop over both lists (the residue loop is inlined once: code size matters here, see residue_loop)
+    const uint32_t n_sub = b_cum[WB], n_ins = INDELS ? b_icum[WB] : 0;
+    const uint32_t p_sub = (n_sub + 31) / 32, p_all = p_sub + (n_ins + 31) / 32;
+    auto load = [&](uint32_t t) {
+      return (!INDELS || t < p_sub) ? load_sub(t * 32 + lane, n_sub) : load_ins((t - p_sub) * 32 + lane, n_ins);
+    };
+    if (p_all) {
+      SlotRegs cur = load(0);
+      for (uint32_t t = 0; t < p_all; t++) {
         SlotRegs nxt = cur;
-        if (g0 + 32 < n) nxt = load(g0 + 32 + lane, n);  // the next pass's words are in flight during this one
+        if (t + 1 < p_all) nxt = load(t + 1);  // the next pass's words are in flight during this one
         residue_loop<SIGMA, ZP, 3>(P, c, cur);
         cur = nxt;
       }
-    };
-    passes(b_cum[WB], load_sub);
-    if (INDELS) passes(b_icum[WB], load_ins);
+    }
 
     // ---- deletions (one per run of equal residues, only if L > 1, variants.cc:301-325) and the
     // identical candidate of every seed: one candidate per item ---------------------------------------------
     const uint32_t n_items = b_dcum[WB];
-    constexpr int DU = 4;  // item passes in flight: their filter-word loads are issued together
+    constexpr int DU = 2;  // item passes in flight: their filter-word loads are issued together
     for (uint32_t g0 = 0; g0 < n_items; g0 += 32 * DU) {
       uint64_t hv[DU];
       unsigned long long w[DU];

@@ -219,7 +219,7 @@ def test_matrix_tile_equals_global_atomics(d, indels, score):
 
 
 def test_matrix_too_large_for_a_tile():
-    """More cells than the tile holds (> 10240): the global-atomics path, same answer."""
+    """More cells than the tile holds (> 1024): the global-atomics path, same answer."""
     a = synth.small_dense_set(311, 120, 40, max_len=5)
     b = synth.small_dense_set(312, 110, 40, max_len=5)
     m, _, info = overlap(a, b, OverlapOptions(differences=1, indels=True))
