@@ -238,24 +238,11 @@ CB_HD uint32_t shr_wrap(uint32_t x, uint32_t s) {
 // Does the filter word (lo, hi) contain bloom_pattern(f)?  The same test as (w & pattern) == pattern,
 // written as shifts of the word instead of a mask built from six variable shifts (tests/csrc/
 // hd_check.cpp checks the equivalence): no branches.
-// f >> k for a constant k.  On the device as the high half of f * 2^(32-k): an IMAD.HI on the FMA
-// pipe.  Shifts and logic ops share the ALU pipe, which issues one warp instruction every other
-// cycle per scheduler (B300_MICROARCH.md: rt_SMSP = 2); the test is eleven such operations, and
-// with its five constant shifts moved over the two pipes run side by side.
-#ifndef CB_SHIFT_ON_FMA
-#define CB_SHIFT_ON_FMA 1  // 0: plain shifts (A/B builds, tools/build_variant.sh)
-#endif
+// f >> k for a constant k.  (Tried: the high half of f * 2^(32-k), an IMAD.HI on the FMA pipe, to
+// take the five constant shifts off the ALU pipe, which issues every other cycle and bounds the
+// enumeration loop — no measurable change at C3 geometry, 15.9 vs 15.8 ms; plain shifts kept.)
 template <int K>
-CB_HD uint32_t shr_const(uint32_t f) {
-#if defined(__CUDA_ARCH__) && CB_SHIFT_ON_FMA
-  if (K == 0) return f;
-  uint32_t r;
-  asm("mul.hi.u32 %0, %1, %2;" : "=r"(r) : "r"(f), "r"(1u << ((32 - K) & 31)));
-  return r;
-#else
-  return f >> K;
-#endif
-}
+CB_HD uint32_t shr_const(uint32_t f) { return f >> K; }
 // bit 0 of the result: the pattern bits of f in the low (high) half of the word are all set
 CB_HD uint32_t pattern_half_lo(uint32_t lo, uint32_t f) {
   uint32_t a = shr_wrap(lo, shr_const<CB_PAT_A0>(f)) & shr_wrap(lo, shr_const<CB_PAT_A1>(f));

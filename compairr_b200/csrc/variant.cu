@@ -122,19 +122,46 @@ struct SlotRegs {
 
 // The inner loop: all SIGMA residues of every lane's slot.  RSHIFT: where the free residue goes in
 // the descriptor (3 = res1: substitution / insertion, 8 = res2: second substitution).
-// (Tried and dropped: a two-stage test — low half of the word for every candidate, high half only
-// for the 3 % that pass it.  The second stage is a loop over each lane's set bits, ~4 iterations per
-// pass at 5 of 32 lanes active; it cost what the first stage saved, and its branchy body pushed the
-// kernel into instruction-cache misses: 23 % of stall samples "no instruction", d = 1 -i 10 % slower.)
-template <int SIGMA, int ZP, int RSHIFT>
+//
+// Two forms of the filter test:
+//   one stage    all 3 + 3 pattern bits for every candidate; the (rare) survivors are extracted
+//                after the loop.  14.75 warp instructions per 32 candidates.
+//   two stages   the loop tests only the three bits of the LOW half of the word (9 instructions per
+//                32 candidates); the ~3 % that pass are looked at again — high half, survivors into
+//                the ring — in a loop over each lane's set bits, ~4 iterations per pass at 5 of 32
+//                lanes active.
+// Measured at C3 geometry (kernels incl. table stage): d = 2  7.9 ms two-stage vs 10.2 ms one-stage;
+// d = 1 -i  17.2 ms two-stage vs 15.9 ms one-stage — in the larger d = 1 kernel the branchy second
+// stage put 23 % of the stall samples on instruction-cache misses ("no instruction").  So d = 2 runs
+// the two-stage form and d = 1 the one-stage form (CB_E1_TWO_STAGE for A/B builds).
+#ifndef CB_E1_TWO_STAGE
+#define CB_E1_TWO_STAGE 0
+#endif
+template <int SIGMA, int ZP, int RSHIFT, bool TWO_STAGE>
 __device__ __forceinline__ void residue_loop(const ProbeParams& P, WarpCtx& c, const SlotRegs& R) {
   const uint32_t wlo = (uint32_t)R.word, whi = (uint32_t)(R.word >> 32);
+  // the pattern field is linear in the hash: slot part ^ (position, residue) part (common.cuh)
+  if (TWO_STAGE) {
+    uint32_t ha = 0;
+#pragma unroll
+    for (int r = SIGMA - 1; r >= 0; r--)  // downwards: ha = 2 ha + bit leaves bit r for residue r
+      ha = ha * 2u + (pattern_half_lo(wlo, R.fbase ^ R.erow[r * ZP]) & 1u);
+    ha &= R.allowed;
+    while (__any_sync(FULL, ha != 0)) {
+      const bool live = ha != 0;
+      const uint32_t r = live ? (uint32_t)__ffs((int)ha) - 1u : 0u;
+      const bool pass = live && (pattern_half_hi(whi, R.fbase ^ R.erow[r * ZP]) & 1u);
+      const uint64_t hv = R.base2 ^ R.zrow[r * ZP];
+      const uint32_t var = R.var | (r << RSHIFT);
+      submit(P, c, pass, hv, [var] { return var; }, R.seed);  // survivors: false positives + true matches
+      ha &= ha - 1;
+    }
+    return;
+  }
   uint32_t hits = 0;
 #pragma unroll
-  for (int r = 0; r < SIGMA; r++) {
-    // the pattern field is linear in the hash: slot part ^ (position, residue) part (common.cuh)
+  for (int r = 0; r < SIGMA; r++)
     if (pattern_hit_halves(wlo, whi, R.fbase ^ R.erow[r * ZP])) hits |= 1u << r;
-  }
   hits &= R.allowed;
   // survivors: a fraction of a percent of the candidates (false positives + true matches)
   while (__any_sync(FULL, hits != 0)) {
@@ -346,7 +373,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
       for (uint32_t t = 0; t < p_all; t++) {
         SlotRegs nxt = cur;
         if (t + 1 < p_all) nxt = load(t + 1);  // the next pass's words are in flight during this one
-        residue_loop<SIGMA, ZP, 3>(P, c, cur);
+        residue_loop<SIGMA, ZP, 3, CB_E1_TWO_STAGE != 0>(P, c, cur);
         cur = nxt;
       }
     }
@@ -464,7 +491,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_const
         R.fbase = pattern_field(R.base2, lane & 3);
         R.var = pack_var(VK_SUBSTITUTION, pc, 0, 0, 0);
         R.seed = slocal;
-        residue_loop<SIGMA, ZP, 3>(P, c, R);
+        residue_loop<SIGMA, ZP, 3, true>(P, c, R);
       }
       submit(P, c, lane == 0 && pattern_hit(ws, pattern_field(h, 0)), h, [] { return pack_var(VK_IDENTICAL, 0, 0, 0, 0); }, slocal);
     }
@@ -499,7 +526,7 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum2_kernel(const __grid_const
       for (uint32_t t = part; t < n_pass; t += P.split) {
         SlotRegs nxt = cur;
         if (t + P.split < n_pass) nxt = load_slot((t + P.split) * 32 + lane);  // one pass ahead: its word is in flight
-        residue_loop<SIGMA, ZP, 8>(P, c, cur);
+        residue_loop<SIGMA, ZP, 8, true>(P, c, cur);
         cur = nxt;
       }
     }
