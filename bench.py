@@ -363,6 +363,7 @@ def run_ours(a):
     # host memory; of set B only this rank's shard (cb_shard_range)
     bf, bc = cdist.shard_range(b.n, rank, world)
     b_shard_e2e = pin_narrow(b.slice(bf, bc), n_reps=b.n_reps)
+    b_shard_e2e.index_base = 0              # of the whole set
     a_e2e = pin_narrow(a_sh)
     h2d_rank = b_shard_e2e.nbytes() + a_e2e.nbytes()
     a_d2 = a_sh.slice(0, min(a.d2_seeds, a_sh.n))
@@ -467,11 +468,21 @@ def run_ours(a):
 
     # ---- end to end: host buffers in, matrix out, every step ------------------------------------------
     def step_e2e():
+        t0 = time.perf_counter()
         eng.set_b_sharded(b_shard_e2e, n_b)     # 1/world over PCIe, all-gather over NVLink, build
+        sb = eng.stats()
+        t1 = time.perf_counter()
         eng.clear_matrix()
         eng.run_a(a_e2e)
+        t2 = time.perf_counter()
         eng.allreduce_matrix()
-        return eng.matrix()
+        m = eng.matrix()
+        t3 = time.perf_counter()
+        if debug:
+            print(f"[e2e rank {rank}] set_b {1e3*(t1-t0):.1f} (upload+hash {sb['ms_hash_b']:.1f}, gather {sb['ms_gather_b']:.1f}, "
+                  f"build {sb['ms_build_b']:.1f}, dups {sb['ms_dups_b']:.1f}) run_a {1e3*(t2-t1):.1f} reduce+read {1e3*(t3-t2):.1f}",
+                  file=sys.stderr, flush=True)
+        return m
     for _ in range(a.warmup):
         step_e2e()
     sync_all()

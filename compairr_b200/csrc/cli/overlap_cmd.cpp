@@ -265,7 +265,8 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
       th.emplace_back([&, g] {
         uint64_t first = 0, count = d2.n();
         cb_shard_range(d2.n(), g, ngpu, &first, &count);
-        const cb_set_cols shard = cols_of(d2, first, count);
+        cb_set_cols shard = cols_of(d2, first, count);
+        shard.index_base = 0;  // of the whole set: hits are reported by their index in set 2
         if (cb_set_b_sharded(ctx[g], &shard, d2.n())) rank_fatal(ctx[g]);
       });
     for (auto& t : th) t.join();

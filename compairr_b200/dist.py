@@ -94,7 +94,7 @@ def overlap_rank(eng, a: SeqSet, b: SeqSet, rank: int, world: int, differences: 
     every rank).  `eng` has joined the communicator already (Engine.comm_init_rank)."""
     first, count = shard_range(b.n, rank, world)
     shard = NarrowSet.from_seqset(b.slice(first, count))
-    shard.n_reps = b.n_reps
+    shard.n_reps, shard.index_base = b.n_reps, b.index_base     # of the WHOLE set, the same on every rank
     eng.set_b_sharded(shard, b.n)
     f, c = plan_shards(a.lengths, world, a.sigma, differences, indels)[rank]
     eng.run_a(a.slice(f, c))        # the slice carries index_base = f: pairs and -x rows are global

@@ -279,7 +279,7 @@ int cb_comm_rank(const cb_ctx *ctx, int *rank, int *world);
    empty).  Host helper, no GPU work. */
 void cb_shard_range(uint64_t n_total, int rank, int world, uint64_t *first, uint64_t *count);
 /* cb_set_b for a communicator: `shard` = this rank's cb_shard_range of set B (columns as in
-   cb_set_b_cols; n_reps = repertoires of the WHOLE set).  Each rank copies only its shard across
+   cb_set_b_cols; n_reps and index_base are those of the WHOLE set, the same on every rank).  Each rank copies only its shard across
    PCIe, packs and hashes it; records, hashes and residues are all-gathered over NVLink; every
    rank then builds the table and the filters of the whole set (the reference's one shared table,
    src/overlap.cc:861-873, replicated per GPU).  Collective.  Sequence indices (pairs, existence

@@ -38,7 +38,7 @@ def _run_world(a, b, world, kw, want_pairs=False):
         try:
             first, count = cdist.shard_range(b.n, r, world)
             shard = NarrowSet.from_seqset(b.slice(first, count))
-            shard.n_reps = b.n_reps
+            shard.n_reps, shard.index_base = b.n_reps, b.index_base
             engs[r].set_b_sharded(shard, b.n)
             f, c = cdist.plan_shards(a.lengths, world, a.sigma, kw.get("differences", 0), kw.get("indels", False))[r]
             engs[r].run_a(a.slice(f, c))
@@ -119,7 +119,7 @@ def test_two_gpus_self_comparison_more_ranks_than_work():
     def rank(r):
         first, count = cdist.shard_range(s.n, r, 2)
         sh = NarrowSet.from_seqset(s.slice(first, count))
-        sh.n_reps = s.n_reps
+        sh.n_reps, sh.index_base = s.n_reps, s.index_base
         engs[r].set_b_sharded(sh, s.n)
         if r == 0:                                  # rank 0 takes everything, rank 1 nothing
             engs[r].run(engs[r].resident_b(), 0, s.n)
