@@ -429,6 +429,35 @@ def run_ours(a):
     run_stats = main["stats"]
     build_stats_launch = eng.stats()
 
+    # ---- end to end: host buffers in, matrix out, every step ------------------------------------------
+    def step_e2e():
+        t0 = time.perf_counter()
+        eng.set_b_sharded(b_shard_e2e, n_b)     # 1/world over PCIe, all-gather over NVLink, build
+        sb = eng.stats()
+        t1 = time.perf_counter()
+        eng.clear_matrix()
+        eng.run_a(a_e2e)
+        t2 = time.perf_counter()
+        eng.allreduce_matrix()
+        m = eng.matrix()
+        t3 = time.perf_counter()
+        if debug:
+            print(f"[e2e rank {rank}] set_b {1e3*(t1-t0):.1f} (upload+hash {sb['ms_hash_b']:.1f}, gather {sb['ms_gather_b']:.1f}, "
+                  f"build {sb['ms_build_b']:.1f}, dups {sb['ms_dups_b']:.1f}) run_a {1e3*(t2-t1):.1f} reduce+read {1e3*(t3-t2):.1f}",
+                  file=sys.stderr, flush=True)
+        return m
+    for _ in range(a.warmup):
+        step_e2e()
+    sync_all()
+    t0e = time.perf_counter()
+    for _ in range(a.steps):
+        m_e2e = step_e2e()
+    e2e_stats = eng.stats()
+    sync_all()
+    ms_e2e = 1e3 * (time.perf_counter() - t0e)
+    d2h = int(m_e2e.nbytes)
+    e2e_checksum = float(m_e2e.sum())
+
     # ---- strong scaling: the fixed C3 problem, set A = strong_reps_a repertoires over all GPUs ------------
     strong = None
     reps_strong = a.strong_reps_a or a.reps_b
@@ -465,35 +494,6 @@ def run_ours(a):
     if da is not None:
         da.free()
     db.free()
-
-    # ---- end to end: host buffers in, matrix out, every step ------------------------------------------
-    def step_e2e():
-        t0 = time.perf_counter()
-        eng.set_b_sharded(b_shard_e2e, n_b)     # 1/world over PCIe, all-gather over NVLink, build
-        sb = eng.stats()
-        t1 = time.perf_counter()
-        eng.clear_matrix()
-        eng.run_a(a_e2e)
-        t2 = time.perf_counter()
-        eng.allreduce_matrix()
-        m = eng.matrix()
-        t3 = time.perf_counter()
-        if debug:
-            print(f"[e2e rank {rank}] set_b {1e3*(t1-t0):.1f} (upload+hash {sb['ms_hash_b']:.1f}, gather {sb['ms_gather_b']:.1f}, "
-                  f"build {sb['ms_build_b']:.1f}, dups {sb['ms_dups_b']:.1f}) run_a {1e3*(t2-t1):.1f} reduce+read {1e3*(t3-t2):.1f}",
-                  file=sys.stderr, flush=True)
-        return m
-    for _ in range(a.warmup):
-        step_e2e()
-    sync_all()
-    t0e = time.perf_counter()
-    for _ in range(a.steps):
-        m_e2e = step_e2e()
-    e2e_stats = eng.stats()
-    sync_all()
-    ms_e2e = 1e3 * (time.perf_counter() - t0e)
-    d2h = int(m_e2e.nbytes)
-    e2e_checksum = float(m_e2e.sum())
 
     # ---- parity at this N: engine (sharded B, sharded A, all-reduce) vs the unmodified reference ------------
     parity = None

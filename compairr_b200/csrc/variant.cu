@@ -137,9 +137,6 @@ struct SlotRegs {
 #ifndef CB_E1_TWO_STAGE
 #define CB_E1_TWO_STAGE 0
 #endif
-#ifndef CB_E1_DU
-#define CB_E1_DU 4
-#endif
 template <int SIGMA, int ZP, int RSHIFT, bool TWO_STAGE>
 __device__ __forceinline__ void residue_loop(const ProbeParams& P, WarpCtx& c, const SlotRegs& R) {
   const uint32_t wlo = (uint32_t)R.word, whi = (uint32_t)(R.word >> 32);
@@ -253,51 +250,34 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
   const uint64_t n_batches = (P.w_count + WB - 1) / WB;
   constexpr uint32_t ALL = (SIGMA >= 32) ? 0xffffffffu : ((1u << SIGMA) - 1u);
 
-  // The dependent chain in front of a batch — dispenser -> records and hashes -> residues and filter
-  // words — is three global round trips (19 % of the stall samples when paid per batch).  Two of them
-  // are taken off the critical path: the dispenser runs two batches ahead, and the next batch's
-  // records and hashes are fetched into registers while the current batch is being worked on.
-  auto take = [&]() {  // next batch index for this warp (lane 0 holds the value in flight)
+  for (;;) {
     unsigned long long b = 0;
     if (lane == 0) b = atomicAdd(P.counters + CTR_WORK, 1ull);
-    return b;
-  };
-  auto fetch = [&](unsigned long long b, uint64_t& off_len, uint64_t& hk) {  // records (lanes < WB) and hashes (lane / 4) of batch b
-    off_len = 0;
-    hk = 0;
-    if (b >= n_batches) return;
-    const uint64_t first = P.w_first + b * WB;
-    const uint64_t left = P.w_first + P.w_count - first;
-    const uint32_t nb = left < WB ? (uint32_t)left : WB;
-    if (lane < nb) off_len = __ldg(&P.a.meta[P.a_first + first + lane].off_len);
-    if (lane < 4 * nb) hk = __ldg(P.a.hash + P.a_first + first + (lane >> 2));
-  };
-  unsigned long long b = __shfl_sync(FULL, take(), 0);
-  unsigned long long b_next = take();  // in flight; read (shuffled) one iteration later
-  uint64_t pf_off_len, pf_hk;
-  fetch(b, pf_off_len, pf_hk);
-  for (;;) {
+    b = __shfl_sync(FULL, b, 0);
     if (b >= n_batches) break;
     const uint64_t first = P.w_first + b * WB;  // relative to a_first
     const uint32_t nb = (uint32_t)((P.w_first + P.w_count - first < WB) ? P.w_first + P.w_count - first : WB);
     __syncwarp();  // previous batch fully consumed
 
-    // ---- stage the batch: lengths, hashes, residues, each seed's own word in the four filters
+    // ---- stage the batch: lengths, hashes, residues, each seed's own word in the four filters.
+    // (Tried and dropped: running the dispenser two batches ahead and fetching the next batch's
+    // records and hashes into registers while the current batch is worked on — the chain dispenser
+    // -> records -> residues is 19 % of the stall samples — 16.1 vs 15.9 ms at C3 geometry: the six
+    // extra live registers cost what the hidden latency gained; four deletion passes of loads in
+    // flight instead of two: 17.5 ms, the unrolled copies grow the kernel by a quarter.)
     uint64_t my_off = 0;
     uint32_t my_len = LEN_SKIP;
     if (lane < nb) {
-      const uint32_t L = (uint32_t)(pf_off_len >> 40);
-      my_off = pf_off_len & ((1ull << 40) - 1);
+      const uint64_t off_len = __ldg(&P.a.meta[P.a_first + first + lane].off_len);
+      const uint32_t L = (uint32_t)(off_len >> 40);
+      my_off = off_len & ((1ull << 40) - 1);
       if (L >= P.len_lo && L <= P.len_hi) my_len = L;
     }
     if (lane < 4 * nb) {  // the seed's own word in each class filter = the word of all its substitution slots of that class
-      if ((lane & 3) == 0) b_hash[lane >> 2] = pf_hk;
-      b_ws[lane] = filter_word(P, pf_hk, lane & 3);
+      const uint64_t hk = __ldg(P.a.hash + P.a_first + first + (lane >> 2));
+      if ((lane & 3) == 0) b_hash[lane >> 2] = hk;
+      b_ws[lane] = filter_word(P, hk, lane & 3);
     }
-    // the batch after this one: its index has arrived by now; the one after that goes in flight
-    b = __shfl_sync(FULL, b_next, 0);
-    b_next = take();
-    fetch(b, pf_off_len, pf_hk);
     {  // slot and item counts -> inclusive prefix sums over the WB seeds
       const bool live = my_len != LEN_SKIP;
       // L substitution slots, L + 1 insertion slots, L deletion candidates + the identical one: the
@@ -406,42 +386,41 @@ __global__ void __launch_bounds__(VK_THREADS, 3) enum1_kernel(const __grid_const
     // ---- deletions (one per run of equal residues, only if L > 1, variants.cc:301-325) and the
     // identical candidate of every seed: one candidate per item ---------------------------------------------
     const uint32_t n_items = b_dcum[WB];
-    constexpr int DU = CB_E1_DU;  // item passes whose filter-word loads are in flight together (a batch of 8 seeds is ~4 passes)
-    auto item = [&](uint32_t g, uint64_t& hv, uint32_t& desc, uint32_t& k) {  // decodes item g; true for a deletion
-      const bool in = g < n_items;
-      if (!in) g = 0;
-      k = seed_of(b_dcum, g);
-      const uint32_t L = b_len[k], t = g - b_dcum[k];
-      const bool is_del = INDELS && t < L;
-      hv = b_hash[k];
-      bool valid = in;
-      uint32_t cls = 0;  // identical: any filter will do; the seed's word in filter 0 is at hand
-      if (is_del) {      // no free residue: any filter, spread over the four
-        hv ^= pre[k * ZP + L] ^ pre[k * ZP + t] ^ sm[k * ZP + t + 1];
-        valid = in && L > 1 && (t == 0 || b_res[k * ZP + t] != b_res[k * ZP + t - 1]);
-        cls = pos_class(t);
-      }
-      desc = (is_del ? pack_var(VK_DELETION, t, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0)) | (cls << 29) | ((uint32_t)valid << 31);
-      return is_del;
-    };
+    constexpr int DU = 2;  // item passes in flight: their filter-word loads are issued together
     for (uint32_t g0 = 0; g0 < n_items; g0 += 32 * DU) {
+      uint64_t hv[DU];
       unsigned long long w[DU];
+      uint32_t desc[DU], ks[DU];  // descriptor | filter class << 29 | valid << 31
 #pragma unroll
-      for (int u = 0; u < DU; u++) {  // loads first ...
-        uint64_t hv;
-        uint32_t desc, k;
-        const bool is_del = item(g0 + u * 32 + lane, hv, desc, k);
-        w[u] = is_del ? filter_word(P, hv, (desc >> 29) & 3u) : b_ws[4 * k];
+      for (int u = 0; u < DU; u++) {
+        uint32_t g = g0 + u * 32 + lane;
+        const bool in = g < n_items;
+        if (!in) g = 0;
+        uint32_t k = 0;
+#pragma unroll
+        for (int j = 1; j < WB; j++) k += g >= b_dcum[j];
+        const uint32_t L = b_len[k], t = g - b_dcum[k];
+        const bool is_del = INDELS && t < L;
+        const uint64_t h = b_hash[k];
+        hv[u] = h;
+        bool valid = in;
+        uint32_t cls = 0;
+        w[u] = b_ws[4 * k];  // identical: any filter will do; the seed's word in filter 0 is at hand
+        if (is_del) {        // no free residue: any filter, spread over the four
+          hv[u] = h ^ pre[k * ZP + L] ^ pre[k * ZP + t] ^ sm[k * ZP + t + 1];
+          valid = in && L > 1 && (t == 0 || b_res[k * ZP + t] != b_res[k * ZP + t - 1]);
+          cls = pos_class(t);
+          w[u] = filter_word(P, hv[u], cls);
+        }
+        desc[u] = (is_del ? pack_var(VK_DELETION, t, 0, 0, 0) : pack_var(VK_IDENTICAL, 0, 0, 0, 0)) | (cls << 29) | ((uint32_t)valid << 31);
+        ks[u] = (uint32_t)first + k;
       }
 #pragma unroll
-      for (int u = 0; u < DU; u++) {  // ... then the tests (the item is decoded again: cheaper than keeping it)
+      for (int u = 0; u < DU; u++) {
         if (g0 + u * 32 >= n_items) break;  // warp-uniform
-        uint64_t hv;
-        uint32_t desc, k;
-        item(g0 + u * 32 + lane, hv, desc, k);
-        const bool pass = (desc >> 31) & pattern_hit(w[u], pattern_field(hv, (desc >> 29) & 3u));
-        const uint32_t var = desc & 0x1fffffffu;  // deletion / identical descriptors use bits 0..21 only
-        submit(P, c, pass, hv, [var] { return var; }, (uint32_t)first + k);
+        const bool pass = (desc[u] >> 31) & pattern_hit(w[u], pattern_field(hv[u], (desc[u] >> 29) & 3u));
+        const uint32_t var = desc[u] & 0x1fffffffu;  // deletion / identical descriptors use bits 0..21 only
+        submit(P, c, pass, hv[u], [var] { return var; }, ks[u]);
       }
     }
   }
