@@ -366,6 +366,7 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
 // picked by other functions of the hash and stay random REDs (2 ms each at 10^8).  Small batches (the chunks of the upload pipeline, which hide behind the PCIe copy
 // anyway) keep the direct path.
 void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n) {
+  s->links_dirty = true;
   const uint64_t table_bytes = t.slots * sizeof(Slot);
   uint64_t *key_in = nullptr, *part_hash = nullptr;
   uint32_t *iota = nullptr, *part_idx = nullptr;
@@ -416,7 +417,7 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
 static int build_table_for(cb_ctx* c, cb_dset* s, bool with_bloom, BuiltTable* out) {
   int rc = cb_table_alloc(c, s->n, with_bloom, out);
   if (rc) return rc;
-  launch_reset_next(s->d_meta, s->n, c->stream);  // the set may have been inserted before
+  if (s->links_dirty) launch_reset_next(s->d_meta, s->n, c->stream);  // the set has been inserted before
   cb_table_insert(c, *out, s, 0, s->n);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
@@ -466,6 +467,7 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
   c->stats.ms_build_b = c->stats.ms_dups_b = 0;
   c->stats.kernel_launches = 0;
   BuiltTable bt;
+  const bool reset_links = b->links_dirty;
   if (c->cfg.differences <= MAXDIFF_HASH) {  // the brute-force path has no table and no dup check
     CU(c, cudaEventRecord(c->ev[0], c->stream));
     rc = build_table_for(c, b, true, &bt);
@@ -476,7 +478,7 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
   if (rc) return rc;
   if (c->d_table) {
     cudaEventElapsedTime(&c->stats.ms_build_b, c->ev[0], c->ev[6]);
-    c->stats.kernel_launches = b->n ? 3 + c->insert_launches : 1;  // clear, reset links, [sort,] insert, duplicates
+    c->stats.kernel_launches = b->n ? 2 + (reset_links ? 1 : 0) + c->insert_launches : 1;  // clear, [reset links,] [sort, filters,] insert, duplicates
   }
   return CB_OK;
 }

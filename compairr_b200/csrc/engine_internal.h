@@ -16,6 +16,7 @@ struct cb_dset {
   uint64_t res_bytes = 0;
   uint32_t n_reps = 0;
   uint32_t longest = 0;
+  bool links_dirty = false;  // SeqRec.next written by a table insert (a fresh upload leaves them SEQ_NIL)
   cb::SeqRec* d_meta = nullptr;
   uint8_t* d_res = nullptr;
   uint64_t* d_hash = nullptr;
