@@ -169,11 +169,11 @@ enum ErrKind {
 // What one reader thread produced from its range of lines: the same columns as SeqDb with
 // thread-local id numbering, merged in file order afterwards.
 struct Part {
-  std::vector<uint8_t> residues;
-  std::vector<uint32_t> len, v, j, rep;
-  std::vector<uint64_t> count;
-  std::vector<char> id_arena, keep_arena;
-  std::vector<uint64_t> id_off, keep_off;
+  RawVec<uint8_t> residues;
+  RawVec<uint32_t> len, v, j, rep;
+  RawVec<uint64_t> count;
+  RawVec<char> id_arena, keep_arena;
+  RawVec<uint64_t> id_off, keep_off;
   Interner reps, vs, js;
   unsigned longest = 0, shortest = ~0u;
   uint64_t total_count = 0, ignored_unknown = 0, ignored_empty = 0, lines = 0;
@@ -224,20 +224,33 @@ void parse_range(const char* b, const char* e, const ParseCtx& cx, Part& out) {
     const sv seq = has_seq ? f[cx.seqcol - 1] : sv();
     const size_t base = out.residues.size();
     bool ignore = false;
-    for (size_t i = 0; i < seq.size(); i++) {
-      const unsigned char ch = (unsigned char)seq[i];
-      const signed char m = g_map[ch];
-      if (m >= 0) {
-        out.residues.push_back((uint8_t)m);
-      } else if (ch >= 32 && ch <= 126) {
-        if (o.ignore_unknown) {
-          ignore = true;
-          out.ignored_unknown++;
-        } else {
-          return fail(ERR_CHAR_PRINTABLE, ch);
+    {  // the common case first: every symbol legal, translated in one branch-free sweep
+      out.residues.resize(base + seq.size());
+      uint8_t* const dst = out.residues.data() + base;
+      signed char bad = 0;
+      for (size_t i = 0; i < seq.size(); i++) {
+        const signed char m = g_map[(unsigned char)seq[i]];
+        dst[i] = (uint8_t)m;
+        bad |= m;
+      }
+      if (bad < 0) {  // an illegal symbol somewhere: redo the sequence symbol by symbol (db.cc:400-440)
+        out.residues.resize(base);
+        for (size_t i = 0; i < seq.size(); i++) {
+          const unsigned char ch = (unsigned char)seq[i];
+          const signed char m = g_map[ch];
+          if (m >= 0) {
+            out.residues.push_back((uint8_t)m);
+          } else if (ch >= 32 && ch <= 126) {
+            if (o.ignore_unknown) {
+              ignore = true;
+              out.ignored_unknown++;
+            } else {
+              return fail(ERR_CHAR_PRINTABLE, ch);
+            }
+          } else {
+            return fail(ERR_CHAR_OTHER, ch);
+          }
         }
-      } else {
-        return fail(ERR_CHAR_OTHER, ch);
       }
     }
     const unsigned seqlen = (unsigned)(out.residues.size() - base);
@@ -470,8 +483,12 @@ void read_airr_tsv(const char* filename, const Options& o, bool require_sequence
     const char* nl = (const char*)memchr(c, '\n', (size_t)(end - c));
     cut[t] = nl ? nl + 1 : end;
   }
+  const bool trace = getenv("COMPAIRR_B200_TRACE") != nullptr;
+  const auto t_parse0 = std::chrono::steady_clock::now();
+  auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_parse0).count(); };
   std::vector<Part> parts(n_thr);
   parallel(n_thr, [&](unsigned t) { parse_range(cut[t], cut[t + 1], cx, parts[t]); });
+  if (trace) fprintf(stderr, "[trace]   reader: %u threads parsed in %.3f s\n", n_thr, since());
   for (unsigned t = 0; t < n_thr; t++) {  // the earliest malformed line, numbered from the top of the file
     if (parts[t].err != ERR_NONE) report(parts[t], lineno + parts[t].err_line, o);
     lineno += parts[t].lines;
@@ -547,6 +564,7 @@ void read_airr_tsv(const char* filename, const Options& o, bool require_sequence
     Part().residues.swap(pt.residues);  // give the memory back early
   });
   parts.clear();
+  if (trace) fprintf(stderr, "[trace]   reader: merged at %.3f s\n", since());
   progress_end(o, "Reading sequences:");
 
   if (db.ignored_unknown) fprintf(g_log, "%lu sequences with unknown symbols ignored.\n", (unsigned long)db.ignored_unknown);

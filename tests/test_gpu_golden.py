@@ -76,3 +76,18 @@ def test_cli_multi_gpu_flag_single_device(tmp_path):
                        capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stderr
     assert out.read_text() == case["output"]
+
+
+def test_cli_write_failure_is_not_success(tmp_path):
+    """A full disk must not look like success: /dev/full accepts the open and fails
+    every flush; the command has to end with a non-zero status and say so."""
+    if not os.path.exists("/dev/full"):
+        pytest.skip("no /dev/full")
+    files = [os.path.join(GOLDEN_DIR, f) for f in ("ref_seta.tsv", "ref_setb.tsv")]
+    r = subprocess.run([CLI, "-m", "-d", "1"] + files + ["-o", "/dev/full", "-l", str(tmp_path / "log.txt")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode != 0
+    assert "Unable to write" in r.stderr
+    r = subprocess.run([CLI, "-m", "-d", "1", "-t", "1"] + files + ["-o", str(tmp_path / "o.tsv"), "-l", str(tmp_path / "log.txt")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "Threads (t):       1" in (tmp_path / "log.txt").read_text()

@@ -18,7 +18,7 @@ try:
     del a, b
     cli = "compairr_b200/bin/compairr_b200"
     env = dict(os.environ, COMPAIRR_B200_TRACE="1")
-    for run in range(3):
+    for run in range(2):
         t = time.time()
         r = subprocess.run([cli, "-m", fa, fb, "-d", "1", "-i", "-o", f"{tmp}/o.tsv", "-l", f"{tmp}/l.txt"], env=env, capture_output=True, text=True)
         print(f"--- run {run}: wall {time.time()-t:.3f} s rc={r.returncode}\n{r.stderr}", flush=True)
