@@ -26,18 +26,52 @@ struct RepStats {
   uint64_t sum_size = 0, sum_count = 0;
 };
 
-RepStats rep_stats(const SeqDb& d) {
+// Per-repertoire sizes, total counts and sums of squared counts (overlap.cc:640-657, 733-750).  The
+// reference adds (double)(c * c) in file order; here host threads add the same u64 products exactly
+// (128-bit partial sums) and, as long as a repertoire's total stays below 2^53 — every partial sum
+// of the serial loop is then exact too — the result is the same double, bit for bit.  A repertoire
+// beyond that (counts in the hundreds of millions) is summed serially, as the reference does.
+RepStats rep_stats(const SeqDb& d, int threads) {
   RepStats s;
   const size_t r = d.rep_names.size();
   s.size.assign(r, 0);
   s.count.assign(r, 0);
   s.sq_count.assign(r, 0.0);
-  for (uint64_t i = 0; i < d.n(); i++) {
-    const unsigned k = d.rep[i];
-    const uint64_t c = d.count[i];
-    s.size[k]++;
-    s.count[k] += c;
-    s.sq_count[k] += (double)(c * c);  // u64 product, then double: as overlap.cc:654
+  const uint64_t n = d.n();
+  const unsigned nt = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)std::max(threads, 1), n / (1u << 20)));
+  std::vector<std::vector<uint64_t>> size(nt, std::vector<uint64_t>(r, 0)), count(nt, std::vector<uint64_t>(r, 0));
+  std::vector<std::vector<unsigned __int128>> sq(nt, std::vector<unsigned __int128>(r, 0));
+  {
+    std::vector<std::thread> pool;
+    for (unsigned t = 0; t < nt; t++)
+      pool.emplace_back([&, t] {
+        for (uint64_t i = n * t / nt; i < n * (t + 1) / nt; i++) {
+          const unsigned k = d.rep[i];
+          const uint64_t c = d.count[i];
+          size[t][k]++;
+          count[t][k] += c;
+          sq[t][k] += (unsigned __int128)(c * c);  // u64 product, as overlap.cc:654
+        }
+      });
+    for (auto& th : pool) th.join();
+  }
+  bool exact = true;
+  for (size_t k = 0; k < r; k++) {
+    unsigned __int128 q = 0;
+    for (unsigned t = 0; t < nt; t++) {
+      s.size[k] += size[t][k];
+      s.count[k] += count[t][k];
+      q += sq[t][k];
+    }
+    if (q >= ((unsigned __int128)1 << 53)) exact = false;
+    s.sq_count[k] = (double)(uint64_t)q;
+  }
+  if (!exact) {
+    s.sq_count.assign(r, 0.0);
+    for (uint64_t i = 0; i < n; i++) {
+      const uint64_t c = d.count[i];
+      s.sq_count[d.rep[i]] += (double)(c * c);
+    }
   }
   s.order.resize(r);
   for (unsigned i = 0; i < r; i++) s.order[i] = i;
@@ -183,7 +217,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
   read_airr_tsv(o.input1, o, o.existence, o.existence || o.pairs, "1", genes, d1);
   fprintf(g_log, "\n");
   mark("set 1 read");
-  const RepStats s1 = rep_stats(d1);
+  const RepStats s1 = rep_stats(d1, host_threads(o.threads, o.threads_given));
   log_rep_table(d1, s1);
   mark("set 1 repertoire table");
   if (o.existence && d1.rep_names.size() > 1)
@@ -198,7 +232,7 @@ void overlap_command(const Options& o, FILE* outfile, FILE* pairsfile) {
     fprintf(g_log, "Set 2 is identical to set 1\n\n");
   }
   const SeqDb& d2 = two_sets ? d2s : d1;
-  const RepStats s2s = two_sets ? rep_stats(d2s) : RepStats();
+  const RepStats s2s = two_sets ? rep_stats(d2s, host_threads(o.threads, o.threads_given)) : RepStats();
   const RepStats& s2 = two_sets ? s2s : s1;
   if (two_sets) {
     if (d2.rep_names.empty()) fatal("Repertoire set missing repertoire_id.");
