@@ -177,7 +177,9 @@ __device__ __forceinline__ void accumulate_warp(const ProbeParams* __restrict__ 
 }
 
 // K4 for the warp's candidate groups (one distinct set-B sequence with its occurrence list per
-// lane): V/J compare and exact verify of the edit ONCE against the head, then score + accumulate +
+// lane): V/J compare and exact verify of the edit ONCE against the head (byte-wise; a word-wide
+// verify for sequences up to 32 residues removed 40 % of this kernel's instructions and none of its
+// time, 14.80 vs 14.83 ms at C3 geometry: the kernel waits on dependent loads, not on issue slots), then score + accumulate +
 // pair append for every occurrence (overlap.cc:189-245).  Called by the whole warp; `cand` lanes
 // hold a group.  The walk over the occurrences is warp-synchronous so that the accumulation can
 // combine lanes.
