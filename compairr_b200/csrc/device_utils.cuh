@@ -68,75 +68,6 @@ __device__ __forceinline__ uint32_t pack_var(uint32_t kind, uint32_t pos1, uint3
   return kind | (r1 << 3) | (r2 << 8) | (pos1 << 13) | (pos2 << 22);
 }
 
-// A sequence of up to 32 residues as four little-endian 64-bit words, residue 0 in the low byte of
-// word 0, zero beyond the end: aligned 64-bit loads (all issued at once: one memory round trip) and
-// funnel shifts.  Reads whole aligned words, i.e. up to 7 bytes past the sequence: residue buffers
-// are allocated with 16 bytes of slack (upload.cu).
-struct Seq32 {
-  uint64_t w[4];
-};
-__device__ __forceinline__ Seq32 load_seq32(const uint8_t* __restrict__ res, uint64_t off, uint32_t len) {
-  const uint64_t* p = reinterpret_cast<const uint64_t*>(res + (off & ~7ull));
-  const uint32_t sh = (uint32_t)(off & 7) * 8, need = ((uint32_t)(off & 7) + len + 7) >> 3;  // <= 5 words
-  uint64_t r[5];
-#pragma unroll
-  for (uint32_t k = 0; k < 5; k++) r[k] = k < need ? __ldg(p + k) : 0ull;
-  Seq32 s;
-#pragma unroll
-  for (uint32_t k = 0; k < 4; k++) {
-    const uint64_t v = sh ? (r[k] >> sh) | (r[k + 1] << (64 - sh)) : r[k];
-    const uint32_t rem = len > 8 * k ? len - 8 * k : 0;
-    s.w[k] = rem >= 8 ? v : (rem ? v & ((1ull << (rem * 8)) - 1) : 0ull);
-  }
-  return s;
-}
-// the sequence with residue q removed (everything behind it moves down one place)
-__device__ __forceinline__ Seq32 remove_residue(const Seq32& x, uint32_t q) {
-  Seq32 y;
-  const uint32_t wq = q >> 3;
-  const uint64_t low = (1ull << ((q & 7) * 8)) - 1;  // the residues of word wq in front of q
-#pragma unroll
-  for (uint32_t k = 0; k < 4; k++) {
-    const uint64_t shifted = (x.w[k] >> 8) | (k < 3 ? x.w[k + 1] << 56 : 0ull);
-    y.w[k] = k < wq ? x.w[k] : (k == wq ? (x.w[k] & low) | (shifted & ~low) : shifted);
-  }
-  return y;
-}
-__device__ __forceinline__ uint32_t residue_at(const Seq32& x, uint32_t q) {
-  const uint32_t k = q >> 3;
-  const uint64_t w = k == 0 ? x.w[0] : k == 1 ? x.w[1] : k == 2 ? x.w[2] : x.w[3];
-  return (uint32_t)(w >> ((q & 7) * 8)) & 0xffu;
-}
-// x == y except (possibly) at the residues q1 and q2 (pass q >= 32 for "none")
-__device__ __forceinline__ bool equal_except(const Seq32& x, const Seq32& y, uint32_t q1, uint32_t q2) {
-  uint64_t diff = 0;
-#pragma unroll
-  for (uint32_t k = 0; k < 4; k++) {
-    uint64_t m = ~0ull;
-    if ((q1 >> 3) == k) m &= ~(0xffull << ((q1 & 7) * 8));
-    if ((q2 >> 3) == k) m &= ~(0xffull << ((q2 & 7) * 8));
-    diff |= (x.w[k] ^ y.w[k]) & m;
-  }
-  return diff == 0;
-}
-// check_variant (variants.cc:166-240) for sequences of at most 32 residues, on whole words: the
-// byte loops of verify_variant() (common.cuh) were 40 % of the table kernel's instructions and a
-// chain of dependent loads each.  Same answers (tests: every parity test goes through here).
-__device__ __forceinline__ bool verify_variant32(const uint8_t* __restrict__ res_a, uint64_t off_a, uint32_t slen,
-                                                 const uint8_t* __restrict__ res_b, uint64_t off_b, uint32_t hlen,
-                                                 uint32_t kind, uint32_t pos1, uint32_t r1, uint32_t pos2, uint32_t r2) {
-  const uint32_t want = kind == VK_DELETION ? slen - 1 : kind == VK_INSERTION ? slen + 1 : slen;
-  if (hlen != want || kind > VK_SUB_SUB) return false;
-  const Seq32 s = load_seq32(res_a, off_a, slen), h = load_seq32(res_b, off_b, hlen);
-  switch (kind) {
-    case VK_IDENTICAL: return equal_except(s, h, 32, 32);
-    case VK_SUBSTITUTION: return residue_at(h, pos1) == r1 && equal_except(s, h, pos1, 32);
-    case VK_DELETION: return equal_except(remove_residue(s, pos1), h, 32, 32);
-    case VK_INSERTION: return residue_at(h, pos1) == r1 && equal_except(s, remove_residue(h, pos1), 32, 32);
-    default: return residue_at(h, pos1) == r1 && residue_at(h, pos2) == r2 && equal_except(s, h, pos1, pos2);
-  }
-}
-
 // K4 accumulate (matrix[R2 * i + j] += s, overlap.cc:218-228), called by the whole warp; `ok` lanes
 // carry a match.  Two forms:
 //   tile == nullptr   one fire-and-forget RED.F64 per match into the global matrix.  At the match
@@ -195,9 +126,7 @@ __device__ __forceinline__ uint32_t verify_and_record(const ProbeParams* __restr
     if (ok) {
       const uint32_t kind = var & 7, r1 = (var >> 3) & 31, r2 = (var >> 8) & 31;
       const uint32_t pos1 = (var >> 13) & 511, pos2 = (var >> 22) & 511;
-      ok = (sm.len <= 32 && hm.len <= 32)
-               ? verify_variant32(P->a.res, sm.off, sm.len, P->b.res, hm.off, hm.len, kind, pos1, r1, pos2, r2)
-               : verify_variant(P->a.res + sm.off, sm.len, P->b.res + hm.off, hm.len, kind, pos1, r1, pos2, r2);
+      ok = verify_variant(P->a.res + sm.off, sm.len, P->b.res + hm.off, hm.len, kind, pos1, r1, pos2, r2);
     }
   }
   uint32_t found = 0;
