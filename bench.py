@@ -559,7 +559,7 @@ def run_ours(a):
         "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
         "config": {"workload": workload_name(a), "set_b_sequences": n_b, "set_a_sequences_per_gpu": n_a,
-                   "probes_per_step": probes_total, "l2": "inputs larger than L2 (filters 2 x %.0f MiB, table %.0f MiB); no flush"
+                   "probes_per_step": probes_total, "l2": "inputs larger than L2 (class filters 4 x %.0f MiB, table %.0f MiB); no flush"
                    % (run_stats["bloom_bytes"] / 2**20 if run_stats["bloom_bytes"] else build_stats_launch["bloom_bytes"] / 2**20,
                       build_stats_launch["table_slots"] * 16 / 2**20),
                    "parallelism": f"set A sharded over {world} GPU(s); set B on every GPU (e2e: 1/{world} uploaded per rank, NVLink all-gather); "
@@ -567,12 +567,12 @@ def run_ours(a):
                    "step": "hash B + build table/filters + dups + hash A + enumeration and table kernels (+ all-reduce)",
                    "generate_s": round(t_gen, 1), "matrix_checksum": checksum, "e2e_matrix_checksum": e2e_checksum},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "variant1_kernel<20,true> + table_kernel", "kernel_ms": kern,
+                     "traffic": traffic, "kernel": "enum1_kernel<20,indels,32> + table_kernel", "kernel_ms": kern,
                      "bytes_per_probe": 8, "peak_source": peak_src,
-                     "note": "8 B/probe is the algorithmic figure (one filter word per variant, SURVEY 8d). The parity "
-                             "filters let all candidates of a slot share one word, so the kernels move far fewer "
-                             "bytes than that (traffic = measured DRAM bytes per step's launches) and are instruction-bound; "
-                             "the fraction says how fast the algorithmic work is done relative to an HBM stream",
+                     "note": "8 B/probe is the algorithmic figure (one filter word per variant, SURVEY 8d). The class "
+                             "filters let all candidates of a slot share one word, so the kernels move fewer bytes "
+                             "than that (traffic = measured DRAM bytes of the enumeration launches of a step) and are bound "
+                             "by the ALU pipe; the fraction says how fast the algorithmic work is done relative to an HBM stream",
                      "dram_bytes_per_probe": (traffic / probes_rank) if traffic else None, "traffic_note": traffic_note},
         "e2e": {"value": e2e_value, "unit": "probes/s", "h2d_bytes_per_step": h2d_total, "d2h_bytes_per_step": d2h * world,
                 "ms_per_step": ms_e2e / a.steps, "ms_gather_b_rank0": e2e_stats.get("ms_gather_b", 0.0)},

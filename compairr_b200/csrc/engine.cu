@@ -319,9 +319,9 @@ static uint32_t blocks_for_bits(unsigned __int128 bits) {
   return (uint32_t)nb;
 }
 
-// Table + the two parity filters (common.cuh) sized for n keys: bloom_bits_per_key bits per key in
-// EACH filter.  Their size no longer has to fit L2: a warp's lookups fall into one or two words per
-// step, not 32 random ones, so the filters are read a few dozen sectors per seed.
+// Table + the four class filters (common.cuh) sized for n keys: bloom_bits_per_key bits per key in
+// EACH filter.  Their size does not have to fit L2: a filter word is fetched once per slot, not once
+// per candidate, so the filters are read a few dozen sectors per seed.
 int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
   BuiltTable t;
   t.slots = 8;

@@ -40,7 +40,7 @@ cudaError_t cb_dfree(void* p);
 struct BuiltTable {
   cb::Slot* table = nullptr;
   uint64_t slots = 0;
-  unsigned long long* bloom = nullptr;  // parity filters E | O back to back, 2 * blocks words
+  unsigned long long* bloom = nullptr;  // the four class filters back to back, CB_CLASSES * blocks words
   uint32_t blocks = 0;                  // 64-bit words per filter
   void release() {
     cb_dfree(table);
@@ -73,7 +73,7 @@ struct cb_ctx {
   bool b_owned = false;
   cb::Slot* d_table = nullptr;
   uint64_t slots = 0;
-  unsigned long long* d_bloom = nullptr;   // parity filters E | O (2 * bloom_blocks words)
+  unsigned long long* d_bloom = nullptr;   // the four class filters (CB_CLASSES * bloom_blocks words)
   uint32_t bloom_blocks = 0;
   uint64_t dups_b = 0;
 
