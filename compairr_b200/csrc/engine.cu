@@ -322,12 +322,12 @@ static uint32_t blocks_for_bits(unsigned __int128 bits) {
 // Table + the four class filters (common.cuh) sized for n keys: bloom_bits_per_key bits per key in
 // EACH filter.  Their size does not have to fit L2: a filter word is fetched once per slot, not once
 // per candidate, so the filters are read a few dozen sectors per seed.
-int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
+int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out, bool clear_table) {
   BuiltTable t;
   t.slots = 8;
   while (t.slots * c->cfg.table_load_pct < n * 100) t.slots <<= 1;
   const unsigned __int128 want_bits = (unsigned __int128)n * c->cfg.bloom_bits_per_key_x16 / 16;
-  t.blocks = with_bloom ? blocks_for_bits(want_bits) : 16;  // the build kernel always sets the filters; scratch ones if unused
+  t.blocks = with_bloom ? blocks_for_bits(want_bits) : 0;  // no filters: a table for duplicate counting / -z only
   cudaError_t e = cudaSuccess;
   if (with_bloom && c->d_table && c->slots == t.slots && c->bloom_blocks == t.blocks) {
     // rebuilding a set-B structure of the same geometry: clear and refill the buffers in place
@@ -340,10 +340,10 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
     c->bloom_blocks = 0;
   } else {
     e = cb_dmalloc(&t.table, t.slots * sizeof(Slot));
-    if (e == cudaSuccess) e = cb_dmalloc(&t.bloom, (size_t)t.blocks * 8 * CB_CLASSES);
+    if (e == cudaSuccess && t.blocks) e = cb_dmalloc(&t.bloom, (size_t)t.blocks * 8 * CB_CLASSES);
   }
-  if (e == cudaSuccess) e = cudaMemsetAsync(t.bloom, 0, (size_t)t.blocks * 8 * CB_CLASSES, c->stream);
-  if (e == cudaSuccess) {
+  if (e == cudaSuccess && t.blocks) e = cudaMemsetAsync(t.bloom, 0, (size_t)t.blocks * 8 * CB_CLASSES, c->stream);
+  if (e == cudaSuccess && clear_table) {
     launch_table_clear(t.table, t.slots, c->stream);
     e = cudaGetLastError();
   }
@@ -362,23 +362,41 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out) {
 // every slot store and every filter update is a random 32-byte sector (measured on B200 at 10^8
 // keys / 4.3 GB: 21 G CAS/s, 22 G stores/s, 49 G RED/s, together 11.4 ms; the same operations in
 // address order 2.4 ms — tools/bench_atomics.cu).  So a batch that is a sizeable part of the
-// table is first sorted by the hash bits that pick the home slot down to segments of 16 slots —
-// three 8-bit radix passes over (h * CB_HOME_MUL, index) pairs, 0.85 ms each at 10^8 — and the
-// build kernel then sweeps the table in address order.  The class-filter updates of a key are
-// picked by other functions of the hash and stay random REDs (2 ms each at 10^8).  Small batches (the chunks of the upload pipeline, which hide behind the PCIe copy
-// anyway) keep the direct path.
-void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n) {
+// table is first sorted by the hash bits that pick the home slot — 8-bit radix passes over
+// (h * CB_HOME_MUL, index) pairs, 0.85 ms each at 10^8 — and then either
+//   - a whole set into an empty table: built tile by tile in shared memory and streamed out, the
+//     table written exactly once and never cleared or read (build_tile_kernel), or
+//   - a batch into a table that already holds keys: the build kernel sweeps the table in address
+//     order, keys sorted down to segments of 16 slots.
+// The class filters are indexed by other functions of the hash: their own L2-blocked passes
+// (launch_filters).  Small batches (the chunks of the upload pipeline, which hide behind the PCIe
+// copy anyway) keep the direct path.
+// Does a set of n keys in a table of `slots` slots take the sorted (partitioned) build?
+static bool sorted_build(const cb_ctx* c, uint64_t slots, uint64_t n) {
+  return !(c->cfg.flags & CB_FLAG_NO_PARTITION) && slots * sizeof(Slot) >= (256ull << 20) && n >= (1ull << 22) &&
+         n * 64 >= slots && n < 0xffffffffull;
+}
+bool cb_tiled_build(const cb_ctx* c, uint64_t slots, uint64_t n) {
+  return sorted_build(c, slots, n) && !(c->cfg.flags & CB_FLAG_NO_TILED_BUILD);
+}
+
+// whole: the table is EMPTY BUT NOT CLEARED (cb_table_alloc(..., clear_table = false)) and this batch
+// is everything it will hold — the tiled build (kernels.cu build_tile_kernel) writes every slot once,
+// keys sorted by their tile only (two radix passes at 10^8 instead of three); if its scratch buffers
+// cannot be had the table is cleared here and filled the direct way.
+void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n, bool whole) {
   s->links_dirty = true;
-  const uint64_t table_bytes = t.slots * sizeof(Slot);
   uint64_t *key_in = nullptr, *part_hash = nullptr;
-  uint32_t *iota = nullptr, *part_idx = nullptr;
+  uint32_t *iota = nullptr, *part_idx = nullptr, *tile_first = nullptr;
   void* temp = nullptr;
   c->insert_launches = n ? 1 : 0;
-  if (!(c->cfg.flags & CB_FLAG_NO_PARTITION) && table_bytes >= (256ull << 20) && n >= (1ull << 22) &&
-      n * 64 >= t.slots && n < 0xffffffffull) {
-    int tbits = 0;
-    while ((1ull << tbits) < t.slots) tbits++;
-    const int pbits = std::max(8, (tbits - 4) / 8 * 8);  // whole radix passes
+  bool filters_done = false, filters_forked = false;
+  int tbits = 0;
+  while ((1ull << tbits) < t.slots) tbits++;
+  const bool tiled = whole && cb_tiled_build(c, t.slots, n);
+  if (sorted_build(c, t.slots, n)) {
+    // tiled: down to tiles of BUILD_TILE_SLOTS; swept: down to segments of 16 slots, whole radix passes
+    const int pbits = tiled ? tbits - BUILD_TILE_BITS : std::max(8, (tbits - 4) / 8 * 8);
     size_t temp_bytes = 0;
     cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, temp_bytes, key_in, part_hash, iota, part_idx, n,
                                                     CB_PARTITION_TOP_BIT - pbits, CB_PARTITION_TOP_BIT, c->stream);
@@ -387,12 +405,32 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
     if (e == cudaSuccess) e = cb_dmalloc(&iota, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cb_dmalloc(&part_idx, n * sizeof(uint32_t));
     if (e == cudaSuccess) e = cb_dmalloc(&temp, temp_bytes ? temp_bytes : 1);
+    if (e == cudaSuccess && tiled) e = cb_dmalloc(&tile_first, ((t.slots >> BUILD_TILE_BITS) + 1) * sizeof(uint32_t));
+    if (e == cudaSuccess && t.bloom && !(c->cfg.flags & CB_FLAG_FILTERS_IN_BUILD)) {
+      // the filters in their own L2-blocked passes, on the side stream: compute- and L2-bound, they
+      // run beside the sort and the table build, which wait on DRAM
+      // (COMPAIRR_B200_FILTER_OVERLAP=0: on the main stream, one after the other; measurements)
+      static const bool beside = [] {
+        const char* v = getenv("COMPAIRR_B200_FILTER_OVERLAP");
+        return !(v && v[0] == '0');
+      }();
+      cudaStream_t fs = c->stream;
+      if (beside && cudaEventRecord(c->ev[8], c->stream) == cudaSuccess &&
+          cudaStreamWaitEvent(c->copy_stream, c->ev[8], 0) == cudaSuccess)
+        fs = c->copy_stream;
+      c->insert_launches += launch_filters(s->d_hash + first, n, t.bloom, t.blocks, c->sm_count, fs);
+      if (fs != c->stream) {
+        cudaEventRecord(c->ev[9], fs);
+        filters_forked = true;
+      }
+      filters_done = true;
+    }
     if (e == cudaSuccess) {
       launch_partition_keys(s->d_hash + first, n, key_in, iota, c->stream);  // h * CB_HOME_MUL: top bits = home slot
       e = cub::DeviceRadixSort::SortPairs(temp, temp_bytes, key_in, part_hash, iota, part_idx, n,
                                           CB_PARTITION_TOP_BIT - pbits, CB_PARTITION_TOP_BIT, c->stream);
     }
-    if (e == cudaSuccess) c->insert_launches += 1 + 2 + pbits / 8;  // keys, histogram, scan, one sweep per digit
+    if (e == cudaSuccess) c->insert_launches += 1 + 2 + (pbits + 7) / 8;  // keys, histogram, scan, one sweep per digit
     if (e != cudaSuccess) {  // no memory for the sort buffers: the direct path still works
       (void)cudaGetLastError();
       cb_dfree(part_hash);
@@ -401,26 +439,36 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
       part_idx = nullptr;
     }
   }
-  // a sorted (large) batch: filters in their own L2-blocked passes, the build kernel sweeps the table only
-  unsigned long long* bloom_in_build = t.bloom;
-  if (part_hash && !(c->cfg.flags & CB_FLAG_FILTERS_IN_BUILD)) {
-    c->insert_launches += launch_filters(s->d_hash + first, n, t.bloom, t.blocks, c->sm_count, c->stream);
-    bloom_in_build = nullptr;
+  // a sorted (large) batch: the build kernels write the table only
+  unsigned long long* bloom_in_build = filters_done ? nullptr : t.bloom;  // nullptr also for a table without filters
+  if (tiled && part_hash && !bloom_in_build) {
+    // iota (the sort's input values) is dead: it holds the spill list
+    cudaMemsetAsync(c->d_counters + CTR_SPILL, 0, sizeof(unsigned long long), c->stream);
+    c->insert_launches += launch_build_tiled(s->d_meta, s->d_res, part_hash, part_idx, first, n, c->cfg.ignore_genes != 0,
+                                             t.table, (uint32_t)tbits, tile_first, iota, c->d_counters, c->sm_count,
+                                             c->stream) - 1;
+  } else {
+    if (whole) {
+      launch_table_clear(t.table, t.slots, c->stream);
+      c->insert_launches++;
+    }
+    launch_build(s->d_meta, s->d_res, s->d_hash, part_hash, part_idx, first, n, c->cfg.ignore_genes != 0, t.table,
+                 t.slots - 1, bloom_in_build, t.blocks, c->stream);
   }
-  launch_build(s->d_meta, s->d_res, s->d_hash, part_hash, part_idx, first, n, c->cfg.ignore_genes != 0, t.table,
-               t.slots - 1, bloom_in_build, t.blocks, c->stream);
+  if (filters_forked) cudaStreamWaitEvent(c->stream, c->ev[9], 0);
   cb_dfree(key_in);
   cb_dfree(part_hash);
   cb_dfree(iota);
   cb_dfree(part_idx);
+  cb_dfree(tile_first);
   cb_dfree(temp);
 }
 
 static int build_table_for(cb_ctx* c, cb_dset* s, bool with_bloom, BuiltTable* out) {
-  int rc = cb_table_alloc(c, s->n, with_bloom, out);
+  int rc = cb_table_alloc(c, s->n, with_bloom, out, false);  // cb_table_insert(whole) clears it if it has to
   if (rc) return rc;
   if (s->links_dirty) launch_reset_next(s->d_meta, s->n, c->stream);  // the set has been inserted before
-  cb_table_insert(c, *out, s, 0, s->n);
+  cb_table_insert(c, *out, s, 0, s->n, true);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     out->release();
@@ -480,7 +528,7 @@ extern "C" int cb_build_b(cb_ctx* c, cb_dset* b) {
   if (rc) return rc;
   if (c->d_table) {
     cudaEventElapsedTime(&c->stats.ms_build_b, c->ev[0], c->ev[6]);
-    c->stats.kernel_launches = b->n ? 2 + (reset_links ? 1 : 0) + c->insert_launches : 1;  // clear, [reset links,] [sort, filters,] insert, duplicates
+    c->stats.kernel_launches = b->n ? 1 + (reset_links ? 1 : 0) + c->insert_launches : 1;  // [reset links,] [clear,] [sort, filters,] insert, duplicates
   }
   return CB_OK;
 }

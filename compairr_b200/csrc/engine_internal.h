@@ -60,7 +60,7 @@ struct cb_ctx {
   cudaMemPool_t pool = nullptr;        // the context's own stream-ordered memory pool
   void* pin[2] = {nullptr, nullptr};   // pinned pass-through buffers of the upload pipeline (pageable callers)
   size_t pin_bytes[2] = {0, 0};
-  cudaEvent_t ev[8]{};
+  cudaEvent_t ev[10]{};  // [8], [9]: fork / join of the filter passes running beside the table build
   std::string err;
 
   uint64_t* d_ztab = nullptr;
@@ -113,8 +113,8 @@ cb::DeviceSetView cb_view_of(const cb_dset* s);
 // engine.cu
 int cb_bind_device(cb_ctx* c);
 int cb_ensure_ztab(cb_ctx* c, uint32_t rows);
-int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out);
-void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n);
+int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out, bool clear_table = true);
+void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first, uint64_t n, bool whole = false);
 int cb_adopt_table(cb_ctx* c, cb_dset* b, BuiltTable& t, bool owned);  // sets ctx fields, counts dups
 void cb_free_dset(cb_dset* s);
 

@@ -14,6 +14,7 @@
 // has each kernel's bound).
 #include <stdio.h>
 #include <stdlib.h>
+#include <algorithm>
 
 #include "kernels.cuh"
 #include "device_utils.cuh"
@@ -175,7 +176,11 @@ __global__ void __launch_bounds__(256)
 build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __restrict__ hash,
              const uint64_t* __restrict__ part_hash, const uint32_t* __restrict__ part_idx,
              uint64_t first, uint64_t n, bool ignore_genes, Slot* table, uint64_t mask,
-             unsigned long long* bloom, uint32_t bloom_blocks) {
+             unsigned long long* bloom, uint32_t bloom_blocks, const uint32_t* __restrict__ sel,
+             const unsigned long long* sel_n) {
+  // sel / sel_n: insert only the sorted positions sel[0 .. *sel_n) — the keys the tiled build
+  // (build_tile_kernel) could not place inside their tile.
+  if (sel) n = *sel_n < n ? *sel_n : n;
   // part_hash/part_idx: the same keys sorted by their top hash bits (position t holds sequence
   // first + part_idx[t]); the grid then sweeps the table and the filters in address order.
   // Both loops have warp-uniform trip counts and the probe loop is voted: lanes that finish early
@@ -185,8 +190,9 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
   const uint64_t stride = (uint64_t)gridDim.x * blockDim.x;
   const uint64_t rounds = (n + stride - 1) / stride;
   for (uint64_t r = 0; r < rounds; r++) {
-    const uint64_t t = r * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
-    bool walking = t < n;
+    const uint64_t k = r * stride + blockIdx.x * (uint64_t)blockDim.x + threadIdx.x;
+    bool walking = k < n;
+    const uint64_t t = walking && sel ? sel[k] : k;
     const uint64_t i = walking ? first + (part_idx ? part_idx[t] : t) : 0;
     const uint64_t h = walking ? (part_hash ? part_hash[t] * CB_HOME_INV : hash[i]) : 0;  // sorted keys are h * CB_HOME_MUL
     const uint32_t tag = slot_tag(h);
@@ -248,7 +254,129 @@ void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const 
   if (n == 0) return;
   const uint64_t blocks = (n + 255) / 256;
   build_kernel<<<(unsigned)(blocks < 148 * 16 ? blocks : 148 * 16), 256, 0, st>>>(
-      meta, res, hash, part_hash, part_idx, first, n, ignore_genes, table, mask, bloom, bloom_blocks);
+      meta, res, hash, part_hash, part_idx, first, n, ignore_genes, table, mask, bloom, bloom_blocks, nullptr, nullptr);
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2, a whole set into an EMPTY table: the tiled build.  The keys arrive sorted by the tile
+// (BUILD_TILE_SLOTS consecutive slots) their home slot lies in.  One CTA builds one tile in shared
+// memory — the same insert as build_kernel, CAS and occurrence lists on shared-memory words — and
+// streams it out, empty slots included: the table is written once, front to back, and is neither
+// cleared beforehand nor read.  A key whose probe run leaves its tile goes to the spill list and is
+// inserted by build_kernel (sel) once every tile is in memory; the linear-probing invariant holds —
+// every slot from its home to the end of the tile was full when it left.
+// ---------------------------------------------------------------------------------------------
+
+__global__ void __launch_bounds__(256) tile_bounds_kernel(const uint64_t* __restrict__ key, uint64_t n, uint32_t shift,
+                                                          uint32_t ntiles, uint32_t* __restrict__ tile_first) {
+  // tile_first[g] = first sorted position whose key belongs to tile g or a later one; [ntiles] = n
+  for (uint32_t g = blockIdx.x * blockDim.x + threadIdx.x; g <= ntiles; g += gridDim.x * blockDim.x) {
+    uint64_t lo = g == ntiles ? n : 0, hi = n;
+    const uint64_t want = (uint64_t)g << shift;
+    while (lo < hi) {
+      const uint64_t mid = (lo + hi) >> 1;
+      if (key[mid] < want) lo = mid + 1; else hi = mid;
+    }
+    tile_first[g] = (uint32_t)lo;
+  }
+}
+
+// Out of line: the tile kernel's probe loop then fits the registers of three 512-thread CTAs per SM.
+__device__ __noinline__ bool same_sequence(const SeqRec* meta, const uint8_t* __restrict__ res, uint64_t i, uint32_t j,
+                                           bool ignore_genes) {
+  const SeqMeta me = ld_meta_plain(meta + i), o = ld_meta_plain(meta + j);
+  return o.len == me.len && (ignore_genes || (o.v == me.v && o.j == me.j)) && seq_equal(res, me.off, o.off, me.len);
+}
+
+__global__ void __launch_bounds__(BUILD_TILE_THREADS, CB_TILE_CTAS)
+build_tile_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __restrict__ part_key,
+                  const uint32_t* __restrict__ part_idx, const uint32_t* __restrict__ tile_first, uint64_t first,
+                  bool ignore_genes, Slot* table, uint32_t tbits, uint32_t ntiles, uint32_t* spill,
+                  unsigned long long* counters) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  Slot* tile = reinterpret_cast<Slot*>(smem_raw);
+  const ulonglong2 empty = make_ulonglong2(0ull, SLOT_EMPTY);
+  // The key a thread inserts next and the bounds of the CTA's next tile are loaded one step ahead:
+  // three dependent DRAM round trips (bounds, key, the sequences of a duplicate) per step otherwise.
+  uint32_t g = blockIdx.x;
+  uint32_t t0 = g < ntiles ? tile_first[g] : 0, t1 = g < ntiles ? tile_first[g + 1] : 0;
+  for (; g < ntiles; g += gridDim.x) {
+    uint32_t t = t0 + threadIdx.x;
+    uint64_t key_n = t < t1 ? __ldcs(part_key + t) : 0;  // h * CB_HOME_MUL: its top bits are the home slot
+    uint32_t idx_n = t < t1 ? __ldcs(part_idx + t) : 0;
+    const uint32_t g_n = g + gridDim.x;
+    const uint32_t t0_n = g_n < ntiles ? tile_first[g_n] : 0, t1_n = g_n < ntiles ? tile_first[g_n + 1] : 0;
+    for (uint32_t k = threadIdx.x; k < BUILD_TILE_SLOTS; k += BUILD_TILE_THREADS) reinterpret_cast<ulonglong2*>(tile)[k] = empty;
+    __syncthreads();
+    const uint32_t rounds = (t1 - t0 + BUILD_TILE_THREADS - 1) / BUILD_TILE_THREADS;
+    for (uint32_t r = 0; r < rounds; r++, t += BUILD_TILE_THREADS) {  // warp-uniform trip counts and a voted probe loop, as in build_kernel
+      bool walking = t < t1;
+      const uint64_t key = key_n;
+      const uint64_t i = first + idx_n;
+      if (t + BUILD_TILE_THREADS < t1) {
+        key_n = __ldcs(part_key + t + BUILD_TILE_THREADS);
+        idx_n = __ldcs(part_idx + t + BUILD_TILE_THREADS);
+      }
+      const uint64_t h = key * CB_HOME_INV;
+      const uint32_t tag = slot_tag(h);
+      const unsigned long long tagged = ((unsigned long long)tag << 32) | i;
+      uint32_t slot = (uint32_t)(key >> (64 - tbits)) & (BUILD_TILE_SLOTS - 1);
+      while (__any_sync(FULL, walking)) {
+        if (walking) {
+          if (slot >= BUILD_TILE_SLOTS) {  // ran off the tile
+            spill[atomicAdd(counters + CTR_SPILL, 1ull)] = t;
+            walking = false;
+          } else {
+            unsigned long long* idxp = reinterpret_cast<unsigned long long*>(&tile[slot].idx);
+            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(idxp);
+            if (cur == SLOT_EMPTY) {
+              cur = atomicCAS(idxp, SLOT_EMPTY, tagged);
+              if (cur == SLOT_EMPTY) {
+                tile[slot].hash = h;
+                walking = false;
+              }
+            }
+            if (walking && (uint32_t)(cur >> 32) == tag &&  // same hash tag: compare the sequences
+                same_sequence(meta, res, i, (uint32_t)cur, ignore_genes)) {
+              const unsigned long long old = atomicExch(idxp, tagged);
+              meta[i].next = (uint32_t)old;
+              walking = false;
+            }
+            slot++;
+          }
+        }
+      }
+    }
+    __syncthreads();
+    ulonglong2* out = reinterpret_cast<ulonglong2*>(table + (uint64_t)g * BUILD_TILE_SLOTS);
+    for (uint32_t k = threadIdx.x; k < BUILD_TILE_SLOTS; k += BUILD_TILE_THREADS)
+      __stcs(out + k, reinterpret_cast<const ulonglong2*>(tile)[k]);  // streamed: not to push the filter words out of L2
+    __syncthreads();
+    t0 = t0_n;
+    t1 = t1_n;
+  }
+}
+
+// part_key sorted on its top (tbits - BUILD_TILE_BITS) bits at least.  tile_first: ntiles + 1 words,
+// spill: n words (both scratch).  counters[CTR_SPILL] must be zero on entry.
+int launch_build_tiled(SeqRec* meta, const uint8_t* res, const uint64_t* part_key, const uint32_t* part_idx,
+                       uint64_t first, uint64_t n, bool ignore_genes, Slot* table, uint32_t tbits, uint32_t* tile_first,
+                       uint32_t* spill, unsigned long long* counters, int sm_count, cudaStream_t st) {
+  const uint32_t ntiles = 1u << (tbits - BUILD_TILE_BITS);
+  static bool attr_set = false;
+  const int smem = (int)(BUILD_TILE_SLOTS * sizeof(Slot));
+  if (!attr_set) {
+    cudaFuncSetAttribute(build_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr_set = true;
+  }
+  tile_bounds_kernel<<<(ntiles + 256) / 256, 256, 0, st>>>(part_key, n, 64 - (tbits - BUILD_TILE_BITS), ntiles, tile_first);
+  const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sm_count * CB_TILE_CTAS);
+  build_tile_kernel<<<grid, BUILD_TILE_THREADS, smem, st>>>(meta, res, part_key, part_idx, tile_first, first, ignore_genes,
+                                                           table, tbits, ntiles, spill, counters);
+  // the spilled keys (a fraction of a percent), by the direct insert
+  build_kernel<<<(unsigned)sm_count * 2, 256, 0, st>>>(meta, res, nullptr, part_key, part_idx, first, n, ignore_genes, table,
+                                                       (1ull << tbits) - 1, nullptr, 0, spill, counters + CTR_SPILL);
+  return 3;
 }
 
 // The class filters of a large set, built apart from the table: one launch per (filter, range of its
@@ -257,13 +385,25 @@ void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const 
 // REDs spread over four filters of 190 MiB each, interleaved with the table sweep, were DRAM
 // sector read-modify-writes (measured inside build_kernel: +4 ms per filter at 10^8 keys).
 // Duplicate keys set the same bits again: harmless.
+template <int U>
 __global__ void __launch_bounds__(256)
 filter_kernel(const uint64_t* __restrict__ hash, uint64_t n, unsigned long long* bloom, uint32_t bloom_blocks,
               uint32_t cls, uint32_t w_lo, uint32_t w_hi) {
-  for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-    const uint64_t h = hash[i];
-    const uint32_t w = mulhi32(blind_field(h, cls), bloom_blocks);
-    if (w >= w_lo && w < w_hi) atomicOr(bloom + (uint64_t)cls * bloom_blocks + w, pfilter_pattern(h, cls));
+  // U independent streaming loads in flight per thread (evict-first: the hashes pass through L2
+  // once, the word range stays)
+  for (uint64_t base = (uint64_t)blockIdx.x * (256 * U); base < n; base += (uint64_t)gridDim.x * (256 * U)) {
+    uint64_t h[U];
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const uint64_t i = base + (uint64_t)k * 256 + threadIdx.x;
+      h[k] = i < n ? __ldcs(hash + i) : 0ull;
+    }
+#pragma unroll
+    for (int k = 0; k < U; k++) {
+      const uint32_t w = mulhi32(blind_field(h[k], cls), bloom_blocks);
+      if (w >= w_lo && w < w_hi && base + (uint64_t)k * 256 + threadIdx.x < n)
+        atomicOr(bloom + (uint64_t)cls * bloom_blocks + w, pfilter_pattern(h[k], cls));
+    }
   }
 }
 
@@ -281,12 +421,17 @@ int launch_filters(const uint64_t* hash, uint64_t n, unsigned long long* bloom, 
   uint32_t parts = (uint32_t)((bytes + (part_mib << 20) - 1) / (part_mib << 20));
   if (parts < 1) parts = 1;
   if (parts > 16) parts = 16;
-  const uint64_t blocks = (n + 255) / 256;
+  static const int unroll = [] {  // COMPAIRR_B200_FILTER_UNROLL=1: one key per thread per trip (measurements)
+    const char* e = getenv("COMPAIRR_B200_FILTER_UNROLL");
+    return e && atoi(e) == 1 ? 1 : 4;
+  }();
+  const uint64_t blocks = (n + 256 * unroll - 1) / (256 * unroll);
   const unsigned grid = (unsigned)(blocks < (uint64_t)sm_count * 8 ? blocks : (uint64_t)sm_count * 8);
   for (uint32_t cls = 0; cls < CB_CLASSES; cls++)
     for (uint32_t k = 0; k < parts; k++) {
       const uint32_t lo = (uint32_t)((uint64_t)bloom_blocks * k / parts), hi = (uint32_t)((uint64_t)bloom_blocks * (k + 1) / parts);
-      filter_kernel<<<grid, 256, 0, st>>>(hash, n, bloom, bloom_blocks, cls, lo, hi);
+      if (unroll == 1) filter_kernel<1><<<grid, 256, 0, st>>>(hash, n, bloom, bloom_blocks, cls, lo, hi);
+      else filter_kernel<4><<<grid, 256, 0, st>>>(hash, n, bloom, bloom_blocks, cls, lo, hi);
     }
   return (int)(CB_CLASSES * parts);
 }

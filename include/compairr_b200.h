@@ -94,6 +94,8 @@ typedef struct cb_config {
 #define CB_FLAG_NO_PARTITION 8u   /* table build in input order, no radix sort by home slot (A/B testing) */
 #define CB_FLAG_FILTERS_IN_BUILD 32u /* large builds: filter bits set by the table-build kernel instead of */
                                     /* the L2-blocked filter passes (A/B testing)                          */
+#define CB_FLAG_NO_TILED_BUILD 64u /* large builds: the sorted sweep over a cleared table instead of the */
+                                   /* tiled shared-memory build (A/B testing)                            */
 #define CB_FLAG_GENERIC_KERNEL 16u /* d = 1, 2: every seed through the any-length enumeration kernel  */
                                    /* (otherwise only seeds longer than 94 residues; A/B testing)     */
 

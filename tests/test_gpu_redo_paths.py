@@ -7,14 +7,15 @@ the CPU oracle finishes in seconds (reference semantics: src/overlap.cc:168-251 
   * pair-buffer overflow -> second pass into an exact-size buffer (engine.cu cb_run), forced with
     cb_config.pairs_capacity
   * radix-partitioned table build (engine.cu cb_table_insert: table >= 256 MiB, >= 2^22 keys) — the
-    build every C3-sized bench step takes
+    build every C3-sized bench step takes: tiles built in shared memory (kernels.cu
+    build_tile_kernel), against the swept (flags 64) and the direct (flags 8) builds
   * the BASELINE.json config shapes C4 (-d 2 -g -s min) and C5 (-x -n -d 2 -p --no-matrix, and the
     d = 3 tensor-core path with (length, V, J) buckets)
 """
 import numpy as np
 import pytest
 
-from compairr_b200 import Engine, OverlapOptions, SeqSet, cluster, overlap, synth
+from compairr_b200 import Engine, OverlapOptions, SeqSet, cluster, dedup, overlap, synth
 from oracle import oracle as orc
 
 pytestmark = pytest.mark.gpu
@@ -126,19 +127,67 @@ def test_partitioned_build_vs_oracle(partition_sized, kw):
         da = eng.upload(a)
         eng.run(da)
         m, run = eng.matrix(), eng.stats()
-        # the same set built WITHOUT the partition sort gives the same table contents
-        with Engine(OverlapOptions(flags=8, **kw), n_reps_a=a.n_reps) as eng2:
-            db2 = eng2.upload(b)
-            eng2.build_b(db2)
-            assert eng2.stats()["kernel_launches"] < st["kernel_launches"]
-            assert eng2.dups_b() == dups
-            da2 = eng2.upload(a)
-            eng2.run(da2)
-            assert np.array_equal(eng2.matrix(), m)
+        # the same set through the swept build (sorted keys into a cleared table) and WITHOUT the
+        # partition sort gives the same table contents
+        for flags in (64, 8):
+            with Engine(OverlapOptions(flags=flags, **kw), n_reps_a=a.n_reps) as eng2:
+                db2 = eng2.upload(b)
+                eng2.build_b(db2)
+                if flags == 8:
+                    assert eng2.stats()["kernel_launches"] < st["kernel_launches"]
+                assert eng2.dups_b() == dups
+                da2 = eng2.upload(a)
+                eng2.run(da2)
+                assert np.array_equal(eng2.matrix(), m)
+                assert eng2.stats()["matches"] == run["matches"]
+        # built twice in place (links reset, table buffers reused, never cleared): same answers
+        eng.build_b(db)
+        assert eng.dups_b() == dups
+        eng.clear_matrix()
+        eng.run(da)
+        assert np.array_equal(eng.matrix(), m)
     mo, _, io = orc.overlap(a, b, threads=8, **kw)
     assert np.array_equal(m, mo)
     assert run["matches"] == io["matches"] and run["probes"] == io["probes"]
     assert dups == orc.count_dups(b, ignore_genes=kw.get("ignore_genes", False))
+
+
+def test_tiled_build_occurrence_lists_dedup_and_pairs(partition_sized):
+    """The occurrence lists the tiled build links (shared-memory atomicExch per duplicate) carry
+    -z and the pair list: same leaders, counts and pairs as the direct build, spilled keys included
+    (a table at 94 % load spills a good part of every tile)."""
+    _, b = partition_sized
+    s = b.slice(0, 4_300_000)
+    s.rep = (s.rep % 3).astype(np.uint32)
+    s.n_reps = 3
+    got = {}
+    for flags in (0, 8):
+        lead, cnt, merged = dedup(s, OverlapOptions(flags=flags))
+        got[flags] = (lead, cnt, merged)
+    assert got[0][2] == got[8][2] > 0
+    assert np.array_equal(got[0][0], got[8][0]) and np.array_equal(got[0][1], got[8][1])
+    o_lead, o_cnt, o_merged = orc.dedup(s.slice(0, 300_000))
+    lead, cnt, merged = dedup(s.slice(0, 300_000), OverlapOptions())
+    assert merged == o_merged and np.array_equal(lead, o_lead) and np.array_equal(cnt, o_cnt)
+
+
+def test_tiled_build_crowded_table():
+    """1.5e7 keys in 2^24 slots (89 % load): probe runs are long and cross tile ends all the time,
+    so a good part of the keys takes the spill route; matrix, pairs and duplicate count against the
+    direct build and the oracle."""
+    pool = synth.make_pool(121, 400_000)
+    s = synth.make_set(124, 150, 100_000, pool=pool, indel_mutants=True, workers=4)
+    q = synth.make_set(125, 4, 5_000, pool=pool, indel_mutants=True)
+    res = {}
+    for flags in (0, 8):
+        m, p, info = overlap(q, s, OverlapOptions(differences=1, indels=True, want_pairs=True, table_load_pct=90,
+                                                  flags=flags))
+        assert info["build"]["table_slots"] == 1 << 24
+        res[flags] = (m, _pairs(p), info["run"]["matches"], info["dups_b"])
+    assert np.array_equal(res[0][0], res[8][0]) and res[0][1:] == res[8][1:]
+    mo, po, _ = orc.overlap(q, s, differences=1, indels=True, want_pairs=True, threads=8)
+    assert np.array_equal(res[0][0], mo) and res[0][1] == _pairs(po)
+    assert res[0][3] == orc.count_dups(s)
 
 
 def test_c4_shape_d2_ignore_genes_min(partition_sized):

@@ -2,24 +2,10 @@
 compared in one gpurun call.  usage: bigcase.py [d1|d2|both] [bpk]"""
 import sys, json, os
 sys.path.insert(0, ".")
-import numpy as np
-from compairr_b200 import Engine, OverlapOptions, synth
-from compairr_b200.seqset import SeqSet
-F = ("residues", "offsets", "v_gene", "j_gene", "rep", "count")
-def cached(name, make):
-    d = f"/dev/shm/cbig_{name}"
-    if os.path.isdir(d):
-        arr = {f: np.load(f"{d}/{f}.npy") for f in F}
-        return SeqSet(arr["residues"], arr["offsets"], arr["v_gene"], arr["j_gene"], arr["rep"], arr["count"], int(arr["rep"].max()) + 1)
-    s = make(); os.makedirs(d)
-    for f in F: np.save(f"{d}/{f}.npy", getattr(s, f))
-    return s
-pool = None
-def mk(seed, reps):
-    global pool
-    pool = pool or synth.make_pool(5, 4_000_000)
-    return synth.make_set(seed, reps, 100000, pool=pool, indel_mutants=True, workers=14)
-b = cached("b", lambda: mk(3, 1000)); a = cached("a", lambda: mk(2, 100))
+sys.path.insert(0, "tools")
+from compairr_b200 import Engine, OverlapOptions
+import bigcase_sets
+a, b = bigcase_sets.sets()
 which = sys.argv[1] if len(sys.argv) > 1 else "both"
 bpk = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0   # 0 = the engine's default
 for d, ind in [(1, True), (2, False)]:
