@@ -442,11 +442,11 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
   // a sorted (large) batch: the build kernels write the table only
   unsigned long long* bloom_in_build = filters_done ? nullptr : t.bloom;  // nullptr also for a table without filters
   if (tiled && part_hash && !bloom_in_build) {
-    // iota (the sort's input values) is dead: it holds the spill list
+    // the sort's inputs are dead: its keys hold the keys set aside tile by tile, its values the spill list
     cudaMemsetAsync(c->d_counters + CTR_SPILL, 0, sizeof(unsigned long long), c->stream);
     c->insert_launches += launch_build_tiled(s->d_meta, s->d_res, part_hash, part_idx, first, n, c->cfg.ignore_genes != 0,
-                                             t.table, (uint32_t)tbits, tile_first, iota, c->d_counters, c->sm_count,
-                                             c->stream) - 1;
+                                             t.table, (uint32_t)tbits, tile_first, reinterpret_cast<uint32_t*>(key_in), iota,
+                                             c->d_counters, c->sm_count, c->stream) - 1;
   } else {
     if (whole) {
       launch_table_clear(t.table, t.slots, c->stream);

@@ -258,13 +258,23 @@ void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const 
 }
 
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
 // K2, a whole set into an EMPTY table: the tiled build.  The keys arrive sorted by the tile
 // (BUILD_TILE_SLOTS consecutive slots) their home slot lies in.  One CTA builds one tile in shared
-// memory — the same insert as build_kernel, CAS and occurrence lists on shared-memory words — and
-// streams it out, empty slots included: the table is written once, front to back, and is neither
-// cleared beforehand nor read.  A key whose probe run leaves its tile goes to the spill list and is
-// inserted by build_kernel (sel) once every tile is in memory; the linear-probing invariant holds —
-// every slot from its home to the end of the tile was full when it left.
+// memory — the insert of build_kernel, CAS and occurrence lists on shared-memory words — and streams
+// it out, empty slots included: the table is written once, front to back, and is neither cleared
+// beforehand nor read.
+// In two passes.  A key that meets a slot with its own hash tag is, nearly always, another
+// occurrence of a sequence the tile already holds (a fifth of the keys of a repertoire collection)
+// and has to be compared residue by residue before it is linked into the slot's list: three
+// dependent DRAM round trips.  Done where it came up, a few lanes of every warp of every round
+// waited for them in turn and the rest of the CTA at its barrier (first version, ncu: 44 % long-
+// scoreboard + 26 % barrier stalls, 3.9 ms at 10^8 keys).  So pass 1 only claims empty slots and
+// sets those keys aside; pass 2 inserts them all at once, every lane with its own round trips in
+// flight.
+// A key whose probe run leaves the tile goes to the spill list and is inserted by build_kernel
+// (sel) once every tile is in memory; the linear-probing invariant holds — every slot from its
+// home to the end of the tile was full when it left, and stays full.
 // ---------------------------------------------------------------------------------------------
 
 __global__ void __launch_bounds__(256) tile_bounds_kernel(const uint64_t* __restrict__ key, uint64_t n, uint32_t shift,
@@ -281,23 +291,27 @@ __global__ void __launch_bounds__(256) tile_bounds_kernel(const uint64_t* __rest
   }
 }
 
-// Out of line: the tile kernel's probe loop then fits the registers of three 512-thread CTAs per SM.
-__device__ __noinline__ bool same_sequence(const SeqRec* meta, const uint8_t* __restrict__ res, uint64_t i, uint32_t j,
-                                           bool ignore_genes) {
-  const SeqMeta me = ld_meta_plain(meta + i), o = ld_meta_plain(meta + j);
-  return o.len == me.len && (ignore_genes || (o.v == me.v && o.j == me.j)) && seq_equal(res, me.off, o.off, me.len);
+// Append t to the spill list for the lanes with p set: one atomicAdd per warp.  Every lane of the warp calls.
+__device__ __forceinline__ void push_spill(bool p, uint32_t t, uint32_t* spill, unsigned long long* cursor) {
+  const unsigned m = __ballot_sync(FULL, p);
+  if (m == 0) return;
+  const unsigned lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  unsigned long long base = 0;
+  if (lane == leader) base = atomicAdd(cursor, (unsigned long long)__popc(m));
+  base = __shfl_sync(FULL, base, leader);
+  if (p) spill[base + __popc(m & ((1u << lane) - 1))] = t;
 }
 
 __global__ void __launch_bounds__(BUILD_TILE_THREADS, CB_TILE_CTAS)
 build_tile_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __restrict__ part_key,
                   const uint32_t* __restrict__ part_idx, const uint32_t* __restrict__ tile_first, uint64_t first,
-                  bool ignore_genes, Slot* table, uint32_t tbits, uint32_t ntiles, uint32_t* spill,
+                  bool ignore_genes, Slot* table, uint32_t tbits, uint32_t ntiles, uint32_t* defer, uint32_t* spill,
                   unsigned long long* counters) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
+  __shared__ uint32_t n_defer;
   Slot* tile = reinterpret_cast<Slot*>(smem_raw);
   const ulonglong2 empty = make_ulonglong2(0ull, SLOT_EMPTY);
-  // The key a thread inserts next and the bounds of the CTA's next tile are loaded one step ahead:
-  // three dependent DRAM round trips (bounds, key, the sequences of a duplicate) per step otherwise.
+  // The key a thread inserts next and the bounds of the CTA's next tile are loaded one step ahead.
   uint32_t g = blockIdx.x;
   uint32_t t0 = g < ntiles ? tile_first[g] : 0, t1 = g < ntiles ? tile_first[g + 1] : 0;
   for (; g < ntiles; g += gridDim.x) {
@@ -307,9 +321,13 @@ build_tile_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t*
     const uint32_t g_n = g + gridDim.x;
     const uint32_t t0_n = g_n < ntiles ? tile_first[g_n] : 0, t1_n = g_n < ntiles ? tile_first[g_n + 1] : 0;
     for (uint32_t k = threadIdx.x; k < BUILD_TILE_SLOTS; k += BUILD_TILE_THREADS) reinterpret_cast<ulonglong2*>(tile)[k] = empty;
+    if (threadIdx.x == 0) n_defer = 0;
     __syncthreads();
+
+    // Pass 1, every key of the tile: claim the first empty slot of its probe run.  A key that meets its own
+    // hash tag on the way is set aside (defer[t0 ...], the tile's own stretch of a scratch array).
     const uint32_t rounds = (t1 - t0 + BUILD_TILE_THREADS - 1) / BUILD_TILE_THREADS;
-    for (uint32_t r = 0; r < rounds; r++, t += BUILD_TILE_THREADS) {  // warp-uniform trip counts and a voted probe loop, as in build_kernel
+    for (uint32_t r = 0; r < rounds; r++, t += BUILD_TILE_THREADS) {  // warp-uniform trip counts, voted probe loops
       bool walking = t < t1;
       const uint64_t key = key_n;
       const uint64_t i = first + idx_n;
@@ -322,28 +340,65 @@ build_tile_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t*
       const unsigned long long tagged = ((unsigned long long)tag << 32) | i;
       uint32_t slot = (uint32_t)(key >> (64 - tbits)) & (BUILD_TILE_SLOTS - 1);
       while (__any_sync(FULL, walking)) {
+        const bool off = walking && slot >= BUILD_TILE_SLOTS;  // ran off the tile
+        push_spill(off, t, spill, counters + CTR_SPILL);
+        if (off) walking = false;
         if (walking) {
-          if (slot >= BUILD_TILE_SLOTS) {  // ran off the tile
-            spill[atomicAdd(counters + CTR_SPILL, 1ull)] = t;
-            walking = false;
-          } else {
-            unsigned long long* idxp = reinterpret_cast<unsigned long long*>(&tile[slot].idx);
-            unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(idxp);
+          unsigned long long* idxp = reinterpret_cast<unsigned long long*>(&tile[slot].idx);
+          unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(idxp);
+          if (cur == SLOT_EMPTY) {
+            cur = atomicCAS(idxp, SLOT_EMPTY, tagged);
             if (cur == SLOT_EMPTY) {
-              cur = atomicCAS(idxp, SLOT_EMPTY, tagged);
-              if (cur == SLOT_EMPTY) {
-                tile[slot].hash = h;
-                walking = false;
-              }
+              tile[slot].hash = h;
+              walking = false;
             }
-            if (walking && (uint32_t)(cur >> 32) == tag &&  // same hash tag: compare the sequences
-                same_sequence(meta, res, i, (uint32_t)cur, ignore_genes)) {
+          }
+          if (walking && (uint32_t)(cur >> 32) == tag) {
+            defer[t0 + atomicAdd(&n_defer, 1u)] = t;
+            walking = false;
+          }
+          slot++;
+        }
+      }
+    }
+    __syncthreads();
+
+    // Pass 2, the keys set aside, all at once: the full insert of build_kernel on the shared-memory tile.
+    const uint32_t nd = n_defer;
+    for (uint32_t k = threadIdx.x; k < (nd + BUILD_TILE_THREADS - 1) / BUILD_TILE_THREADS * BUILD_TILE_THREADS;
+         k += BUILD_TILE_THREADS) {
+      bool walking = k < nd;
+      const uint32_t td = walking ? defer[t0 + k] : 0;
+      const uint64_t key = walking ? part_key[td] : 0;
+      const uint64_t i = walking ? first + part_idx[td] : 0;
+      const uint64_t h = key * CB_HOME_INV;
+      const uint32_t tag = slot_tag(h);
+      const unsigned long long tagged = ((unsigned long long)tag << 32) | i;
+      uint32_t slot = (uint32_t)(key >> (64 - tbits)) & (BUILD_TILE_SLOTS - 1);
+      while (__any_sync(FULL, walking)) {
+        const bool off = walking && slot >= BUILD_TILE_SLOTS;
+        push_spill(off, td, spill, counters + CTR_SPILL);
+        if (off) walking = false;
+        if (walking) {
+          unsigned long long* idxp = reinterpret_cast<unsigned long long*>(&tile[slot].idx);
+          unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(idxp);
+          if (cur == SLOT_EMPTY) {
+            cur = atomicCAS(idxp, SLOT_EMPTY, tagged);
+            if (cur == SLOT_EMPTY) {
+              tile[slot].hash = h;
+              walking = false;
+            }
+          }
+          if (walking && (uint32_t)(cur >> 32) == tag) {  // same hash tag: compare the sequences
+            const SeqMeta me = ld_meta_plain(meta + i), o = ld_meta_plain(meta + (uint32_t)cur);
+            if (o.len == me.len && (ignore_genes || (o.v == me.v && o.j == me.j)) &&
+                seq_equal(res, me.off, o.off, me.len)) {
               const unsigned long long old = atomicExch(idxp, tagged);
               meta[i].next = (uint32_t)old;
               walking = false;
             }
-            slot++;
           }
+          slot++;
         }
       }
     }
@@ -358,10 +413,10 @@ build_tile_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t*
 }
 
 // part_key sorted on its top (tbits - BUILD_TILE_BITS) bits at least.  tile_first: ntiles + 1 words,
-// spill: n words (both scratch).  counters[CTR_SPILL] must be zero on entry.
+// defer, spill: n words each (all scratch).  counters[CTR_SPILL] must be zero on entry.
 int launch_build_tiled(SeqRec* meta, const uint8_t* res, const uint64_t* part_key, const uint32_t* part_idx,
                        uint64_t first, uint64_t n, bool ignore_genes, Slot* table, uint32_t tbits, uint32_t* tile_first,
-                       uint32_t* spill, unsigned long long* counters, int sm_count, cudaStream_t st) {
+                       uint32_t* defer, uint32_t* spill, unsigned long long* counters, int sm_count, cudaStream_t st) {
   const uint32_t ntiles = 1u << (tbits - BUILD_TILE_BITS);
   static bool attr_set = false;
   const int smem = (int)(BUILD_TILE_SLOTS * sizeof(Slot));
@@ -372,9 +427,9 @@ int launch_build_tiled(SeqRec* meta, const uint8_t* res, const uint64_t* part_ke
   tile_bounds_kernel<<<(ntiles + 256) / 256, 256, 0, st>>>(part_key, n, 64 - (tbits - BUILD_TILE_BITS), ntiles, tile_first);
   const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sm_count * CB_TILE_CTAS);
   build_tile_kernel<<<grid, BUILD_TILE_THREADS, smem, st>>>(meta, res, part_key, part_idx, tile_first, first, ignore_genes,
-                                                           table, tbits, ntiles, spill, counters);
-  // the spilled keys (a fraction of a percent), by the direct insert
-  build_kernel<<<(unsigned)sm_count * 2, 256, 0, st>>>(meta, res, nullptr, part_key, part_idx, first, n, ignore_genes, table,
+                                                           table, tbits, ntiles, defer, spill, counters);
+  // the keys that left their tile (a fraction of a percent at the default load), by the direct insert
+  build_kernel<<<(unsigned)sm_count * 4, 256, 0, st>>>(meta, res, nullptr, part_key, part_idx, first, n, ignore_genes, table,
                                                        (1ull << tbits) - 1, nullptr, 0, spill, counters + CTR_SPILL);
   return 3;
 }
@@ -410,7 +465,8 @@ filter_kernel(const uint64_t* __restrict__ hash, uint64_t n, unsigned long long*
 int launch_filters(const uint64_t* hash, uint64_t n, unsigned long long* bloom, uint32_t bloom_blocks, int sm_count,
                    cudaStream_t st) {
   if (n == 0) return 0;
-  // word ranges of at most ~48 MiB: resident in L2 beside the streamed hashes
+  // word ranges of at most ~48 MiB: resident in L2 beside the streamed hashes (whole build at 10^8 keys with
+  // ranges of 24 / 48 / 64 / 96 / 200 MiB: 14.4 / 10.6 / 11.2 / 13.5 / 17.7 ms)
   // (COMPAIRR_B200_FILTER_PART_MIB: tuning knob for measurements)
   static const uint64_t part_mib = [] {
     const char* e = getenv("COMPAIRR_B200_FILTER_PART_MIB");
@@ -421,17 +477,16 @@ int launch_filters(const uint64_t* hash, uint64_t n, unsigned long long* bloom, 
   uint32_t parts = (uint32_t)((bytes + (part_mib << 20) - 1) / (part_mib << 20));
   if (parts < 1) parts = 1;
   if (parts > 16) parts = 16;
-  static const int unroll = [] {  // COMPAIRR_B200_FILTER_UNROLL=1: one key per thread per trip (measurements)
-    const char* e = getenv("COMPAIRR_B200_FILTER_UNROLL");
-    return e && atoi(e) == 1 ? 1 : 4;
-  }();
-  const uint64_t blocks = (n + 256 * unroll - 1) / (256 * unroll);
+  // four keys per thread per trip: 12.1 -> 11.2 ms for the whole build at 10^8 keys against one.  CTAs per SM: 8
+  // (5, 4, 3, 2 tried to leave room for the table build running beside the passes: 10.9, 10.9, 11.2, 11.8 ms
+  // against 10.6)
+  constexpr int U = 4;
+  const uint64_t blocks = (n + 256 * U - 1) / (256 * U);
   const unsigned grid = (unsigned)(blocks < (uint64_t)sm_count * 8 ? blocks : (uint64_t)sm_count * 8);
   for (uint32_t cls = 0; cls < CB_CLASSES; cls++)
     for (uint32_t k = 0; k < parts; k++) {
       const uint32_t lo = (uint32_t)((uint64_t)bloom_blocks * k / parts), hi = (uint32_t)((uint64_t)bloom_blocks * (k + 1) / parts);
-      if (unroll == 1) filter_kernel<1><<<grid, 256, 0, st>>>(hash, n, bloom, bloom_blocks, cls, lo, hi);
-      else filter_kernel<4><<<grid, 256, 0, st>>>(hash, n, bloom, bloom_blocks, cls, lo, hi);
+      filter_kernel<U><<<grid, 256, 0, st>>>(hash, n, bloom, bloom_blocks, cls, lo, hi);
     }
   return (int)(CB_CLASSES * parts);
 }

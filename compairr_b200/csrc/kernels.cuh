@@ -115,8 +115,8 @@ void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const 
                   uint64_t mask, unsigned long long* bloom, uint32_t bloom_blocks, cudaStream_t st);
 // A whole set into an EMPTY, UNCLEARED table of 2^tbits slots (tbits >= BUILD_TILE_BITS): one CTA per tile of
 // BUILD_TILE_SLOTS slots builds it in shared memory and streams it out.  part_key sorted on (at least) its top
-// tbits - BUILD_TILE_BITS bits; tile_first (2^(tbits - BUILD_TILE_BITS) + 1 words) and spill (n words) are
-// scratch; counters[CTR_SPILL] must be zero on entry.  Returns the launches made.
+// tbits - BUILD_TILE_BITS bits; tile_first (2^(tbits - BUILD_TILE_BITS) + 1 words), defer and spill (n words
+// each) are scratch; counters[CTR_SPILL] must be zero on entry.  Returns the launches made.
 constexpr int BUILD_TILE_BITS = 12;
 constexpr uint32_t BUILD_TILE_SLOTS = 1u << BUILD_TILE_BITS;  // 64 KiB of shared memory
 #ifndef CB_TILE_THREADS
@@ -128,7 +128,7 @@ constexpr uint32_t BUILD_TILE_SLOTS = 1u << BUILD_TILE_BITS;  // 64 KiB of share
 constexpr int BUILD_TILE_THREADS = CB_TILE_THREADS;
 int launch_build_tiled(SeqRec* meta, const uint8_t* res, const uint64_t* part_key, const uint32_t* part_idx,
                        uint64_t first, uint64_t n, bool ignore_genes, Slot* table, uint32_t tbits, uint32_t* tile_first,
-                       uint32_t* spill, unsigned long long* counters, int sm_count, cudaStream_t st);
+                       uint32_t* defer, uint32_t* spill, unsigned long long* counters, int sm_count, cudaStream_t st);
 // the four class filters of hashes [0, n), L2-sized word ranges at a time; returns the launches made
 int launch_filters(const uint64_t* hash, uint64_t n, unsigned long long* bloom, uint32_t bloom_blocks, int sm_count,
                    cudaStream_t st);
