@@ -203,6 +203,7 @@ extern "C" int cb_create(const cb_config* cfg, cb_ctx** out) {
   // cost ~110 B of DRAM traffic each: no change in any kernel's time on B200.)
   CU_CREATE(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
   CU_CREATE(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+  CU_CREATE(cudaStreamCreateWithFlags(&c->side_stream, cudaStreamNonBlocking));
   c->stream = c->own_stream;
   g_alloc_stream = c->stream;
   g_alloc_pool = c->pool;
@@ -254,6 +255,7 @@ extern "C" void cb_destroy(cb_ctx* c) {
   g_alloc_pool = nullptr;
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->side_stream) cudaStreamDestroy(c->side_stream);
   delete c;
 }
 
@@ -416,8 +418,8 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
       }();
       cudaStream_t fs = c->stream;
       if (beside && cudaEventRecord(c->ev[8], c->stream) == cudaSuccess &&
-          cudaStreamWaitEvent(c->copy_stream, c->ev[8], 0) == cudaSuccess)
-        fs = c->copy_stream;
+          cudaStreamWaitEvent(c->side_stream, c->ev[8], 0) == cudaSuccess)
+        fs = c->side_stream;  // (not the copy stream: the upload pipeline's next chunk is on its way there)
       c->insert_launches += launch_filters(s->d_hash + first, n, t.bloom, t.blocks, c->sm_count, fs);
       if (fs != c->stream) {
         cudaEventRecord(c->ev[9], fs);

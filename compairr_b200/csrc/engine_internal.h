@@ -57,6 +57,7 @@ struct cb_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // H2D side of the pipelined upload
+  cudaStream_t side_stream = nullptr;  // filter passes of a sorted table insert, beside sort and table build
   cudaMemPool_t pool = nullptr;        // the context's own stream-ordered memory pool
   void* pin[2] = {nullptr, nullptr};   // pinned pass-through buffers of the upload pipeline (pageable callers)
   size_t pin_bytes[2] = {0, 0};
