@@ -355,6 +355,9 @@ build_tile_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t*
           }
           if (walking && (uint32_t)(cur >> 32) == tag) {
             defer[t0 + atomicAdd(&n_defer, 1u)] = t;
+            // pass 2 will compare the two sequences: start their records on the way to L2 now
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(meta + i));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(meta + (uint32_t)cur));
             walking = false;
           }
           slot++;

@@ -119,11 +119,13 @@ void launch_build(SeqRec* meta, const uint8_t* res, const uint64_t* hash, const 
 // each) are scratch; counters[CTR_SPILL] must be zero on entry.  Returns the launches made.
 constexpr int BUILD_TILE_BITS = 12;
 constexpr uint32_t BUILD_TILE_SLOTS = 1u << BUILD_TILE_BITS;  // 64 KiB of shared memory
+// CTA shape of the tile kernel (whole build at 10^8 keys: 256x3 11.9, 512x2 10.43, 384x3 10.28, 512x3 with spills
+// 11.3, 1024x1 12.8 ms): three 64-KiB tiles per SM in flight
 #ifndef CB_TILE_THREADS
-#define CB_TILE_THREADS 512
+#define CB_TILE_THREADS 384
 #endif
 #ifndef CB_TILE_CTAS
-#define CB_TILE_CTAS 2  // per SM
+#define CB_TILE_CTAS 3  // per SM
 #endif
 constexpr int BUILD_TILE_THREADS = CB_TILE_THREADS;
 int launch_build_tiled(SeqRec* meta, const uint8_t* res, const uint64_t* part_key, const uint32_t* part_idx,
