@@ -421,12 +421,9 @@ int launch_build_tiled(SeqRec* meta, const uint8_t* res, const uint64_t* part_ke
                        uint64_t first, uint64_t n, bool ignore_genes, Slot* table, uint32_t tbits, uint32_t* tile_first,
                        uint32_t* defer, uint32_t* spill, unsigned long long* counters, int sm_count, cudaStream_t st) {
   const uint32_t ntiles = 1u << (tbits - BUILD_TILE_BITS);
-  static bool attr_set = false;
   const int smem = (int)(BUILD_TILE_SLOTS * sizeof(Slot));
-  if (!attr_set) {
-    cudaFuncSetAttribute(build_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-    attr_set = true;
-  }
+  // on every launch: the attribute is per device, and one process may drive several (CLI --gpus N)
+  cudaFuncSetAttribute(build_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   tile_bounds_kernel<<<(ntiles + 256) / 256, 256, 0, st>>>(part_key, n, 64 - (tbits - BUILD_TILE_BITS), ntiles, tile_first);
   const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sm_count * CB_TILE_CTAS);
   build_tile_kernel<<<grid, BUILD_TILE_THREADS, smem, st>>>(meta, res, part_key, part_idx, tile_first, first, ignore_genes,

@@ -97,6 +97,20 @@ def test_two_gpus_matrix_and_pairs_vs_oracle(sets, kw):
 
 
 @need2
+def test_two_gpus_tiled_build_in_one_process():
+    """Set B large enough for the tiled build (4.4e6 keys, 2^24 slots), both contexts in ONE process: the
+    tile kernel's 64 KiB of dynamic shared memory has to be granted on every device."""
+    pool = synth.make_pool(121, 400_000)
+    b = synth.make_set(122, 44, 100_000, pool=pool, indel_mutants=True, workers=4)
+    a = synth.make_set(123, 8, 10_000, pool=pool, indel_mutants=True)
+    kw = dict(differences=1, indels=True)
+    ms, _, dups = _run_world(a, b, 2, kw)
+    mo, _, _ = orc.overlap(a, b, threads=8, **kw)
+    assert np.array_equal(ms[0], mo) and np.array_equal(ms[1], mo)
+    assert dups[0] == dups[1] == orc.count_dups(b)
+
+
+@need2
 def test_two_gpus_existence_rows(sets):
     a, b = sets
     q = a.slice(0, 5000)
