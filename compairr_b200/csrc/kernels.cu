@@ -4,6 +4,8 @@
 //   hash_kernel        K1  batched Zobrist hashing                    (replaces zobrist.cc:74-88, db.cc:903-916)
 //   build_kernel       K2  open-addressing insert (+ filter bits)     (replaces overlap.cc:63-128 insert part,
 //                                                                      hashtable.h:48-77, bloompat.h:50-53)
+//   build_tile_kernel  K2  the same insert for a whole set into an empty table: tiles of 4096 slots built in
+//                          shared memory from keys sorted by tile, the table written once (+ tile_bounds_kernel)
 //   dups_kernel        K2b exact-duplicate count                      (replaces overlap.cc:63-128 dup part, :579-605)
 //   filter_kernel      K2  the four class filters of a large set, L2-sized word ranges at a time
 //   identical_kernel   K3/K4 for d = 0: one thread per seed           (replaces overlap.cc:253-284 with variants.cc:260-268)
