@@ -109,11 +109,26 @@ hash_kernel(const SeqRec* __restrict__ meta, const uint8_t* __restrict__ res, ui
        i += (uint64_t)gridDim.x * blockDim.x) {
     const SeqMeta m = ld_meta(meta + i);
     uint64_t h = ignore_genes ? 0ull : vj_hash(seed, m.v, m.j);
-    const uint8_t* s = res + m.off;
     const uint32_t len = m.len <= zrows ? m.len : 0;  // longer than the table: rehashed later
-    for (uint32_t p = 0; p < len; p++) {
-      const uint32_t r = __ldg(s + p);
-      h ^= ZSMEM ? zs[p * sigma + r] : __ldg(ztab + p * sigma + r);
+    // The residues as aligned 64-bit words, one load ahead (a byte load per residue kept L1 at 84 %
+    // of its peak and DRAM at 39 %).  Only words that hold a residue of this sequence are read.
+    const uint64_t* w = reinterpret_cast<const uint64_t*>(res + (m.off & ~7ull));
+    const uint32_t sh = (uint32_t)(m.off & 7);
+    const uint32_t nw = len ? (sh + len + 7) >> 3 : 0;
+    uint64_t cur = nw ? __ldg(w) : 0ull;
+    uint32_t p = 0;
+    for (uint32_t k = 0; k < nw; k++) {
+      const uint64_t nxt = k + 1 < nw ? __ldg(w + k + 1) : 0ull;
+      const uint32_t b0 = k == 0 ? sh : 0u;
+      const uint32_t left = sh + len - 8 * k;  // bytes of the sequence from the start of this word on
+      const uint32_t b1 = left < 8 ? left : 8u;
+      uint64_t x = cur >> (8 * b0);
+      for (uint32_t b = b0; b < b1; b++, p++) {
+        const uint32_t r = (uint32_t)x & 0xffu;
+        x >>= 8;
+        h ^= ZSMEM ? zs[p * sigma + r] : __ldg(ztab + p * sigma + r);
+      }
+      cur = nxt;
     }
     out[i] = h;
   }
@@ -240,8 +255,9 @@ build_kernel(SeqRec* meta, const uint8_t* __restrict__ res, const uint64_t* __re
 // Before a set is inserted a second time its occurrence links are reset — one streaming pass
 // instead of a random store per slot owner inside the build kernel.
 __global__ void __launch_bounds__(256) reset_next_kernel(SeqRec* meta, uint64_t n) {
+  // only the records that carry a link are written: the rest of the pass is a read
   for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
-    meta[i].next = SEQ_NIL;
+    if (meta[i].next != SEQ_NIL) meta[i].next = SEQ_NIL;
 }
 
 void launch_reset_next(SeqRec* meta, uint64_t n, cudaStream_t st) {
