@@ -171,6 +171,42 @@ def test_tiled_build_occurrence_lists_dedup_and_pairs(partition_sized):
     assert merged == o_merged and np.array_equal(lead, o_lead) and np.array_equal(cnt, o_cnt)
 
 
+def _with_hub(b, k, src, at=0):
+    """b plus k copies of sequence `at` of src (its V and J too), spread over the repertoires."""
+    lo, hi = int(src.offsets[at]), int(src.offsets[at + 1])
+    lens = np.concatenate([b.lengths, np.full(k, hi - lo, dtype=b.lengths.dtype)])
+    off = np.zeros(lens.size + 1, dtype=np.uint64)
+    np.cumsum(lens, out=off[1:])
+    return SeqSet(np.concatenate([b.residues, np.tile(src.residues[lo:hi], k)]), off,
+                  np.concatenate([b.v_gene, np.full(k, src.v_gene[at], np.uint32)]),
+                  np.concatenate([b.j_gene, np.full(k, src.j_gene[at], np.uint32)]),
+                  np.concatenate([b.rep, (np.arange(k) % b.n_reps).astype(np.uint32)]),
+                  np.concatenate([b.count, np.ones(k, np.uint64)]), b.n_reps)
+
+
+def test_tiled_build_hub_sequence(partition_sized):
+    """One sequence present many thousand times: all its copies meet in one slot of one tile (the tile
+    kernel sets them aside and links them in its second pass, one atomicExch each on the same word) and
+    every matching seed walks the whole list."""
+    a, b = partition_sized
+    kw = dict(differences=1, indels=True)
+    q = a.slice(0, 20_000)
+    s = _with_hub(b, 20_000, q)
+    m, _, info = overlap(q, s, OverlapOptions(**kw))
+    assert info["build"]["table_slots"] * 16 >= 256 << 20
+    mo, _, io = orc.overlap(q, s, threads=8, **kw)
+    assert np.array_equal(m, mo) and info["run"]["matches"] == io["matches"] > 20_000
+    assert info["dups_b"] == orc.count_dups(s) > 19_000
+    # a hub too large for the serial oracle (its insert is quadratic in the copies): tiled against direct build
+    s = _with_hub(b, 200_000, q)
+    res = []
+    for flags in (0, 8):
+        m, _, info = overlap(q, s, OverlapOptions(flags=flags, **kw))
+        res.append((m, info["run"]["matches"], info["dups_b"]))
+    assert np.array_equal(res[0][0], res[1][0]) and res[0][1:] == res[1][1:]
+    assert res[0][2] > 199_000
+
+
 def test_tiled_build_crowded_table():
     """1.5e7 keys in 2^24 slots (89 % load): probe runs are long and cross tile ends all the time,
     so a good part of the keys takes the spill route; matrix, pairs and duplicate count against the
