@@ -376,7 +376,7 @@ int cb_table_alloc(cb_ctx* c, uint64_t n, bool with_bloom, BuiltTable* out, bool
 // Does a set of n keys in a table of `slots` slots take the sorted (partitioned) build?
 static bool sorted_build(const cb_ctx* c, uint64_t slots, uint64_t n) {
   return !(c->cfg.flags & CB_FLAG_NO_PARTITION) && slots * sizeof(Slot) >= (256ull << 20) && n >= (1ull << 22) &&
-         n * 64 >= slots && n < 0xffffffffull;
+         n * 64 >= slots && n < 0xffffffffull - 4096;  // 32-bit sorted positions, a CTA's stride of headroom
 }
 bool cb_tiled_build(const cb_ctx* c, uint64_t slots, uint64_t n) {
   return sorted_build(c, slots, n) && !(c->cfg.flags & CB_FLAG_NO_TILED_BUILD);
