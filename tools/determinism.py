@@ -1,3 +1,5 @@
+"""Run-to-run determinism: the same 2e6 x 3e6 overlap three times with and without the filters (flag 2), each against
+the oracle (the build races for slots, the results must not depend on who wins)."""
 import sys, json
 sys.path.insert(0, ".")
 import numpy as np
