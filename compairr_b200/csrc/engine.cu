@@ -395,7 +395,7 @@ void cb_table_insert(cb_ctx* c, const BuiltTable& t, cb_dset* s, uint64_t first,
   bool filters_done = false, filters_forked = false;
   int tbits = 0;
   while ((1ull << tbits) < t.slots) tbits++;
-  const bool tiled = whole && cb_tiled_build(c, t.slots, n);
+  const bool tiled = whole && cb_tiled_build(c, t.slots, n) && !(t.bloom && (c->cfg.flags & CB_FLAG_FILTERS_IN_BUILD));
   if (sorted_build(c, t.slots, n)) {
     // tiled: down to tiles of BUILD_TILE_SLOTS; swept: down to segments of 16 slots, whole radix passes
     const int pbits = tiled ? tbits - BUILD_TILE_BITS : std::max(8, (tbits - 4) / 8 * 8);
